@@ -1,0 +1,250 @@
+// tubedetr_b200 -- multi-head attention core for TubeDETR's three attention sites (head_dim = 32):
+//   encoder spatial multi-modal self-attention  (reference models/transformer.py:637-640; S = HW + L <= 256 keys)
+//   decoder temporal self-attention (TSA)       (models/transformer.py:698-722;  T <= 200 keys, head-mean P returned WITH grad)
+//   decoder time-aligned cross-attention        (models/transformer.py:724-745;  1 query per frame, S keys)
+// Math restated from torch F.multi_head_attention_forward (need_weights path): S = (q*hd^-1/2) k^T + (-inf on padded keys),
+// P = softmax(S), O = P V, Pbar = mean_h P.  One CTA per (batch, head): K^T and V of that head live in shared memory
+// (fp32, <= 64 KB), one warp per query row, probabilities written once (needed by backward and by the guided-attention loss).
+// Round-1 implementation on CUDA cores in fp32 (the attention core is <1% of the step FLOPs); the projections around it
+// run on tcgen05 through tdb_gemm.  DESIGN.md lists the tcgen05 fused KV-projection variant as the next step.
+#include "../../include/tubedetr_b200.h"
+#include "tdb_common.cuh"
+
+void tdb_count_launch(int n);
+
+namespace tdb {
+
+constexpr int HD = 32;
+constexpr int kAttnThreads = 256;
+
+// q/k/v: bf16 with row stride ld* (elements) and batch stride = L*ld*; head h occupies columns [h*32, h*32+32)
+struct AttnParams {
+  const bf16 *q, *k, *v;
+  long long ldq, ldk, ldv;
+  const uint8_t* kpm;  // [B][Lk] nonzero = masked key, may be null
+  bf16* o;             // [B][Lq][H*32]
+  long long ldo;
+  float* p;            // [B][H][Lq][Lk]
+  int B, H, Lq, Lk;
+  float scale;
+};
+
+__global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams a) {
+  extern __shared__ float sm[];
+  const int Lkp = a.Lk | 1;                 // odd pitch: conflict-free transposed K
+  float* kt = sm;                           // [32][Lkp]
+  float* vs = kt + HD * Lkp;                // [Lk][32]
+  float* prow = vs + a.Lk * HD;             // [warps][Lk]
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const bf16* kb = a.k + (long long)b * a.Lk * a.ldk + h * HD;
+  const bf16* vb = a.v + (long long)b * a.Lk * a.ldv + h * HD;
+  for (int i = threadIdx.x; i < a.Lk * HD; i += blockDim.x) {
+    int j = i >> 5, d = i & 31;
+    kt[d * Lkp + j] = __bfloat162float(kb[(long long)j * a.ldk + d]);
+    vs[j * HD + d] = __bfloat162float(vb[(long long)j * a.ldv + d]);
+  }
+  __syncthreads();
+  const uint8_t* mk = a.kpm ? a.kpm + (long long)b * a.Lk : nullptr;
+  float* pw = prow + warp * a.Lk;
+  for (int i = blockIdx.y * nwarps + warp; i < a.Lq; i += gridDim.y * nwarps) {
+    const bf16* qr = a.q + ((long long)b * a.Lq + i) * a.ldq + h * HD;
+    float qd = __bfloat162float(qr[lane]) * a.scale;
+    float mx = -INFINITY;
+    for (int j0 = 0; j0 < a.Lk; j0 += 32) {
+      int j = j0 + lane;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        float qv = __shfl_sync(0xffffffffu, qd, d);
+        if (j < a.Lk) s += qv * kt[d * Lkp + j];
+      }
+      if (j < a.Lk) {
+        if (mk && mk[j]) s = -INFINITY;
+        pw[j] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < a.Lk; j += 32) {
+      float e = (mx == -INFINITY) ? 0.f : __expf(pw[j] - mx);
+      pw[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    float inv = 1.f / sum;  // all keys masked -> NaN, exactly like the reference softmax
+    __syncwarp();
+    float* pg = a.p + (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    float acc = 0.f;
+    for (int j = 0; j < a.Lk; ++j) acc += pw[j] * vs[j * HD + lane];
+    for (int j = lane; j < a.Lk; j += 32) pg[j] = pw[j] * inv;
+    a.o[((long long)b * a.Lq + i) * a.ldo + h * HD + lane] = __float2bfloat16(acc * inv);
+    __syncwarp();
+  }
+}
+
+// Pbar[b][i][j] = mean_h P[b][h][i][j]
+__global__ void head_mean_kernel(const float* __restrict__ p, float* __restrict__ pbar, int B, int H, long long LL) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * LL) return;
+  long long b = idx / LL, r = idx - b * LL;
+  float s = 0.f;
+  for (int h = 0; h < H; ++h) s += p[(b * H + h) * LL + r];
+  pbar[idx] = s / H;
+}
+
+struct AttnBwdParams {
+  const bf16 *q, *k, *v, *dout;
+  long long ldq, ldk, ldv, lddo;
+  const float* p;      // [B][H][Lq][Lk]
+  const float* dpbar;  // [B][Lq][Lk] gradient of the head-mean probabilities, may be null
+  float* ds;           // [B][H][Lq][Lk] scratch: dS = P o (dP - rowsum(P o dP))
+  bf16 *dq, *dk, *dv;  // same layout as q/k/v (strides lddq..)
+  long long lddq, lddk, lddv;
+  int B, H, Lq, Lk;
+  float scale;
+};
+
+// row pass: one warp per query row: dP = dO V^T (+ dPbar/H), dS, dQ = scale * dS K
+__global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwdParams a) {
+  extern __shared__ float sm[];
+  const int Lkp = a.Lk | 1;
+  float* vt = sm;                    // [32][Lkp]   V transposed
+  float* ks = vt + HD * Lkp;         // [Lk][32]
+  float* drow = ks + a.Lk * HD;      // [warps][Lk]
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const bf16* kb = a.k + (long long)b * a.Lk * a.ldk + h * HD;
+  const bf16* vb = a.v + (long long)b * a.Lk * a.ldv + h * HD;
+  for (int i = threadIdx.x; i < a.Lk * HD; i += blockDim.x) {
+    int j = i >> 5, d = i & 31;
+    vt[d * Lkp + j] = __bfloat162float(vb[(long long)j * a.ldv + d]);
+    ks[j * HD + d] = __bfloat162float(kb[(long long)j * a.ldk + d]);
+  }
+  __syncthreads();
+  float* dw = drow + warp * a.Lk;
+  const float invH = 1.f / a.H;
+  for (int i = blockIdx.y * nwarps + warp; i < a.Lq; i += gridDim.y * nwarps) {
+    float dod = __bfloat162float(a.dout[((long long)b * a.Lq + i) * a.lddo + h * HD + lane]);
+    const float* pr = a.p + (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    const float* dpb = a.dpbar ? a.dpbar + ((long long)b * a.Lq + i) * a.Lk : nullptr;
+    float rs = 0.f;
+    for (int j0 = 0; j0 < a.Lk; j0 += 32) {
+      int j = j0 + lane;
+      float dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        float dv = __shfl_sync(0xffffffffu, dod, d);
+        if (j < a.Lk) dp += dv * vt[d * Lkp + j];
+      }
+      if (j < a.Lk) {
+        if (dpb) dp += dpb[j] * invH;
+        float pj = pr[j];
+        dw[j] = dp;
+        rs += pj * dp;
+      }
+    }
+    rs = warp_sum(rs);
+    float* dsg = a.ds + (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    for (int j = lane; j < a.Lk; j += 32) {
+      float pj = pr[j];
+      float d = pj > 0.f ? pj * (dw[j] - rs) : 0.f;  // masked keys have P = 0 exactly
+      dw[j] = d;
+      dsg[j] = d;
+    }
+    __syncwarp();
+    float acc = 0.f;
+    for (int j = 0; j < a.Lk; ++j) acc += dw[j] * ks[j * HD + lane];
+    a.dq[((long long)b * a.Lq + i) * a.lddq + h * HD + lane] = __float2bfloat16(acc * a.scale);
+    __syncwarp();
+  }
+}
+
+// column pass: one warp per key j: dV[j] = sum_i P[i][j] dO[i];  dK[j] = scale * sum_i dS[i][j] Q[i]
+__global__ void __launch_bounds__(kAttnThreads) mha_bwd_col_kernel(const AttnBwdParams a) {
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float* pb = a.p + ((long long)b * a.H + h) * a.Lq * a.Lk;
+  const float* dsb = a.ds + ((long long)b * a.H + h) * a.Lq * a.Lk;
+  for (int j = blockIdx.y * nwarps + warp; j < a.Lk; j += gridDim.y * nwarps) {
+    float av = 0.f, ak = 0.f;
+    for (int i = 0; i < a.Lq; ++i) {
+      float pij = __ldg(pb + (long long)i * a.Lk + j);
+      float dsij = __ldg(dsb + (long long)i * a.Lk + j);
+      float dod = __bfloat162float(a.dout[((long long)b * a.Lq + i) * a.lddo + h * HD + lane]);
+      float qd = __bfloat162float(a.q[((long long)b * a.Lq + i) * a.ldq + h * HD + lane]);
+      av += pij * dod;
+      ak += dsij * qd;
+    }
+    a.dv[((long long)b * a.Lk + j) * a.lddv + h * HD + lane] = __float2bfloat16(av);
+    a.dk[((long long)b * a.Lk + j) * a.lddk + h * HD + lane] = __float2bfloat16(ak * a.scale);
+  }
+}
+
+}  // namespace tdb
+
+using namespace tdb;
+
+static size_t attn_smem_bytes(int Lk, int threads) {
+  int Lkp = Lk | 1;
+  return sizeof(float) * ((size_t)HD * Lkp + (size_t)Lk * HD + (size_t)(threads / 32) * Lk);
+}
+static int attn_grid_y(int BH, int Lq) {
+  int per = (Lq + (kAttnThreads / 32) - 1) / (kAttnThreads / 32);
+  int want = (2 * 148 + BH - 1) / BH;
+  if (want < 1) want = 1;
+  return want < per ? want : per;
+}
+
+static int attn_init() {
+  static bool attr = false;
+  if (!attr) {
+    TDB_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TDB_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  return TDB_OK;
+}
+
+extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                           const uint8_t* kpm, void* o, int64_t ldo, float* p, float* pbar, int B, int H, int Lq, int Lk,
+                           float scale, void* stream_) {
+  TDB_REQUIRE(q && k && v && o && p && B > 0 && H > 0 && Lq > 0 && Lk > 0, "tdb_mha_fwd: bad args");
+  size_t smem = attn_smem_bytes(Lk, kAttnThreads);
+  TDB_REQUIRE(smem <= 200 * 1024, "tdb_mha_fwd: Lk=%d too long for the single-CTA kernel", Lk);
+  int rc = attn_init();
+  if (rc) return rc;
+  AttnParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, kpm, (bf16*)o, ldo, p, B, H, Lq, Lk, scale};
+  dim3 grid(B * H, attn_grid_y(B * H, Lq));
+  mha_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream_>>>(a);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(1);
+  if (pbar) {
+    long long LL = (long long)Lq * Lk;
+    head_mean_kernel<<<(unsigned)(((long long)B * LL + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(p, pbar, B, H, LL);
+    TDB_CHECK_CUDA(cudaGetLastError());
+    tdb_count_launch(1);
+  }
+  return TDB_OK;
+}
+
+extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                           const void* dout, int64_t lddo, const float* p, const float* dpbar, float* ds_scratch, void* dq,
+                           int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk,
+                           float scale, void* stream_) {
+  TDB_REQUIRE(q && k && v && dout && p && ds_scratch && dq && dk && dv, "tdb_mha_bwd: null pointer");
+  size_t smem = attn_smem_bytes(Lk, kAttnThreads);
+  TDB_REQUIRE(smem <= 200 * 1024, "tdb_mha_bwd: Lk=%d too long", Lk);
+  int rc = attn_init();
+  if (rc) return rc;
+  AttnBwdParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)dout, ldq, ldk, ldv, lddo, p, dpbar,
+                  ds_scratch, (bf16*)dq, (bf16*)dk, (bf16*)dv, lddq, lddk, lddv, B, H, Lq, Lk, scale};
+  dim3 g1(B * H, attn_grid_y(B * H, Lq));
+  mha_bwd_row_kernel<<<g1, kAttnThreads, smem, (cudaStream_t)stream_>>>(a);
+  dim3 g2(B * H, attn_grid_y(B * H, Lk));
+  mha_bwd_col_kernel<<<g2, kAttnThreads, 0, (cudaStream_t)stream_>>>(a);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(2);
+  return TDB_OK;
+}

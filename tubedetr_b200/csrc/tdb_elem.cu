@@ -1,0 +1,427 @@
+// tubedetr_b200 -- HBM-bound helper kernels around the GEMM: layout transforms for the ResNet stem / stride-2 convs,
+// weight preparation, LayerNorm (+residual) forward/backward, column sums.  All coalesced, 16-byte vectorised where the
+// layout allows; grid sized from the element count.  Reference call sites: SURVEY.md section 2.2 K1, K3 (stride-2), K4, K9, K14.
+#include "../../include/tubedetr_b200.h"
+#include "tdb_common.cuh"
+
+void tdb_count_launch(int n);
+
+namespace tdb {
+
+static inline unsigned nblocks(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------ stem: fp32 NCHW frames -> bf16 im2col rows [N*Ho*Wo][192]
+// column = c*49 + kh*7 + kw (torch weight flatten order), zero padded 147 -> 192; conv 7x7 / stride 2 / pad 3
+__global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int Ho, int Wo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, group of 8 columns)
+  long long total = (long long)N * Ho * Wo * 24;
+  if (idx >= total) return;
+  int g = (int)(idx % 24);
+  long long row = idx / 24;
+  int wo = (int)(row % Wo);
+  long long t = row / Wo;
+  int ho = (int)(t % Ho);
+  int n = (int)(t / Ho);
+  uint32_t packed[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int cidx = g * 8 + i * 2 + j;
+      float val = 0.f;
+      if (cidx < 147) {
+        int c = cidx / 49;
+        int r = cidx - c * 49;
+        int kh = r / 7, kw = r - kh * 7;
+        int hi = ho * 2 - 3 + kh, wi = wo * 2 - 3 + kw;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = __ldg(x + (((long long)n * 3 + c) * H + hi) * W + wi);
+      }
+      v[j] = val;
+    }
+    packed[i] = pack_bf16x2(v[0], v[1]);
+  }
+  *reinterpret_cast<uint4*>(col + row * 192 + g * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+// ------------------------------------------------------------------ 3x3 / stride 2 / pad 1 max pool, NHWC bf16, 8 channels per thread
+__global__ void maxpool3x3s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cg = C / 8;
+  long long total = (long long)N * Ho * Wo * cg;
+  if (idx >= total) return;
+  int c8 = (int)(idx % cg);
+  long long t = idx / cg;
+  int wo = (int)(t % Wo);
+  t /= Wo;
+  int ho = (int)(t % Ho);
+  int n = (int)(t / Ho);
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+  for (int kh = 0; kh < 3; ++kh) {
+    int hi = ho * 2 - 1 + kh;
+    if (hi < 0 || hi >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      int wi = wo * 2 - 1 + kw;
+      if (wi < 0 || wi >= W) continue;
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + hi) * W + wi) * C + c8 * 8));
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
+      m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], d.x); m[7] = fmaxf(m[7], d.y);
+    }
+  }
+  *reinterpret_cast<uint4*>(y + (((long long)n * Ho + ho) * Wo + wo) * C + c8 * 8) =
+      make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+}
+
+// ------------------------------------------------------------------ 3x3 / stride 2 / pad 1 im2col, NHWC bf16 -> [N*Ho*Wo][9*C] (tap major)
+__global__ void im2col3x3s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C, int Ho, int Wo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cg = C / 8;
+  long long total = (long long)N * Ho * Wo * 9 * cg;
+  if (idx >= total) return;
+  int c8 = (int)(idx % cg);
+  long long t = idx / cg;
+  int tap = (int)(t % 9);
+  long long row = t / 9;
+  int wo = (int)(row % Wo);
+  long long t2 = row / Wo;
+  int ho = (int)(t2 % Ho);
+  int n = (int)(t2 / Ho);
+  int kh = tap / 3, kw = tap - kh * 3;
+  int hi = ho * 2 - 1 + kh, wi = wo * 2 - 1 + kw;
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+    u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + hi) * W + wi) * C + c8 * 8));
+  *reinterpret_cast<uint4*>(col + row * (9ll * C) + tap * C + c8 * 8) = u;
+}
+
+// transpose of the above as a gather (deterministic): dx[n,h,w,:] = sum over (ho,wo,tap) hitting (h,w); then ReLU mask by y>0
+__global__ void col2im3x3s2_mask_kernel(const bf16* __restrict__ dcol, const bf16* __restrict__ ymask, bf16* __restrict__ dx,
+                                        int N, int H, int W, int C, int Ho, int Wo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cg = C / 8;
+  long long total = (long long)N * H * W * cg;
+  if (idx >= total) return;
+  int c8 = (int)(idx % cg);
+  long long pix = idx / cg;
+  int w = (int)(pix % W);
+  long long t = pix / W;
+  int h = (int)(t % H);
+  int n = (int)(t / H);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    int hh = h + 1 - kh;  // = 2*ho
+    if (hh < 0 || (hh & 1)) continue;
+    int ho = hh >> 1;
+    if (ho >= Ho) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      int ww = w + 1 - kw;
+      if (ww < 0 || (ww & 1)) continue;
+      int wo = ww >> 1;
+      if (wo >= Wo) continue;
+      long long row = ((long long)n * Ho + ho) * Wo + wo;
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(dcol + row * (9ll * C) + (kh * 3 + kw) * C + c8 * 8));
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  }
+  if (ymask) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(ymask + pix * C + c8 * 8));
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    float mk[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = mk[i] > 0.f ? acc[i] : 0.f;
+  }
+  *reinterpret_cast<uint4*>(dx + pix * C + c8 * 8) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                                pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+}
+
+// ------------------------------------------------------------------ stride-2 pixel subsample (1x1 stride-2 downsample conv input) and its transpose
+__global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cg = C / 8;
+  long long total = (long long)N * Ho * Wo * cg;
+  if (idx >= total) return;
+  int c8 = (int)(idx % cg);
+  long long t = idx / cg;
+  int wo = (int)(t % Wo);
+  t /= Wo;
+  int ho = (int)(t % Ho);
+  int n = (int)(t / Ho);
+  *reinterpret_cast<uint4*>(y + (((long long)n * Ho + ho) * Wo + wo) * C + c8 * 8) =
+      __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + c8 * 8));
+}
+__global__ void upsample2_zero_kernel(const bf16* __restrict__ y, bf16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cg = C / 8;
+  long long total = (long long)N * H * W * cg;
+  if (idx >= total) return;
+  int c8 = (int)(idx % cg);
+  long long pix = idx / cg;
+  int w = (int)(pix % W);
+  long long t = pix / W;
+  int h = (int)(t % H);
+  int n = (int)(t / H);
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
+    u = __ldg(reinterpret_cast<const uint4*>(y + (((long long)n * Ho + (h >> 1)) * Wo + (w >> 1)) * C + c8 * 8));
+  *reinterpret_cast<uint4*>(x + pix * C + c8 * 8) = u;
+}
+
+// ------------------------------------------------------------------ weights: fp32 torch [Cout][Cin][kh][kw] -> bf16 [Cout][Kpad] tap-major
+// (column = tap*Cin + c), optional second copy pre-multiplied by rowscale[cout] (FrozenBN scale folded for dgrad).
+// taps==49 (stem) keeps torch order c*49+tap.  Columns >= taps*Cin are zero.
+__global__ void prep_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, bf16* __restrict__ out_scaled,
+                                   const float* __restrict__ rowscale, int Cout, int Cin, int taps, int Kpad) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Cout * Kpad;
+  if (idx >= total) return;
+  int col = (int)(idx % Kpad);
+  int co = (int)(idx / Kpad);
+  float v = 0.f;
+  if (col < taps * Cin) {
+    if (taps == 49) {
+      v = w[(long long)co * taps * Cin + col];
+    } else {
+      int tap = col / Cin, c = col - tap * Cin;
+      v = w[((long long)co * Cin + c) * taps + tap];
+    }
+  }
+  out[idx] = __float2bfloat16(v);
+  if (out_scaled) out_scaled[idx] = __float2bfloat16(v * rowscale[co]);
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 cast with optional add (x + pos), 4 elements per thread
+__global__ void cast_add_bf16_kernel(const float* __restrict__ x, const float* __restrict__ add, bf16* __restrict__ y, long long n4) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n4) return;
+  float4 v = __ldg(reinterpret_cast<const float4*>(x) + idx);
+  if (add) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(add) + idx);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  reinterpret_cast<uint2*>(y)[idx] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+// ------------------------------------------------------------------ LayerNorm over d=256 with fused residual add.  One warp per row.
+// z = x + r (r optional, fp32);  y = (z - mean) * rstd * gamma + beta.  Writes y fp32, optional bf16 copy of y and of (y + pos).
+template <int D>
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, const float* __restrict__ pos, float* __restrict__ y,
+                                     bf16* __restrict__ y_bf, bf16* __restrict__ ypos_bf, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, int rows, float eps) {
+  constexpr int PER = D / 32;
+  int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (long long)warp * D;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    int c = i * 32 + lane;
+    v[i] = xr[c] + (r ? r[(long long)warp * D + c] : 0.f);
+    s += v[i];
+  }
+  float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    float dlt = v[i] - mean;
+    q += dlt * dlt;
+  }
+  float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    int c = i * 32 + lane;
+    float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    y[(long long)warp * D + c] = o;
+    if (y_bf) y_bf[(long long)warp * D + c] = __float2bfloat16(o);
+    if (ypos_bf) ypos_bf[(long long)warp * D + c] = __float2bfloat16(o + pos[(long long)warp * D + c]);
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[warp] = mean;
+    if (rstd_out) rstd_out[warp] = rstd;
+  }
+}
+
+// backward: given dy (fp32), z recomputed from (x, r), mean, rstd: dz = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma
+// writes dz (fp32; it is the gradient of BOTH x and r) and per-block partial dgamma/dbeta [blocks][2][D] for a fixed-order reduce.
+template <int D>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ r,
+                                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     float* __restrict__ dz, float* __restrict__ partial, int rows) {
+  constexpr int PER = D / 32;
+  __shared__ float sg[8][D];
+  __shared__ float sb[8][D];
+  int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ag[PER], ab[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) ag[i] = ab[i] = 0.f;
+  for (int row = blockIdx.x * 8 + wib; row < rows; row += gridDim.x * 8) {
+    float m = mean[row], rs = rstd[row];
+    float g[PER], xh[PER];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int c = i * 32 + lane;
+      long long o = (long long)row * D + c;
+      float z = x[o] + (r ? r[o] : 0.f);
+      xh[i] = (z - m) * rs;
+      float d = dy[o];
+      g[i] = d * gamma[c];
+      ag[i] += d * xh[i];
+      ab[i] += d;
+      s1 += g[i];
+      s2 += g[i] * xh[i];
+    }
+    s1 = warp_sum(s1) * (1.f / D);
+    s2 = warp_sum(s2) * (1.f / D);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) dz[(long long)row * D + i * 32 + lane] = rs * (g[i] - s1 - xh[i] * s2);
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    sg[wib][i * 32 + lane] = ag[i];
+    sb[wib][i * 32 + lane] = ab[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += sg[w][c];
+      b += sb[w][c];
+    }
+    partial[((long long)blockIdx.x * 2 + 0) * D + c] = a;
+    partial[((long long)blockIdx.x * 2 + 1) * D + c] = b;
+  }
+}
+// out[c] (+)= sum_b partial[b][c] in fixed order; used for dgamma/dbeta (stride 2*D) and generic column sums
+__global__ void colsum_partials_kernel(const float* __restrict__ partial, int nparts, long long part_stride, int D,
+                                       float* __restrict__ out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float s = 0.f;
+  for (int b = 0; b < nparts; ++b) s += partial[b * part_stride + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// column sums of a bf16 [rows][N] matrix (bias gradients): stage 1 -> partial [nb][N] fp32
+__global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, int rows, int N, float* __restrict__ partial, int rows_per_block) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  int r0 = blockIdx.y * rows_per_block;
+  int r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += __bfloat162float(x[(long long)r * ld + c]);
+  partial[(long long)blockIdx.y * N + c] = s;
+}
+
+}  // namespace tdb
+
+using namespace tdb;
+#define STREAM ((cudaStream_t)stream_)
+#define LAUNCH_OK()                      \
+  do {                                   \
+    TDB_CHECK_CUDA(cudaGetLastError());  \
+    tdb_count_launch(1);                 \
+    return TDB_OK;                       \
+  } while (0)
+
+extern "C" int tdb_stem_im2col(const float* x, void* col, int N, int H, int W, void* stream_) {
+  TDB_REQUIRE(x && col && N > 0 && H > 0 && W > 0, "tdb_stem_im2col: bad args");
+  int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  long long total = (long long)N * Ho * Wo * 24;
+  stem_im2col_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>(x, (bf16*)col, N, H, W, Ho, Wo);
+  LAUNCH_OK();
+}
+extern "C" int tdb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
+  TDB_REQUIRE(x && y && C % 8 == 0, "tdb_maxpool3x3s2: bad args");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)x, (bf16*)y, N, H, W, C, Ho, Wo);
+  LAUNCH_OK();
+}
+extern "C" int tdb_im2col3x3s2(const void* x, void* col, int N, int H, int W, int C, void* stream_) {
+  TDB_REQUIRE(x && col && C % 8 == 0, "tdb_im2col3x3s2: bad args");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * Ho * Wo * 9 * (C / 8);
+  im2col3x3s2_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)x, (bf16*)col, N, H, W, C, Ho, Wo);
+  LAUNCH_OK();
+}
+extern "C" int tdb_col2im3x3s2_mask(const void* dcol, const void* ymask, void* dx, int N, int H, int W, int C, void* stream_) {
+  TDB_REQUIRE(dcol && dx && C % 8 == 0, "tdb_col2im3x3s2_mask: bad args");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)N * H * W * (C / 8);
+  col2im3x3s2_mask_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)dcol, (const bf16*)ymask, (bf16*)dx, N, H, W, C, Ho, Wo);
+  LAUNCH_OK();
+}
+extern "C" int tdb_subsample2(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
+  TDB_REQUIRE(x && y && C % 8 == 0, "tdb_subsample2: bad args");
+  int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  long long total = (long long)N * Ho * Wo * (C / 8);
+  subsample2_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)x, (bf16*)y, N, H, W, C, Ho, Wo);
+  LAUNCH_OK();
+}
+extern "C" int tdb_upsample2_zero(const void* y, void* x, int N, int H, int W, int C, void* stream_) {
+  TDB_REQUIRE(x && y && C % 8 == 0, "tdb_upsample2_zero: bad args");
+  int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  long long total = (long long)N * H * W * (C / 8);
+  upsample2_zero_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)y, (bf16*)x, N, H, W, C, Ho, Wo);
+  LAUNCH_OK();
+}
+extern "C" int tdb_prep_weight(const float* w, void* out, void* out_scaled, const float* rowscale, int Cout, int Cin,
+                               int taps, int Kpad, void* stream_) {
+  TDB_REQUIRE(w && out && Cout > 0 && Cin > 0 && (taps == 1 || taps == 9 || taps == 49) && Kpad >= taps * Cin, "tdb_prep_weight: bad args");
+  TDB_REQUIRE(!out_scaled || rowscale, "tdb_prep_weight: scaled copy needs rowscale");
+  long long total = (long long)Cout * Kpad;
+  prep_weight_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>(w, (bf16*)out, (bf16*)out_scaled, rowscale, Cout, Cin, taps, Kpad);
+  LAUNCH_OK();
+}
+extern "C" int tdb_cast_add_bf16(const float* x, const float* add, void* y, int64_t n, void* stream_) {
+  TDB_REQUIRE(x && y && n % 4 == 0, "tdb_cast_add_bf16: n must be a multiple of 4");
+  cast_add_bf16_kernel<<<nblocks(n / 4, 256), 256, 0, STREAM>>>(x, add, (bf16*)y, n / 4);
+  LAUNCH_OK();
+}
+extern "C" int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta, const float* pos,
+                                 float* y, void* y_bf, void* ypos_bf, float* mean, float* rstd, int rows, int D, float eps,
+                                 void* stream_) {
+  TDB_REQUIRE(x && gamma && beta && y && rows > 0 && D == 256, "tdb_layernorm_fwd: only D=256 (got %d)", D);
+  TDB_REQUIRE(!ypos_bf || pos, "tdb_layernorm_fwd: ypos needs pos");
+  layernorm_fwd_kernel<256><<<nblocks((long long)rows * 32, 256), 256, 0, STREAM>>>(x, r, gamma, beta, pos, y, (bf16*)y_bf,
+                                                                                    (bf16*)ypos_bf, mean, rstd, rows, eps);
+  LAUNCH_OK();
+}
+extern "C" int tdb_layernorm_bwd_blocks(int rows) {
+  int b = (rows + 7) / 8;
+  return b > 296 ? 296 : b;
+}
+extern "C" int tdb_layernorm_bwd(const float* dy, const float* x, const float* r, const float* gamma, const float* mean,
+                                 const float* rstd, float* dz, float* dgamma, float* dbeta, float* partial, int rows, int D,
+                                 int accumulate, void* stream_) {
+  TDB_REQUIRE(dy && x && gamma && mean && rstd && dz && partial && rows > 0 && D == 256, "tdb_layernorm_bwd: bad args");
+  int blocks = tdb_layernorm_bwd_blocks(rows);
+  layernorm_bwd_kernel<256><<<blocks, 256, 0, STREAM>>>(dy, x, r, gamma, mean, rstd, dz, partial, rows);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  if (dgamma) colsum_partials_kernel<<<1, 256, 0, STREAM>>>(partial, blocks, 2 * D, D, dgamma, accumulate);
+  if (dbeta) colsum_partials_kernel<<<1, 256, 0, STREAM>>>(partial + D, blocks, 2 * D, D, dbeta, accumulate);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(3);
+  return TDB_OK;
+}
+extern "C" int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* partial, int nparts, float* out,
+                               int accumulate, void* stream_) {
+  TDB_REQUIRE(x && partial && out && rows > 0 && N > 0 && nparts > 0, "tdb_colsum_bf16: bad args");
+  int rpb = (rows + nparts - 1) / nparts;
+  dim3 grid((N + 127) / 128, nparts);
+  colsum_bf16_kernel<<<grid, 128, 0, STREAM>>>((const bf16*)x, ld, rows, N, partial, rpb);
+  colsum_partials_kernel<<<(N + 255) / 256, 256, 0, STREAM>>>(partial, nparts, N, N, out, accumulate);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(2);
+  return TDB_OK;
+}

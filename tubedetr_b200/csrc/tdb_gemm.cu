@@ -1,0 +1,522 @@
+// tubedetr_b200 -- the tcgen05 / TMEM / TMA GEMM behind every convolution and linear layer (sm_100a).
+//
+// Persistent, warp-specialised, cta_group::1, tile 128 x BN x 64 (BN in {64,128,256}):
+//   warp 0   : TMA producer (one elected lane)   global -> 128B-swizzled smem ring, mbarrier complete_tx
+//   warp 1   : MMA issuer   (one elected lane)   tcgen05.mma kind::f16 bf16 x bf16 -> fp32 in TMEM, tcgen05.commit
+//   warp 2   : TMEM allocator / deallocator      2 x BN columns = double-buffered accumulator
+//   warps 4-7: epilogue                          tcgen05.ld -> scale/bias/residual/ReLU/mask -> row-remapped global stores
+// The accumulator double buffer lets the epilogue of tile i overlap the main loop of tile i+1.
+// Implicit 3x3 convolution = 9 taps inside the reduction loop, each tap a constant row offset into the zero-haloed
+// activation matrix (DESIGN.md "padded-grid implicit GEMM"); TMA zero-fills out-of-range rows.
+// Replaces reference call sites K2-K5, K7, K9-K11, K13: cuDNN convs + FrozenBatchNorm2d
+// (models/backbone.py:60-70,118-122), input_proj (models/tubedetr.py:131,134), all nn.Linear of models/transformer.py.
+#include <atomic>
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/tubedetr_b200.h"
+#include "tdb_common.cuh"
+
+namespace tdb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 256;
+constexpr int kChunkBytes = 64 * 128;  // one [64 rows][128 B] swizzled chunk
+
+struct GemmKParams {
+  int M, N;
+  int kb_per_tap;
+  int ntaps;
+  int a_major, b_major;
+  int a_off0[TDB_MAX_TAPS], a_off1[TDB_MAX_TAPS], b_off0[TDB_MAX_TAPS], b_off1[TDB_MAX_TAPS];
+  int nz, splits, kb_per_split;
+  int z_b_off1[TDB_MAX_TAPS], z_out_col[TDB_MAX_TAPS];
+  int m_tiles, n_tiles, total_work;
+  const float* scale;
+  const float* bias;
+  const bf16* residual;
+  long long ldr;
+  const bf16* mask;
+  long long ldmask;
+  int relu;
+  void* out;
+  int out_f32;
+  long long ldo;
+  int remap, img_h, img_w;
+  int debug_flags;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct WorkItem {
+  int m0, n0, z, split, kb_begin, iters;
+};
+
+__device__ __forceinline__ WorkItem decode_work(const GemmKParams& p, int w, int BN) {
+  WorkItem it;
+  int nt = w % p.n_tiles;
+  int r = w / p.n_tiles;
+  int mt = r % p.m_tiles;
+  r /= p.m_tiles;
+  it.split = r % p.splits;
+  it.z = r / p.splits;
+  it.m0 = mt * BM;
+  it.n0 = nt * BN;
+  if (p.splits == 1) {
+    it.kb_begin = 0;
+    it.iters = p.ntaps * p.kb_per_tap;
+  } else {
+    it.kb_begin = it.split * p.kb_per_split;
+    int e = it.kb_begin + p.kb_per_split;
+    if (e > p.kb_per_tap) e = p.kb_per_tap;
+    it.iters = e - it.kb_begin;
+  }
+  return it;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const WorkItem wi = decode_work(p, w, BN);
+        for (int it = 0; it < wi.iters; ++it) {
+          int tap, kk;
+          if (p.splits == 1) {
+            tap = it / p.kb_per_tap;
+            kk = it - tap * p.kb_per_tap;
+          } else {
+            tap = 0;
+            kk = wi.kb_begin + it;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          uint8_t* sB = sA + BM * BK * 2;
+          if (p.a_major == 0) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kk * BK + p.a_off0[tap], wi.m0 + p.a_off1[tap]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sA + j * kChunkBytes, &tmA, &full_bar[stage], wi.m0 + j * 64 + p.a_off0[tap],
+                          kk * BK + p.a_off1[tap]);
+          }
+          if (p.b_major == 0) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], kk * BK + p.b_off0[tap], wi.n0 + p.b_off1[tap]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], wi.n0 + j * 64 + p.b_off0[tap],
+                          kk * BK + p.b_off1[tap] + p.z_b_off1[wi.z]);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_major, p.b_major);
+      const uint32_t a_kstep = p.a_major ? 2048u : 32u;
+      const uint32_t b_kstep = p.b_major ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_major ? (uint32_t)kChunkBytes : 16u;
+      const uint32_t b_lbo = p.b_major ? (uint32_t)kChunkBytes : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const WorkItem wi = decode_work(p, w, BN);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < wi.iters; ++it) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_base = a_base + BM * BK * 2;
+#pragma unroll
+          for (int s = 0; s < BK / 16; ++s) {
+            const uint64_t adesc = (p.a_major && (p.debug_flags & 1)) ? umma_smem_desc(a_base + s * a_kstep, 1024, a_lbo)
+                                                                      : umma_smem_desc(a_base + s * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = (p.b_major && (p.debug_flags & 1)) ? umma_smem_desc(b_base + s * b_kstep, 1024, b_lbo)
+                                                                      : umma_smem_desc(b_base + s * b_kstep, b_lbo, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (it > 0 || s > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int wq = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int Hp = p.img_h + 2, Wp = p.img_w + 2;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const WorkItem wi = decode_work(p, w, BN);
+      const int row_t = wi.m0 + wq * 32 + lane;
+      bool valid = row_t < p.M;
+      long long out_row = row_t;
+      if (p.remap == TDB_REMAP_COMPACT_TO_PADDED) {
+        int hw = p.img_h * p.img_w;
+        int n = row_t / hw;
+        int rem = row_t - n * hw;
+        int h = rem / p.img_w;
+        int x = rem - h * p.img_w;
+        out_row = ((long long)n * Hp + h + 1) * Wp + x + 1;
+      } else if (p.remap == TDB_REMAP_PADDED_TO_COMPACT) {
+        int hw = Hp * Wp;
+        int n = row_t / hw;
+        int rem = row_t - n * hw;
+        int h = rem / Wp;
+        int x = rem - h * Wp;
+        valid = valid && h >= 1 && h <= p.img_h && x >= 1 && x <= p.img_w;
+        out_row = ((long long)n * p.img_h + (h - 1)) * p.img_w + (x - 1);
+      }
+      int out_col0 = wi.n0 + p.z_out_col[wi.z];
+      if (p.splits > 1) out_row += (long long)wi.split * p.M;
+
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          const int col = wi.n0 + c;  // column in scale/bias/mask/residual space
+          if (p.scale != nullptr) {
+            const float4* sp = reinterpret_cast<const float4*>(p.scale + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 s = __ldg(sp + i);
+              v[4 * i] *= s.x; v[4 * i + 1] *= s.y; v[4 * i + 2] *= s.z; v[4 * i + 3] *= s.w;
+            }
+          }
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 s = __ldg(bp + i);
+              v[4 * i] += s.x; v[4 * i + 1] += s.y; v[4 * i + 2] += s.z; v[4 * i + 3] += s.w;
+            }
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = __ldg(rp + i);
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
+              v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.mask != nullptr) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (long long)row_t * p.ldmask + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = __ldg(mp + i);
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * i] = f0.x > 0.f ? v[8 * i] : 0.f;         v[8 * i + 1] = f0.y > 0.f ? v[8 * i + 1] : 0.f;
+              v[8 * i + 2] = f1.x > 0.f ? v[8 * i + 2] : 0.f; v[8 * i + 3] = f1.y > 0.f ? v[8 * i + 3] : 0.f;
+              v[8 * i + 4] = f2.x > 0.f ? v[8 * i + 4] : 0.f; v[8 * i + 5] = f2.y > 0.f ? v[8 * i + 5] : 0.f;
+              v[8 * i + 6] = f3.x > 0.f ? v[8 * i + 6] : 0.f; v[8 * i + 7] = f3.y > 0.f ? v[8 * i + 7] : 0.f;
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ split-K reduction (fixed order => deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
+                                     const float* __restrict__ rowscale, float* __restrict__ out, int taps,
+                                     int accumulate) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)M * N;
+  if (idx >= total) return;
+  int m = (int)(idx / N);
+  int n = (int)(idx - (long long)m * N);
+  float s = 0.f;
+  for (int i = 0; i < splits; ++i) s += part[(long long)i * total + idx];
+  if (rowscale) s *= rowscale[m];
+  long long o = idx;
+  if (taps > 1) {  // [Cout][tap][Cin] -> torch [Cout][Cin][kh][kw]
+    int cin = N / taps;
+    int tap = n / cin;
+    int c = n - tap * cin;
+    o = ((long long)m * cin + c) * taps + tap;
+  }
+  out[o] = accumulate ? out[o] + s : s;
+}
+
+}  // namespace tdb
+
+// ====================================================================== host side
+static thread_local char g_err[512] = "";
+void tdb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static std::atomic<long long> g_launches{0};
+void tdb_count_launch(int n) { g_launches += n; }
+
+extern "C" const char* tdb_last_error_string(void) { return g_err; }
+extern "C" int tdb_version(void) { return TDB_ABI_VERSION; }
+extern "C" int64_t tdb_launch_count(void) { return g_launches.load(); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+static std::mutex g_init_mu;
+
+int tdb_num_sms() { return g_num_sms; }
+
+int tdb_init_once() {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (g_encode) return TDB_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  TDB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || fn == nullptr) {
+    tdb_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return TDB_ERR_DRIVER;
+  }
+  int dev = 0;
+  TDB_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  TDB_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    tdb_set_error("tubedetr_b200 needs an sm_100a device (found sm_%d%d); there is no fallback path", prop.major, prop.minor);
+    return TDB_ERR_DRIVER;
+  }
+  g_num_sms = prop.multiProcessorCount;
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
+  g_encode = (EncodeTiledFn)fn;
+  return TDB_OK;
+}
+
+// row-major bf16 matrix [rows][cols] (leading dim ld elements) -> 2D tensor map with a [box_rows][64] 128B-swizzled box
+int tdb_make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0) {
+    tdb_set_error("tensor map: base %p / ld %lld not 16-byte aligned", base, (long long)ld);
+    return TDB_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tdb_set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld, box_rows);
+    return TDB_ERR_DRIVER;
+  }
+  return TDB_OK;
+}
+
+static int pick_block_n(int N, long long work_per_bn1 /* m_tiles*nz*splits */, int forced) {
+  if (forced == 64 || forced == 128 || forced == 256) return (N % forced == 0) ? forced : 0;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    int bn = cands[i];
+    if (N % bn) continue;
+    if (work_per_bn1 * (N / bn) >= g_num_sms) return bn;
+  }
+  for (int i = 2; i >= 0; --i)
+    if (N % cands[i] == 0) return cands[i];
+  return 0;
+}
+
+extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
+  using namespace tdb;
+  int rc = tdb_init_once();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TDB_REQUIRE(d && d->A && d->B && d->out, "tdb_gemm: null operand");
+  TDB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "tdb_gemm: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
+  TDB_REQUIRE(d->N % 64 == 0, "tdb_gemm: N=%d must be a multiple of 64", d->N);
+  TDB_REQUIRE(d->ntaps >= 1 && d->ntaps <= TDB_MAX_TAPS, "tdb_gemm: ntaps=%d", d->ntaps);
+  const int nz = d->nz < 1 ? 1 : d->nz;
+  TDB_REQUIRE(nz <= TDB_MAX_TAPS, "tdb_gemm: nz=%d", nz);
+  if (d->a_major == 0 || d->b_major == 0)
+    TDB_REQUIRE(d->K % 64 == 0, "tdb_gemm: K=%d must be a multiple of 64 for K-major operands", d->K);
+  int splits = d->splits < 1 ? 1 : d->splits;
+  const int kb = (d->K + BK - 1) / BK;
+  int kb_per_split = kb;
+  if (splits > 1) {
+    TDB_REQUIRE(d->ntaps == 1 && d->out_dtype == TDB_OUT_F32, "tdb_gemm: split reduction needs ntaps==1 and fp32 partials");
+    TDB_REQUIRE(!d->scale && !d->bias && !d->residual && !d->mask && !d->relu && d->remap == 0, "tdb_gemm: no epilogue with splits");
+    if (splits > kb) splits = kb;
+    kb_per_split = (kb + splits - 1) / splits;
+    splits = (kb + kb_per_split - 1) / kb_per_split;
+  }
+  const int m_tiles = (d->M + BM - 1) / BM;
+  const int bn = pick_block_n(d->N, (long long)m_tiles * nz * splits, d->block_n);
+  TDB_REQUIRE(bn != 0, "tdb_gemm: no tile width for N=%d (block_n=%d)", d->N, d->block_n);
+  if (d->remap != TDB_REMAP_NONE) TDB_REQUIRE(d->img_h > 0 && d->img_w > 0, "tdb_gemm: remap needs img_h/img_w");
+
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M; p.N = d->N; p.kb_per_tap = kb; p.ntaps = d->ntaps;
+  p.a_major = d->a_major ? 1 : 0; p.b_major = d->b_major ? 1 : 0;
+  for (int i = 0; i < TDB_MAX_TAPS; ++i) {
+    p.a_off0[i] = d->a_off0[i]; p.a_off1[i] = d->a_off1[i];
+    p.b_off0[i] = d->b_off0[i]; p.b_off1[i] = d->b_off1[i];
+    p.z_b_off1[i] = d->nz >= 1 ? d->z_b_off1[i] : 0;
+    p.z_out_col[i] = d->nz >= 1 ? d->z_out_col[i] : 0;
+  }
+  p.nz = nz; p.splits = splits; p.kb_per_split = kb_per_split;
+  p.m_tiles = m_tiles; p.n_tiles = d->N / bn;
+  long long total = (long long)p.m_tiles * p.n_tiles * nz * splits;
+  TDB_REQUIRE(total < (1ll << 30), "tdb_gemm: too many tiles");
+  p.total_work = (int)total;
+  p.scale = d->scale; p.bias = d->bias;
+  p.residual = (const bf16*)d->residual; p.ldr = d->ldr;
+  p.mask = (const bf16*)d->mask; p.ldmask = d->ldmask;
+  p.relu = d->relu; p.out = d->out; p.out_f32 = d->out_dtype == TDB_OUT_F32; p.ldo = d->ldo;
+  p.remap = d->remap; p.img_h = d->img_h; p.img_w = d->img_w;
+  p.debug_flags = d->debug_flags;
+  TDB_REQUIRE(p.ldo % 8 == 0 && (!p.residual || p.ldr % 8 == 0) && (!p.mask || p.ldmask % 8 == 0), "tdb_gemm: leading dims must be multiples of 8");
+
+  CUtensorMap tmA, tmB;
+  rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, p.a_major ? 64 : BM);
+  if (rc) return rc;
+  rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : bn);
+  if (rc) return rc;
+
+  int grid = p.total_work < g_num_sms ? p.total_work : g_num_sms;
+  if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
+  switch (bn) {
+    case 64: tdb_gemm_kernel<64><<<grid, kGemmThreads, GemmCfg<64>::kSmemBytes, stream>>>(tmA, tmB, p); break;
+    case 128: tdb_gemm_kernel<128><<<grid, kGemmThreads, GemmCfg<128>::kSmemBytes, stream>>>(tmA, tmB, p); break;
+    default: tdb_gemm_kernel<256><<<grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(tmA, tmB, p); break;
+  }
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(1);
+  return TDB_OK;
+}
+
+extern "C" int tdb_gemm_effective_splits(int K, int splits) {
+  const int kb = (K + tdb::BK - 1) / tdb::BK;
+  if (splits < 1) splits = 1;
+  if (splits > kb) splits = kb;
+  const int per = (kb + splits - 1) / splits;
+  return (kb + per - 1) / per;
+}
+
+extern "C" int tdb_splitk_reduce(const float* part, int splits, int M, int N, const float* rowscale, float* out,
+                                 int taps, int accumulate, void* stream_) {
+  TDB_REQUIRE(part && out && splits >= 1 && M > 0 && N > 0 && taps >= 1 && N % taps == 0, "tdb_splitk_reduce: bad args");
+  long long total = (long long)M * N;
+  int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  tdb::splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream_>>>(part, splits, M, N, rowscale, out, taps, accumulate);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(1);
+  return TDB_OK;
+}
