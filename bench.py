@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- clips/sec of one TubeDETR training pass (forward + loss + backward) on synthetic VidSTG-shaped clips.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W   [--impl reference]
+  N>1 is launched under torch.distributed.run (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+Workload = BASELINE.json configs[1]/[2]: per GPU B=1 clip, T=100 frames, stride k=4 (25 slow + 100 fast frames),
+res 352, 20-token caption, random-init seeded weights, bf16 tensor-core compute with fp32 master weights.
+A step = H2D-resident inputs -> TubeDETR.forward (encode) -> TubeDETR.forward (decode) -> SetCriterion -> backward
+(all parameter gradients incl. RoBERTa) -> (N>1) one NCCL all-reduce of the flat gradient buffer.
+`value`  : device-timed, inputs already in HBM.      `e2e`: same step fed from pinned host memory every step
+(H2D of both frame tensors, D2H of the loss), through the public module API.
+--impl reference times the CPU oracle (the reference algorithm restated in oracle/, pinned to the reference's own
+outputs) on this box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_FRAMES, STRIDE, RES, NTOK = 100, 4, 352, 20
+FLOP_PER_CLIP = 6.824e12      # analytic fwd+bwd FLOPs of one clip at this config
+WORKLOAD = "cfg2: per-GPU B=1 clip, T=100, k=4 (25 slow + 100 fast frames), res=352, L=20 tokens, fwd+loss+bwd"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU oracle arm
+def oracle_step_seconds(nframes, threads, steps=1):
+    """fwd + loss + bwd of the CPU oracle on a sub-clip of `nframes` frames at res 352 / k=4 (eval-mode numerics)."""
+    from oracle import tubedetr_oracle as O
+    from tubedetr_b200.synthetic import make_batch, pack_clips
+    from tubedetr_b200.weights import seeded_state_dict
+    torch.set_num_threads(threads)
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_manifest.json")))
+    sd = seeded_state_dict([tuple(m) for m in man], 0)
+    rg = torch.load(os.path.join(ROOT, "tests", "golden", "cfg1b.pt"), weights_only=False)["requires_grad"]
+    trainable = [k for k, v in rg.items() if v and "pooler" not in k]   # what the reference trains (backbone.py:82-89)
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    b = make_batch([nframes], (RES, RES), STRIDE, [NTOK], seed=0)
+    ff, fm = pack_clips(b["clips"])
+    fs, sm_ = pack_clips([c[:, ::STRIDE] for c in b["clips"]])
+    keep = torch.tensor([e for e in range(b["inter_idx"][0][0], b["inter_idx"][0][1] + 1)])
+    wd = O.weight_dict()
+    times = []
+    for _ in range(steps + 1):           # first iteration is warm-up
+        t0 = time.perf_counter()
+        out, _ = O.forward(sd, fs, sm_, ff, fm, [nframes], b["input_ids"], b["attention_mask"], STRIDE)
+        losses = O.criterion(out, b["target_boxes"], b["inter_idx"], b["time_mask"], keep)
+        total = sum(losses[k] * wd[k] for k in losses)
+        torch.autograd.grad(total, [sd[k] for k in trainable], allow_unused=True)
+        times.append(time.perf_counter() - t0)
+    return sum(times[1:]) / max(len(times) - 1, 1)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nfr = 12
+    sec = oracle_step_seconds(nfr, cores, steps=max(1, min(args.steps, 3)))
+    clip_sec = sec * (T_FRAMES / nfr)
+    val = 1.0 / clip_sec
+    line = {"metric": "clips_per_sec_fwd_bwd", "value": val, "unit": "clips/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": clip_sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU oracle (reference algorithm, fp32 eager PyTorch) on host cores"},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"{nfr}-frame sub-clip (3 slow + 12 fast frames, res 352, L=20) fwd+loss+bwd, "
+                                       f"{sec:.1f} s/step, scaled x{T_FRAMES / nfr:.2f} to the 100-frame clip"},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def build_everything(device, seed=0):
+    from tubedetr_b200 import build_model
+    from tubedetr_b200.weights import seeded_tensor
+    a = argparse.Namespace(num_queries=1, aux_loss=True, video_max_len_train=200, stride=STRIDE, guided_attn=True, fast=True,
+                           fast_mode="", sted=True, no_tsa=False, enc_layers=6, dec_layers=6, lr_backbone=1e-5,
+                           bbox_loss_coef=5, giou_loss_coef=2, sted_loss_coef=10, guided_attn_loss_coef=1, sigma=1,
+                           device=str(device), hidden_dim=256, nheads=8, dim_feedforward=2048, backbone="resnet101",
+                           dilation=False, position_embedding="sine")
+    model, crit, wd = build_model(a)
+    sd = {k: seeded_tensor(seed, k, v.shape, v.dtype) for k, v in model.state_dict().items()}
+    model.load_state_dict(sd, strict=True)
+    return model.to(device).eval(), crit, wd      # eval(): dropout is not implemented in the kernels yet
+
+
+class Step:
+    """One training pass on static device buffers (CUDA-graph friendly)."""
+
+    def __init__(self, model, crit, wd, device, rank, world, use_graph=True):
+        from tubedetr_b200 import NestedTensor
+        from tubedetr_b200.synthetic import make_batch, pack_clips
+        self.model, self.crit, self.wd, self.world = model, crit, wd, world
+        b = make_batch([T_FRAMES], (RES, RES), STRIDE, [NTOK], seed=100 + rank)
+        ff, fm = pack_clips(b["clips"])
+        fs, ms = pack_clips([c[:, ::STRIDE] for c in b["clips"]])
+        self.host_fast, self.host_slow = ff.pin_memory(), fs.pin_memory()
+        self.d_fast, self.d_slow = torch.empty_like(ff, device=device), torch.empty_like(fs, device=device)
+        self.stage_fast, self.stage_slow = torch.empty_like(self.d_fast), torch.empty_like(self.d_slow)
+        self.d_fast.copy_(self.host_fast)
+        self.d_slow.copy_(self.host_slow)
+        self.samples = NestedTensor(self.d_slow, ms.to(device))
+        self.fast = NestedTensor(self.d_fast, fm.to(device))
+        self.caps = (b["input_ids"].to(device), b["attention_mask"].to(device))
+        self.keep = torch.tensor(list(range(b["inter_idx"][0][0], b["inter_idx"][0][1] + 1)), device=device)
+        self.targets = [{"boxes": bx[None].to(device)} for bx in b["target_boxes"]]
+        self.inter_idx, self.time_mask = b["inter_idx"], b["time_mask"].to(device)
+        self.crit.static = self.crit.prepare(self.targets, self.inter_idx, self.time_mask)
+        # flat gradient buffer: every .grad is a view into it => ONE all-reduce, static addresses for graph replay
+        ps = [p for p in model.parameters() if p.requires_grad]
+        self.flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=device)
+        o = 0
+        for p in ps:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.loss = torch.zeros((), device=device)
+        self.host_loss = torch.zeros((), pin_memory=True)
+        self.copy_stream = torch.cuda.Stream()
+        self.graph = None
+        self.use_graph = use_graph
+        self.launches_per_step = None
+
+    def body(self):
+        self.flat.zero_()
+        mc = self.model(self.samples, [T_FRAMES], self.caps, encode_and_save=True, samples_fast=self.fast)
+        out = self.model(self.samples, [T_FRAMES], self.caps, encode_and_save=False, memory_cache=mc)
+        out = dict(out, pred_boxes=out["pred_boxes"][self.keep],
+                   aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][self.keep]) for a in out["aux_outputs"]])
+        losses = self.crit(out, self.targets, self.inter_idx, self.time_mask)
+        total = sum(losses[k] * self.wd[k] for k in losses if k in self.wd)
+        total.backward()
+        self.loss.copy_(total.detach())
+
+    def capture(self):
+        from tubedetr_b200 import _lib
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        c0 = _lib.launch_count()
+        if self.use_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.body()
+                self.graph = g
+            except Exception as e:  # keep going eagerly, say so
+                sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
+                self.graph = None
+                torch.cuda.synchronize()
+                c0 = _lib.launch_count()
+                self.body()
+        else:
+            self.body()
+        torch.cuda.synchronize()
+        self.launches_per_step = _lib.launch_count() - c0
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.body()
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat)      # the single gradient collective (sum; scale folded into lr)
+
+    def run_e2e(self, prefetched):
+        """inputs come from pinned host memory: H2D on a copy stream (overlapping the previous step), D2H of the loss."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(prefetched)
+        self.d_fast.copy_(self.stage_fast, non_blocking=True)
+        self.d_slow.copy_(self.stage_slow, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(cur)
+        nxt = self.prefetch(after=done)
+        self.run()
+        self.host_loss.copy_(self.loss, non_blocking=True)
+        return nxt
+
+    def prefetch(self, after=None):
+        with torch.cuda.stream(self.copy_stream):
+            if after is not None:
+                self.copy_stream.wait_event(after)
+            self.stage_fast.copy_(self.host_fast, non_blocking=True)
+            self.stage_slow.copy_(self.host_slow, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return ev
+
+
+def kernel_probe(device, pk):
+    """Dominant kernel alone: layer3 3x3 conv (22 of them per frame) as the implicit tcgen05 GEMM on the 100-frame batch."""
+    from tubedetr_b200.gemm import REMAP_P2C, gemm
+    N, h, w, C = 100, 22, 22, 256
+    Rp = N * (h + 2) * (w + 2)
+    nb = 6                                       # rotate buffers: 6 x (29.5 + 24.8) MB > 126 MB L2
+    xs = [torch.randn(Rp, C, device=device).to(torch.bfloat16) for _ in range(nb)]
+    ys = [torch.empty(N * h * w, C, dtype=torch.bfloat16, device=device) for _ in range(nb)]
+    wk = (torch.randn(C, 9 * C, device=device) * 0.02).to(torch.bfloat16)
+    sc, sh = torch.ones(C, device=device), torch.zeros(C, device=device)
+    taps = [(kh - 1) * (w + 2) + (kw - 1) for kh in range(3) for kw in range(3)]
+
+    def launch(i):
+        gemm(xs[i % nb], wk, ys[i % nb], Rp, C, C, ntaps=9, a_off1=taps, b_off0=[t * C for t in range(9)], scale=sc, bias=sh,
+             relu=True, remap=REMAP_P2C, img_hw=(h, w))
+    for i in range(6):
+        launch(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 30
+    e0.record()
+    for i in range(reps):
+        launch(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * N * h * w * C * 9 * C           # algorithmic (un-haloed) conv FLOPs per launch
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "tdb_gemm_kernel<256> (layer3 3x3 conv, implicit GEMM, 100 frames)", "achieved": ach,
+            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
+            "peak_source": pk["src"] + " cuBLAS bf16 burst", "ms_per_launch": ms, "flops_per_launch": flops}
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    pk = peaks()
+    model, crit, wd = build_everything(device)
+    st = Step(model, crit, wd, device, rank, world, use_graph=not args.no_graph)
+    st.capture()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn_iter, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn_iter(steps)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    def loop_dev(n):
+        for _ in range(n):
+            st.run()
+
+    def loop_e2e(n):
+        ev = st.prefetch()
+        for _ in range(n):
+            ev = st.run_e2e(ev)
+        torch.cuda.current_stream().synchronize()
+
+    loop_dev(max(args.warmup, 3))
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev = timed(loop_dev, args.steps)
+    loop_e2e(2)
+    ms_e2e = timed(loop_e2e, args.steps)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    loss_val = float(st.loss.item())
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    probe = kernel_probe(device, pk)
+    per_step = ms_dev / args.steps
+    clips = world / (per_step * 1e-3)
+    per_step_e2e = ms_e2e / args.steps
+    h2d = st.host_fast.numel() * 4 + st.host_slow.numel() * 4
+    cpu = None
+    if not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        nfr = 12
+        sec = oracle_step_seconds(nfr, cores, steps=1)
+        cpu = {"value": 1.0 / (sec * T_FRAMES / nfr), "unit": "clips/s", "cores": cores, "kind": "port",
+               "sample": f"{nfr}-frame sub-clip (3 slow + 12 fast frames, res 352, L=20) fwd+loss+bwd on the CPU oracle, "
+                         f"{sec:.1f} s/step, scaled x{T_FRAMES / nfr:.2f} to the 100-frame clip"}
+    line = {"metric": "clips_per_sec_fwd_bwd", "value": clips, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world, "parallelism": f"dp{world}",
+                       "l2": "inputs + activations of a step (>2 GB) exceed the 126 MB L2; no explicit flush",
+                       "cuda_graph": st.graph is not None, "numerics": "eval-mode (dropout not applied)",
+                       "loss": loss_val},
+            "e2e": {"value": world / (per_step_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": per_step_e2e},
+            "gpu_launches": int(st.launches_per_step * args.steps),
+            "step_mfu": {"flops_per_clip": FLOP_PER_CLIP, "achieved_tflops_per_gpu": FLOP_PER_CLIP / (per_step * 1e-3) / 1e12,
+                         "frac_of_sustained_peak": FLOP_PER_CLIP / (per_step * 1e-3) / 1e12 / pk["tf_sustained"]},
+            "roofline": probe, "cpu_baseline": cpu, "clocks": sampler.summary() if sampler else None}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,6 +80,56 @@ int tdb_gemm_effective_splits(int K, int splits);
 int tdb_splitk_reduce(const float* part, int splits, int M, int N, const float* rowscale, float* out, int taps,
                       int accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Layout transforms around the GEMM (all NHWC bf16 "pixel rows" unless noted).
+ * ------------------------------------------------------------------------------------------------ */
+/* ResNet stem (reference models/backbone.py:98 -> torchvision conv1 7x7/2/p3): fp32 NCHW frames -> bf16 im2col rows
+ * [N*Ho*Wo][192] (147 real columns, order c*49+kh*7+kw); the conv itself + FrozenBN + ReLU is one tdb_gemm */
+int tdb_stem_im2col(const float* x, void* col, int N, int H, int W, void* stream);
+/* torchvision maxpool 3x3/2/p1 after the stem */
+int tdb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* stride-2 3x3 convs (first block of layer2/3/4, torchvision v1.5): explicit im2col [N*Ho*Wo][9*C] (tap major) ... */
+int tdb_im2col3x3s2(const void* x, void* col, int N, int H, int W, int C, void* stream);
+/* ... and its transpose as a deterministic gather, fused with the ReLU mask (ymask > 0) of the conv input */
+int tdb_col2im3x3s2_mask(const void* dcol, const void* ymask, void* dx, int N, int H, int W, int C, void* stream);
+/* stride-2 1x1 `downsample` conv input (pixel subsample) and its transpose (zero upsample) */
+int tdb_subsample2(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int tdb_upsample2_zero(const void* y, void* x, int N, int H, int W, int C, void* stream);
+/* fp32 torch conv weight [Cout][Cin][kh][kw] -> bf16 GEMM layout [Cout][Kpad] (tap major; taps==49 keeps torch order),
+ * optional second copy scaled per output channel (FrozenBN scale folded for dgrad, reference models/backbone.py:60-70) */
+int tdb_prep_weight(const float* w, void* out, void* out_scaled, const float* rowscale, int Cout, int Cin, int taps,
+                    int Kpad, void* stream);
+/* y(bf16) = x (+ add), n % 4 == 0 */
+int tdb_cast_add_bf16(const float* x, const float* add, void* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm with fused residual add (post-norm blocks, reference models/transformer.py:641-645, 721-750, 581;
+ * FeatureResizer LN eps 1e-12 :765).  D must be 256.  z = x + r; y = LN(z).  Optional bf16 copies of y and y + pos
+ * (the operand of the next projection GEMM).  Backward returns dz (gradient of both x and r) and dgamma/dbeta.
+ * ------------------------------------------------------------------------------------------------ */
+int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta, const float* pos, float* y,
+                      void* y_bf, void* ypos_bf, float* mean, float* rstd, int rows, int D, float eps, void* stream);
+int tdb_layernorm_bwd_blocks(int rows); /* partial workspace = blocks * 2 * D floats */
+int tdb_layernorm_bwd(const float* dy, const float* x, const float* r, const float* gamma, const float* mean,
+                      const float* rstd, float* dz, float* dgamma, float* dbeta, float* partial, int rows, int D,
+                      int accumulate, void* stream);
+/* column sums of a bf16 [rows][N] matrix (bias gradients), two-stage fixed order; partial = nparts * N floats */
+int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* partial, int nparts, float* out, int accumulate,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention core, head_dim 32 (torch F.multi_head_attention_forward need_weights path; reference call sites
+ * models/transformer.py:637-640 encoder, 698-722 temporal self-attention, 724-745 time-aligned cross-attention).
+ * q/k/v/o: bf16 rows [B*L][>= H*32] with row strides ld*; kpm [B][Lk] nonzero = padded key.
+ * p [B][H][Lq][Lk] probabilities (kept for backward); pbar [B][Lq][Lk] = mean over heads (guided-attention loss) or NULL.
+ * Backward takes dO and optionally dPbar and returns dq/dk/dv in the layout of q/k/v.
+ * ------------------------------------------------------------------------------------------------ */
+int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm,
+                void* o, int64_t ldo, float* p, float* pbar, int B, int H, int Lq, int Lk, float scale, void* stream);
+int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
+                int64_t lddo, const float* p, const float* dpbar, float* ds_scratch, void* dq, int64_t lddq, void* dk,
+                int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,94 @@
+"""CPU checks of the drop-in boundary: state_dict names/shapes, build(args) surface, C-ABI symbols, criterion parity."""
+import argparse
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import load_gold, manifest, run_oracle, state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(**kw):
+    d = dict(num_queries=1, aux_loss=True, video_max_len_train=200, stride=2, guided_attn=True, fast=True, fast_mode="",
+             sted=True, no_tsa=False, enc_layers=6, dec_layers=6, lr_backbone=1e-5, bbox_loss_coef=5, giou_loss_coef=2,
+             sted_loss_coef=10, guided_attn_loss_coef=1, sigma=1, device="cpu", hidden_dim=256, nheads=8,
+             dim_feedforward=2048, backbone="resnet101", dilation=False, position_embedding="sine")
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+@pytest.fixture(scope="module")
+def built():
+    from tubedetr_b200 import build_model
+    return build_model(_args())
+
+
+def test_state_dict_matches_reference_manifest(built):
+    model = built[0]
+    mine = {k: (list(v.shape), str(v.dtype)) for k, v in model.state_dict().items()}
+    ref = {k: (s, d) for k, s, d in manifest()}
+    assert set(mine) == set(ref), (sorted(set(mine) ^ set(ref))[:10])
+    bad = [k for k in ref if mine[k] != ref[k]]
+    assert not bad, bad[:10]
+    model.load_state_dict(state_dict(), strict=True)
+
+
+def test_trainable_set_matches_reference(built):
+    g = load_gold("cfg1b")
+    mine = {k: p.requires_grad for k, p in built[0].named_parameters()}
+    assert mine == g["requires_grad"]
+
+
+def test_weight_dict_and_losses_keys(built):
+    g = load_gold("cfg1")
+    assert {k: float(v) for k, v in built[2].items()} == {k: float(v) for k, v in g["weight_dict"].items()}
+    assert built[1].losses == ["boxes", "sted", "guided_attn"]
+
+
+def test_unsupported_flags_raise():
+    from tubedetr_b200 import build_model
+    with pytest.raises(NotImplementedError):
+        build_model(_args(fast_mode="gating"))
+    with pytest.raises(NotImplementedError):
+        build_model(_args(stride=0))
+
+
+def test_criterion_matches_reference_losses(built):
+    """SetCriterion (pure host/torch logic, device agnostic) on the oracle's outputs reproduces the reference's 24 losses."""
+    g = load_gold("cfg1b")
+    with torch.no_grad():
+        out, cache, b = run_oracle(g["cfg"])
+    keep = b["keep"]
+    o = dict(out, pred_boxes=out["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in out["aux_outputs"]])
+    targets = [{"boxes": bx[None]} for bx in b["target_boxes"]]
+    losses = built[1](o, targets, b["inter_idx"], b["time_mask"])
+    assert set(losses) == set(g["losses"])
+    for k, v in g["losses"].items():
+        torch.testing.assert_close(losses[k], v, atol=1e-4, rtol=1e-3, msg=k)
+
+
+def test_cabi_exports_every_declared_symbol():
+    from tubedetr_b200.build import LIB, build
+    build()
+    lib = ctypes.CDLL(LIB)
+    hdr = open(os.path.join(ROOT, "include", "tubedetr_b200.h")).read()
+    syms = sorted(set(re.findall(r"\b(tdb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 10
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.tdb_version() == 1
+    lib.tdb_gemm_effective_splits.restype = ctypes.c_int
+    assert lib.tdb_gemm_effective_splits(1000, 5) == 4  # 16 k-blocks, 4 per split
+
+
+def test_model_without_cuda_fails_loudly(built):
+    from tubedetr_b200 import NestedTensor
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    s = NestedTensor(torch.zeros(2, 3, 64, 64), torch.zeros(2, 64, 64, dtype=torch.bool))
+    with pytest.raises(RuntimeError):
+        built[0](s, [4], ["a caption"], encode_and_save=True, samples_fast=s)

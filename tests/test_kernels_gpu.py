@@ -1,0 +1,170 @@
+"""GPU parity of the helper / attention / LayerNorm kernels (through the C ABI) against fp32 PyTorch."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _r(shape, seed, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g).to(dtype).cuda()
+
+
+def _close(got, ref, tol):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    assert err <= tol * (ref.abs().max().item() + 1e-6), f"max err {err}, ref max {ref.abs().max().item()}"
+
+
+def test_stem_im2col_and_maxpool():
+    from tubedetr_b200 import kernels as K
+    from tubedetr_b200.gemm import gemm
+    N, H, W = 2, 64, 96
+    x = _r((N, 3, H, W), 1, torch.float32)
+    w = _r((64, 3, 7, 7), 2, torch.float32) * 0.1
+    Ho, Wo = H // 2, W // 2
+    col = torch.empty(N * Ho * Wo, 192, dtype=torch.bfloat16, device="cuda")
+    K.stem_im2col(x, col, N, H, W)
+    wk = torch.empty(64, 192, dtype=torch.bfloat16, device="cuda")
+    K.prep_weight(w, wk, None, None, 64, 3, 49, 192)
+    y = torch.empty(N * Ho * Wo, 64, dtype=torch.bfloat16, device="cuda")
+    gemm(col, wk, y, N * Ho * Wo, 64, 192, relu=True)
+    ref = F.relu(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3))
+    _close(y.view(N, Ho, Wo, 64).permute(0, 3, 1, 2), ref, 1e-2)
+    Hp, Wp = (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1
+    z = torch.empty(N, Hp, Wp, 64, dtype=torch.bfloat16, device="cuda")
+    K.maxpool3x3s2(y, z, N, Ho, Wo, 64)
+    refp = F.max_pool2d(y.view(N, Ho, Wo, 64).permute(0, 3, 1, 2).float(), 3, 2, 1)
+    assert torch.equal(z.permute(0, 3, 1, 2).float(), refp)
+
+
+@pytest.mark.parametrize("H,W", [(22, 22), (11, 13)])
+def test_stride2_conv_paths(H, W):
+    from tubedetr_b200 import kernels as K
+    from tubedetr_b200.gemm import gemm
+    N, C, Co = 3, 64, 128
+    x = _r((N, H, W, C), 3)
+    w = _r((Co, C, 3, 3), 4, torch.float32) * 0.1
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    col = torch.empty(N * Ho * Wo, 9 * C, dtype=torch.bfloat16, device="cuda")
+    K.im2col3x3s2(x, col, N, H, W, C)
+    wk = torch.empty(Co, 9 * C, dtype=torch.bfloat16, device="cuda")
+    K.prep_weight(w, wk, None, None, Co, C, 9, 9 * C)
+    y = torch.empty(N * Ho * Wo, Co, dtype=torch.bfloat16, device="cuda")
+    gemm(col, wk, y, N * Ho * Wo, Co, 9 * C)
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.conv2d(xf, w.bfloat16().float(), stride=2, padding=1)
+    _close(y.view(N, Ho, Wo, Co).permute(0, 3, 1, 2), ref, 1e-2)
+    # backward data path: dcol = g @ W (MN-major B), gather back, masked
+    g = _r((N * Ho * Wo, Co), 5)
+    dcol = torch.empty(N * Ho * Wo, 9 * C, dtype=torch.bfloat16, device="cuda")
+    gemm(g, wk, dcol, N * Ho * Wo, 9 * C, Co, b_major=1)
+    dx = torch.empty(N, H, W, C, dtype=torch.bfloat16, device="cuda")
+    K.col2im3x3s2_mask(dcol, x, dx, N, H, W, C)
+    ref.backward(g.float().view(N, Ho, Wo, Co).permute(0, 3, 1, 2))
+    _close(dx, xf.grad.permute(0, 2, 3, 1) * (x.float() > 0), 2e-2)
+    # subsample / zero-upsample are exact transposes
+    xs = torch.empty(N, Ho, Wo, C, dtype=torch.bfloat16, device="cuda")
+    K.subsample2(x, xs, N, H, W, C)
+    assert torch.equal(xs, x[:, ::2, ::2].contiguous())
+    up = torch.empty(N, H, W, C, dtype=torch.bfloat16, device="cuda")
+    K.upsample2_zero(xs, up, N, H, W, C)
+    refu = torch.zeros_like(x)
+    refu[:, ::2, ::2] = xs
+    assert torch.equal(up, refu)
+
+
+def test_prep_weight_layouts():
+    from tubedetr_b200 import kernels as K
+    w = _r((64, 32, 3, 3), 6, torch.float32)
+    s = torch.rand(64, device="cuda") + 0.5
+    o = torch.empty(64, 9 * 32, dtype=torch.bfloat16, device="cuda")
+    os_ = torch.empty_like(o)
+    K.prep_weight(w, o, os_, s, 64, 32, 9, 9 * 32)
+    ref = w.permute(0, 2, 3, 1).reshape(64, -1)
+    assert torch.equal(o, ref.bfloat16())
+    assert torch.equal(os_, (ref * s[:, None]).bfloat16())
+
+
+def test_layernorm_fwd_bwd():
+    from tubedetr_b200 import kernels as K
+    rows, D = 777, 256
+    x, r = _r((rows, D), 7, torch.float32), _r((rows, D), 8, torch.float32)
+    pos = _r((rows, D), 9, torch.float32)
+    gm, bt = _r((D,), 10, torch.float32) * 0.1 + 1, _r((D,), 11, torch.float32) * 0.1
+    y = torch.empty(rows, D, device="cuda")
+    yb = torch.empty(rows, D, dtype=torch.bfloat16, device="cuda")
+    yp = torch.empty_like(yb)
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    K.layernorm_fwd(x, r, gm, bt, pos, y, yb, yp, mean, rstd, rows, D, 1e-5)
+    z = (x + r).requires_grad_(True)
+    gmr, btr = gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+    ref = F.layer_norm(z, (D,), gmr, btr, 1e-5)
+    _close(y, ref, 1e-5)
+    _close(yb, ref, 1e-2)
+    _close(yp, ref + pos, 1e-2)
+    dy = _r((rows, D), 12, torch.float32)
+    ref.backward(dy)
+    dz = torch.empty(rows, D, device="cuda")
+    dg, db = torch.empty(D, device="cuda"), torch.empty(D, device="cuda")
+    K.layernorm_bwd(dy, x, r, gm, mean, rstd, dz, dg, db, rows, D)
+    _close(dz, z.grad, 1e-4)
+    _close(dg, gmr.grad, 1e-4)
+    _close(db, btr.grad, 1e-4)
+
+
+def _ref_attn(q, k, v, kpm, H, scale):
+    B, Lq, d = q.shape
+    Lk = k.shape[1]
+    qh = (q * scale).view(B, Lq, H, 32).transpose(1, 2)
+    kh = k.view(B, Lk, H, 32).transpose(1, 2)
+    vh = v.view(B, Lk, H, 32).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2)
+    if kpm is not None:
+        s = s.masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
+    p = s.softmax(-1)
+    return (p @ vh).transpose(1, 2).reshape(B, Lq, d), p
+
+
+@pytest.mark.parametrize("B,Lq,Lk", [(5, 59, 59), (2, 100, 100), (12, 1, 141), (1, 200, 200)])
+def test_mha_fwd_bwd(B, Lq, Lk):
+    from tubedetr_b200 import kernels as K
+    H, d = 8, 256
+    scale = 1 / math.sqrt(32)
+    q, k, v = _r((B, Lq, d), 20), _r((B, Lk, d), 21), _r((B, Lk, d), 22)
+    kpm = torch.zeros(B, Lk, dtype=torch.uint8, device="cuda")
+    kpm[:, Lk - Lk // 5:] = 1
+    kpm[0] = 0
+    o = torch.empty(B * Lq, d, dtype=torch.bfloat16, device="cuda")
+    p = torch.empty(B, H, Lq, Lk, device="cuda")
+    pbar = torch.empty(B, Lq, Lk, device="cuda")
+    K.mha_fwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), kpm, o, p, pbar, B, H, Lq, Lk, scale)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ro, rp = _ref_attn(qf, kf, vf, kpm, H, scale)
+    _close(o.view(B, Lq, d), ro, 1e-2)
+    _close(p, rp, 1e-4)
+    _close(pbar, rp.mean(1), 1e-4)
+    do = _r((B, Lq, d), 23)
+    dpbar = _r((B, Lq, Lk), 24, torch.float32)
+    (ro * do.float()).sum().add((rp.mean(1) * dpbar).sum()).backward()
+    ds = torch.empty_like(p)
+    dq, dk, dv = (torch.empty(t.shape[0] * t.shape[1], d, dtype=torch.bfloat16, device="cuda") for t in (q, k, v))
+    K.mha_bwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), do.view(-1, d), p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale)
+    _close(dq.view_as(q), qf.grad, 2e-2)
+    _close(dk.view_as(k), kf.grad, 2e-2)
+    _close(dv.view_as(v), vf.grad, 2e-2)
+
+
+def test_colsum_and_cast():
+    from tubedetr_b200 import kernels as K
+    x = _r((1000, 256), 30)
+    out = torch.zeros(256, device="cuda")
+    K.colsum_bf16(x, out)
+    _close(out, x.float().sum(0), 1e-4)
+    a, b = _r((300, 256), 31, torch.float32), _r((300, 256), 32, torch.float32)
+    y = torch.empty(300, 256, dtype=torch.bfloat16, device="cuda")
+    K.cast_add_bf16(a, b, y)
+    assert torch.equal(y, (a + b).bfloat16())

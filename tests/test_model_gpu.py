@@ -1,0 +1,141 @@
+"""End-to-end GPU parity of the drop-in TubeDETR / SetCriterion against the reference fixtures (tests/golden/*.pt)
+and against the CPU oracle.  Tolerances: BASELINE.json north_star -- 2e-2 for the bf16 path on pred_boxes / pred_sted."""
+import argparse
+import os
+
+import pytest
+import torch
+
+from helpers import batch_for, load_gold, state_dict
+
+pytestmark = pytest.mark.gpu
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _args(cfg):
+    fl = cfg["flags"]
+    return argparse.Namespace(
+        num_queries=1, aux_loss=True, video_max_len_train=200, stride=cfg["stride"], guided_attn="--no_guided_attn" not in fl,
+        fast="--no_fast" not in fl, fast_mode="", sted=True, no_tsa="--no_tsa" in fl, enc_layers=6, dec_layers=6,
+        lr_backbone=1e-5, bbox_loss_coef=5, giou_loss_coef=2, sted_loss_coef=10, guided_attn_loss_coef=1, sigma=1,
+        device="cuda", hidden_dim=256, nheads=8, dim_feedforward=2048, backbone="resnet101", dilation=False,
+        position_embedding="sine")
+
+
+_MODELS = {}
+
+
+def _model(cfg):
+    from tubedetr_b200 import build_model
+    key = (cfg["stride"], tuple(cfg["flags"]))
+    if key not in _MODELS:
+        model, crit, wd = build_model(_args(cfg))
+        sd = state_dict()
+        model.load_state_dict({k: sd[k] for k in model.state_dict()}, strict=True)  # --no_fast drops fast_* keys
+        _MODELS[key] = (model.cuda().eval(), crit, wd)
+    return _MODELS[key]
+
+
+def _run(cfg):
+    from tubedetr_b200 import NestedTensor
+    model, crit, wd = _model(cfg)
+    b = batch_for(cfg)
+    samples = NestedTensor(b["frames_slow"].cuda(), b["mask_slow"].cuda())
+    fast = NestedTensor(b["frames_fast"].cuda(), b["mask_fast"].cuda())
+    caps = (b["input_ids"].cuda(), b["attention_mask"].cuda())
+    mc = model(samples, cfg["durations"], caps, encode_and_save=True, samples_fast=fast if model.fast else None)
+    out = model(samples, cfg["durations"], caps, encode_and_save=False, memory_cache=mc)
+    return model, crit, wd, b, mc, out
+
+
+def _err(a, b):
+    return (a.float().cpu() - b.float().cpu()).abs().max().item()
+
+
+def _log(msg):
+    os.makedirs(REPORT, exist_ok=True)
+    with open(os.path.join(REPORT, "model_parity.txt"), "a") as f:
+        f.write(msg + "\n")
+    print(msg)
+
+
+def test_backbone_features_match_reference():
+    g = load_gold("cfg1")
+    model, *_ = _model(g["cfg"])
+    b = batch_for(g["cfg"])
+    with torch.no_grad():
+        W = model._engine.prepare(model._backbone_tensors())
+        feat, h, w, _ = model._engine.forward(b["frames_slow"][:1].cuda(), W, save=False, tag="t")
+    ref = g["feat_slow0"][0].permute(1, 2, 0).reshape(h * w, 2048)
+    e = _err(feat, ref)
+    _log(f"backbone feat: max err {e:.4g} (ref absmax {ref.abs().max():.3f}, mean {ref.abs().mean():.3f})")
+    assert e <= 3e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg1b", "nofast", "notsa"])
+def test_forward_matches_reference(name):
+    g = load_gold(name)
+    with torch.no_grad():
+        model, crit, wd, b, mc, out = _run(g["cfg"])
+    for k in ("mask", "query_mask", "text_attention_mask"):
+        assert torch.equal(mc[k].cpu(), g[k]), k
+    for k in ("pos_embed", "query_embed"):
+        assert _err(mc[k], g[k]) < 1e-4, k
+    e_mem = _err(mc["img_memory"], g["img_memory"])
+    e_box = _err(out["pred_boxes"], g["pred_boxes"])
+    e_sted = _err(out["pred_sted"], g["pred_sted"])
+    e_aux = _err(torch.stack([a["pred_boxes"] for a in out["aux_outputs"]]), g["aux_pred_boxes"])
+    _log(f"{name}: img_memory err {e_mem:.4g} (absmax {g['img_memory'].abs().max():.3f}) pred_boxes {e_box:.4g} "
+         f"pred_sted {e_sted:.4g} (absmax {g['pred_sted'].abs().max():.3f}) aux_boxes {e_aux:.4g}")
+    assert out["pred_boxes"].shape == g["pred_boxes"].shape and out["pred_sted"].shape == g["pred_sted"].shape
+    assert e_box <= 2e-2 and e_aux <= 2e-2
+    assert e_sted <= 2e-2 * max(1.0, g["pred_sted"].abs().max().item())
+    assert e_mem <= 3e-2 * g["img_memory"].abs().max().item()
+    if "weights" in g and name != "notsa":
+        e_w, e_cw = _err(out["weights"], g["weights"]), _err(out["ca_weights"], g["ca_weights"])
+        _log(f"{name}: weights err {e_w:.4g} ca_weights err {e_cw:.4g}")
+        assert e_w <= 2e-2 and e_cw <= 2e-2
+
+
+@pytest.mark.parametrize("name", ["cfg1b", "cfg1"])
+def test_losses_and_gradients_match_reference(name):
+    g = load_gold(name)
+    model, crit, wd, b, mc, out = _run(g["cfg"])
+    keep = b["keep"].cuda()
+    o = dict(out, pred_boxes=out["pred_boxes"][keep],
+             aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in out["aux_outputs"]])
+    targets = [{"boxes": bx[None].cuda()} for bx in b["target_boxes"]]
+    losses = crit(o, targets, b["inter_idx"], b["time_mask"].cuda())
+    total = sum(losses[k] * wd[k] for k in losses if k in wd)
+    _log(f"{name}: total loss {total.item():.5f} vs reference {g['loss_total'].item():.5f}")
+    assert abs(total.item() - g["loss_total"].item()) <= 2e-2 * abs(g["loss_total"].item())
+    for k, v in g["losses"].items():
+        assert abs(losses[k].item() - v.item()) <= 3e-2 * max(abs(v.item()), 0.05), (k, losses[k].item(), v.item())
+    model.zero_grad()
+    total.backward()
+    worst = []
+    checked = 0
+    for k, p in model.named_parameters():
+        if k not in g["grad_norm"]:
+            assert p.grad is None or not p.requires_grad or p.grad.abs().max() == 0 or "pooler" in k, k
+            continue
+        assert p.grad is not None, k
+        ref_n = g["grad_norm"][k]
+        got_n = p.grad.float().norm().item()
+        f = p.grad.flatten()
+        step = max(f.numel() // 64, 1)
+        samp = f[::step][:64].float().cpu()
+        ref_s = g["grad_sample"][k]
+        rel = abs(got_n - ref_n) / max(ref_n, 1e-6)
+        cos = torch.nn.functional.cosine_similarity(samp, ref_s, dim=0).item() if ref_s.norm() > 0 else 1.0
+        worst.append((rel, cos, k, got_n, ref_n))
+        checked += 1
+    worst.sort(reverse=True)
+    for rel, cos, k, got_n, ref_n in worst[:12]:
+        _log(f"{name}: grad {k}: norm {got_n:.4g} vs {ref_n:.4g} (rel {rel:.3f}) sample-cos {cos:.4f}")
+    assert checked > 300
+    bad = [w for w in worst if w[0] > 0.10 and w[4] > 1e-4]
+    assert len(bad) <= 0.02 * checked, bad[:10]
+    med = sorted(w[0] for w in worst)[len(worst) // 2]
+    _log(f"{name}: grad-norm rel err median {med:.4f}, params checked {checked}")
+    assert med < 0.03

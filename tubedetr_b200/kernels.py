@@ -1,0 +1,77 @@
+"""Python marshalling for the non-GEMM C-ABI entry points (no math here)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+_i64 = C.c_int64
+_f = C.c_float
+
+
+def stem_im2col(x, col, N, H, W):
+    check(lib().tdb_stem_im2col(ptr(x), ptr(col), N, H, W, stream_ptr()), "stem_im2col")
+
+
+def maxpool3x3s2(x, y, N, H, W, Cc):
+    check(lib().tdb_maxpool3x3s2(ptr(x), ptr(y), N, H, W, Cc, stream_ptr()), "maxpool")
+
+
+def im2col3x3s2(x, col, N, H, W, Cc):
+    check(lib().tdb_im2col3x3s2(ptr(x), ptr(col), N, H, W, Cc, stream_ptr()), "im2col3x3s2")
+
+
+def col2im3x3s2_mask(dcol, ymask, dx, N, H, W, Cc):
+    check(lib().tdb_col2im3x3s2_mask(ptr(dcol), ptr(ymask), ptr(dx), N, H, W, Cc, stream_ptr()), "col2im3x3s2")
+
+
+def subsample2(x, y, N, H, W, Cc):
+    check(lib().tdb_subsample2(ptr(x), ptr(y), N, H, W, Cc, stream_ptr()), "subsample2")
+
+
+def upsample2_zero(y, x, N, H, W, Cc):
+    check(lib().tdb_upsample2_zero(ptr(y), ptr(x), N, H, W, Cc, stream_ptr()), "upsample2_zero")
+
+
+def prep_weight(w, out, out_scaled, rowscale, Cout, Cin, taps, Kpad):
+    check(lib().tdb_prep_weight(ptr(w), ptr(out), ptr(out_scaled), ptr(rowscale), Cout, Cin, taps, Kpad, stream_ptr()),
+          "prep_weight")
+
+
+def cast_add_bf16(x, add, y):
+    check(lib().tdb_cast_add_bf16(ptr(x), ptr(add), ptr(y), _i64(x.numel()), stream_ptr()), "cast_add_bf16")
+
+
+def layernorm_fwd(x, r, gamma, beta, pos, y, y_bf, ypos_bf, mean, rstd, rows, D, eps):
+    check(lib().tdb_layernorm_fwd(ptr(x), ptr(r), ptr(gamma), ptr(beta), ptr(pos), ptr(y), ptr(y_bf), ptr(ypos_bf),
+                                  ptr(mean), ptr(rstd), rows, D, _f(eps), stream_ptr()), "layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dgamma, dbeta, rows, D, accumulate=False):
+    nb = int(lib().tdb_layernorm_bwd_blocks(rows))
+    partial = torch.empty(nb * 2 * D, dtype=torch.float32, device=dy.device)
+    check(lib().tdb_layernorm_bwd(ptr(dy), ptr(x), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), ptr(dz), ptr(dgamma),
+                                  ptr(dbeta), ptr(partial), rows, D, int(accumulate), stream_ptr()), "layernorm_bwd")
+
+
+def colsum_bf16(x, out, accumulate=False):
+    rows, N = x.shape
+    nparts = max(1, min(64, rows // 64))
+    partial = torch.empty(nparts * N, dtype=torch.float32, device=x.device)
+    check(lib().tdb_colsum_bf16(ptr(x), _i64(x.stride(0)), rows, N, ptr(partial), nparts, ptr(out), int(accumulate),
+                                stream_ptr()), "colsum_bf16")
+    return out
+
+
+def mha_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale):
+    """q,k,v: 2-D bf16 views [B*L, >=H*32] (row stride = .stride(0)); kpm uint8 [B,Lk] or None."""
+    check(lib().tdb_mha_fwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(kpm),
+                            ptr(o), _i64(o.stride(0)), ptr(p), ptr(pbar), B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_fwd")
+
+
+def mha_bwd(q, k, v, dout, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale):
+    check(lib().tdb_mha_bwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)),
+                            ptr(dout), _i64(dout.stride(0)), ptr(p), ptr(dpbar), ptr(ds),
+                            ptr(dq), _i64(dq.stride(0)), ptr(dk), _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)),
+                            B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_bwd")

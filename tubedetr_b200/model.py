@@ -1,0 +1,583 @@
+"""Drop-in TubeDETR module, SetCriterion and build() on the B200 kernels.
+
+Boundary kept from the reference:
+  * TubeDETR.forward(samples, durations, captions, encode_and_save=True, memory_cache=None, samples_fast=None)
+    -- reference models/tubedetr.py:93-101; two-phase protocol of engine.py:67-80; memory_cache keys of
+    models/transformer.py:448-458; output keys of models/tubedetr.py:223-254.
+  * SetCriterion(losses, sigma).forward(outputs, targets, inter_idx, time_mask) -- models/tubedetr.py:257-460.
+  * build(args) -> (model, criterion, weight_dict) -- models/tubedetr.py:463-506.
+  * state_dict names/shapes identical to the reference (923 entries) so its checkpoints load with strict=True.
+Internals are NOT the reference's: activations are batch-major pixel/token rows ([frames*tokens, C]), all convolutions
+and linear layers run on the tcgen05 GEMM, attention / LayerNorm on the kernels of libtdb.so, and the per-clip Python
+loops of the reference (tubedetr.py:167-179, transformer.py:275-308, 400-417) are single gathers.
+Only the reference default path is implemented (temporal stride > 0, fast_mode "", sine embeddings); other flag values
+are rejected loudly in build().  Dropout is not applied yet (eval-mode numerics; DESIGN.md "open items").
+"""
+import math
+import zlib
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+from . import ops
+from .resnet import STAGES, ResNet101Engine
+
+D_MODEL, NHEAD, DFF = 256, 8, 2048
+
+
+class NestedTensor(object):
+    """Same container as reference util/misc.py:106-120 (tensors + bool pad mask)."""
+
+    def __init__(self, tensors, mask):
+        self.tensors = tensors
+        self.mask = mask
+
+    def to(self, *args, **kwargs):
+        return type(self)(self.tensors.to(*args, **kwargs), self.mask.to(*args, **kwargs) if self.mask is not None else None)
+
+    def decompose(self):
+        return self.tensors, self.mask
+
+    @classmethod
+    def from_tensor_list(cls, clips):
+        from .synthetic import pack_clips
+        return cls(*pack_clips(clips))
+
+
+# ----------------------------------------------------------------------------- parameter containers (names only)
+class _Conv(nn.Module):
+    def __init__(self, cin, cout, k, bias=False, trainable=True):
+        super().__init__()
+        w = torch.empty(cout, cin, k, k)
+        nn.init.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")
+        self.weight = nn.Parameter(w, requires_grad=trainable)
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class _FrozenBN(nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        self.register_buffer("weight", torch.ones(n))
+        self.register_buffer("bias", torch.zeros(n))
+        self.register_buffer("running_mean", torch.zeros(n))
+        self.register_buffer("running_var", torch.ones(n))
+
+    def _load_from_state_dict(self, state_dict, prefix, *a, **k):
+        state_dict.pop(prefix + "num_batches_tracked", None)
+        super()._load_from_state_dict(state_dict, prefix, *a, **k)
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, cin, width, first, trainable):
+        super().__init__()
+        self.conv1, self.bn1 = _Conv(cin, width, 1, trainable=trainable), _FrozenBN(width)
+        self.conv2, self.bn2 = _Conv(width, width, 3, trainable=trainable), _FrozenBN(width)
+        self.conv3, self.bn3 = _Conv(width, width * 4, 1, trainable=trainable), _FrozenBN(width * 4)
+        if first:
+            self.downsample = nn.Sequential(_Conv(cin, width * 4, 1, trainable=trainable), _FrozenBN(width * 4))
+
+
+class _Body(nn.Module):
+    def __init__(self, train_backbone=True):
+        super().__init__()
+        self.conv1, self.bn1 = _Conv(3, 64, 7, trainable=False), _FrozenBN(64)
+        cin = 64
+        for li, (width, nb, _) in enumerate(STAGES, start=1):
+            tr = train_backbone and li >= 2  # reference models/backbone.py:82-89
+            setattr(self, f"layer{li}", nn.Sequential(*[_Bottleneck(cin if b == 0 else width * 4, width, b == 0, tr)
+                                                        for b in range(nb)]))
+            cin = width * 4
+
+
+class _BackboneBase(nn.Module):
+    def __init__(self, train_backbone):
+        super().__init__()
+        self.body = _Body(train_backbone)
+        self.num_channels = 2048
+
+
+class _PosSine(nn.Module):
+    """reference models/position_encoding.py:52-94 with N_steps=128, normalize=True."""
+
+    def forward(self, mask):
+        nm = (~mask).float()
+        y, x = nm.cumsum(1), nm.cumsum(2)
+        y = y / (y[:, -1:, :] + 1e-6) * (2 * math.pi)
+        x = x / (x[:, :, -1:] + 1e-6) * (2 * math.pi)
+        i = torch.arange(128, dtype=torch.float32, device=mask.device)
+        dim_t = 10000.0 ** (2 * torch.div(i, 2, rounding_mode="floor") / 128)
+
+        def enc(e):
+            pe = e[..., None] / dim_t
+            return torch.stack((pe[..., 0::2].sin(), pe[..., 1::2].cos()), dim=-1).flatten(-2)
+
+        return torch.cat((enc(y), enc(x)), dim=-1)  # (N,h,w,256) channel-last
+
+
+class _Lin(nn.Module):
+    def __init__(self, cin, cout, xavier=False, zero=False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        self.bias = nn.Parameter(torch.zeros(cout))
+        if zero:
+            nn.init.zeros_(self.weight)
+        elif xavier:
+            nn.init.xavier_uniform_(self.weight)
+        else:
+            nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+            nn.init.uniform_(self.bias, -1 / math.sqrt(cin), 1 / math.sqrt(cin))
+
+
+class _LN(nn.Module):
+    def __init__(self, d, eps=1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d))
+        self.bias = nn.Parameter(torch.zeros(d))
+        self.eps = eps
+
+
+class _MHA(nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = _Lin(d, d, xavier=True)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class _EncLayer(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.self_attn = _MHA(D_MODEL)
+        self.linear1, self.linear2 = _Lin(D_MODEL, DFF, xavier=True), _Lin(DFF, D_MODEL, xavier=True)
+        self.norm1, self.norm2 = _LN(D_MODEL), _LN(D_MODEL)
+
+
+class _DecLayer(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.self_attn, self.cross_attn_image = _MHA(D_MODEL), _MHA(D_MODEL)
+        self.linear1, self.linear2 = _Lin(D_MODEL, DFF, xavier=True), _Lin(DFF, D_MODEL, xavier=True)
+        self.norm1, self.norm3, self.norm4 = _LN(D_MODEL), _LN(D_MODEL), _LN(D_MODEL)
+
+
+class _Stack(nn.Module):
+    def __init__(self, cls, n, final_norm):
+        super().__init__()
+        self.layers = nn.ModuleList([cls() for _ in range(n)])
+        if final_norm:
+            self.norm = _LN(D_MODEL)
+
+
+class _TimeSine(nn.Module):
+    def __init__(self, max_len, d):
+        super().__init__()
+        from .weights import _time_sine
+        self.register_buffer("te", _time_sine(max_len, d))
+
+
+class _Resizer(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc = _Lin(768, D_MODEL)
+        self.layer_norm = _LN(D_MODEL, eps=1e-12)  # reference models/transformer.py:765
+
+
+class _MLP(nn.Module):
+    def __init__(self, din, dh, dout, n):
+        super().__init__()
+        h = [dh] * (n - 1)
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip([din] + h, h + [dout]))
+
+    def forward(self, x):
+        for i, l in enumerate(self.layers):
+            x = l(x)
+            if i < len(self.layers) - 1:
+                x = F.relu(x)
+        return x
+
+
+class HashTokenizer:
+    """Offline stand-in when the roberta-base vocabulary is not on disk: deterministic word hashing into RoBERTa's id
+    range with BOS=0 / EOS=2 / PAD=1.  (The real RobertaTokenizerFast is used when available.)"""
+
+    def __call__(self, texts, device):
+        toks = [[0] + [3 + zlib.crc32(w.encode()) % 50000 for w in t.lower().split()] + [2] for t in texts]
+        L = max(len(t) for t in toks)
+        ids = torch.full((len(toks), L), 1, dtype=torch.long)
+        am = torch.zeros(len(toks), L, dtype=torch.long)
+        for i, t in enumerate(toks):
+            ids[i, :len(t)] = torch.tensor(t)
+            am[i, :len(t)] = 1
+        return ids.to(device), am.to(device)
+
+
+def _make_text_encoder(name="roberta-base"):
+    from transformers import RobertaConfig, RobertaModel, RobertaTokenizerFast
+    try:
+        tok = RobertaTokenizerFast.from_pretrained(name, local_files_only=True)
+        enc = RobertaModel.from_pretrained(name, local_files_only=True)
+
+        def tokenize(texts, device):
+            be = tok.batch_encode_plus(texts, padding="longest", return_tensors="pt").to(device)
+            return be["input_ids"], be["attention_mask"]
+        return enc, tokenize
+    except Exception:
+        cfg = RobertaConfig(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, pad_token_id=1,
+                            bos_token_id=0, eos_token_id=2, layer_norm_eps=1e-5)
+        return RobertaModel(cfg), HashTokenizer()
+
+
+class Transformer(nn.Module):
+    """Parameter container + the video-text encoder / space-time decoder drivers."""
+
+    def __init__(self, num_encoder_layers=6, num_decoder_layers=6, video_max_len=200, stride=5, no_tsa=False, fast=True):
+        super().__init__()
+        self.encoder = _Stack(_EncLayer, num_encoder_layers, final_norm=False)
+        self.decoder = _Stack(_DecLayer, num_decoder_layers, final_norm=True)
+        self.time_embed = _TimeSine(video_max_len, D_MODEL)
+        self.fast = fast
+        if fast:
+            self.fast_encoder = _Lin(D_MODEL, D_MODEL)
+            self.fast_residual = _Lin(D_MODEL, D_MODEL, zero=True)  # reference zero-inits it (transformer.py:173-174)
+        self.text_encoder, self._tokenize = _make_text_encoder()
+        self.resizer = _Resizer()
+        self.d_model, self.nhead, self.stride, self.no_tsa = D_MODEL, NHEAD, stride, no_tsa
+        self.video_max_len = video_max_len
+
+    def _reset_temporal_parameters(self):  # called by reference main.py:545 after loading MDETR weights
+        if self.fast:
+            nn.init.zeros_(self.fast_residual.weight)
+            nn.init.zeros_(self.fast_residual.bias)
+
+    # ---- one post-norm encoder layer on token rows (reference transformer.py:629-646)
+    def _enc_layer(self, l, x32, xb, xpb, pos, kpm, n, S, need_pos):
+        a = l.self_attn
+        qk, v = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((0, 512), (512, 768)), xpb, xb)
+        o, _ = ops.mha(qk, None, v, kpm, n, NHEAD, S, S, 32 ** -0.5, packed=True)
+        att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
+        x32, xb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias)
+        hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True)
+        f = ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True)
+        if need_pos:
+            return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias, pos)
+        return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias) + (None,)
+
+    # ---- one decoder layer (reference transformer.py:684-751); rows are (b,t) batch-major
+    def _dec_layer(self, l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S):
+        a = l.self_attn
+        if self.no_tsa:  # each time query attends to itself only (transformer.py:701-711)
+            (v,) = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((512, 768),), xb)
+            att = ops.linear(v, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
+            w = torch.ones(B * T, 1, 1, dtype=torch.float32, device=x32.device)
+        else:
+            qk, v = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((0, 512), (512, 768)), xqb, xb)
+            o, w = ops.mha(qk, None, v, kpm_q, B, NHEAD, T, T, 32 ** -0.5, packed=True)
+            att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
+        x32, xb, xqb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, qp)
+        c = l.cross_attn_image
+        q, k, v = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256), (256, 512), (512, 768)), xqb, mempb, memb)
+        o, cw = ops.mha(q, k, v, kpm_mem, B * T, NHEAD, 1, S, 32 ** -0.5)
+        att = ops.linear(o, c.out_proj.weight, c.out_proj.bias, out_fp32=True)
+        x32, xb = ops.add_layernorm(x32, att, l.norm3.weight, l.norm3.bias)
+        hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True)
+        f = ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True)
+        x32, xb, xqb = ops.add_layernorm(x32, f, l.norm4.weight, l.norm4.bias, qp)
+        return x32, xb, xqb, w, cw
+
+
+class TubeDETR(nn.Module):
+    def __init__(self, num_queries=1, aux_loss=True, video_max_len=200, stride=5, guided_attn=True, fast=True,
+                 fast_mode="", sted=True, no_tsa=False, enc_layers=6, dec_layers=6, train_backbone=True):
+        super().__init__()
+        assert num_queries == 1 and fast_mode == "" and stride > 0, "only the reference default path is implemented"
+        self.num_queries = num_queries
+        self.transformer = Transformer(enc_layers, dec_layers, video_max_len, stride, no_tsa, fast)
+        self.bbox_embed = _MLP(D_MODEL, D_MODEL, 4, 3)
+        self.query_embed = nn.Embedding(num_queries, D_MODEL)
+        self.input_proj = _Conv(2048, D_MODEL, 1, bias=True)
+        self.backbone = nn.Sequential(_BackboneBase(train_backbone), _PosSine())
+        self.backbone.num_channels = 2048
+        self.aux_loss, self.video_max_len, self.stride = aux_loss, video_max_len, stride
+        self.guided_attn, self.fast, self.fast_mode, self.sted = guided_attn, fast, fast_mode, sted
+        if sted:
+            self.sted_embed = _MLP(D_MODEL, D_MODEL, 2, 2)
+            self.sted_embed.dropout = 0.5  # reference applies Dropout(0.5) here in train mode (not applied yet)
+        self._engine = ResNet101Engine()
+
+    # ------------------------------------------------------------------ helpers
+    def _backbone_tensors(self):
+        return {"backbone.0.body." + k: v for k, v in list(self.backbone[0].body.named_parameters()) +
+                list(self.backbone[0].body.named_buffers())}
+
+    @staticmethod
+    def _resize_mask(mask, h, w):
+        H, W = mask.shape[-2:]
+        ii = (torch.arange(h, device=mask.device) * (H / h)).floor().long().clamp(max=H - 1)
+        jj = (torch.arange(w, device=mask.device) * (W / w)).floor().long().clamp(max=W - 1)
+        return mask[:, ii][:, :, jj]
+
+    def _tokenize(self, captions, device):
+        if isinstance(captions, (tuple, list)) and len(captions) == 2 and torch.is_tensor(captions[0]):
+            return captions[0].to(device), captions[1].to(device)  # pre-tokenised (input_ids, attention_mask)
+        return self.transformer._tokenize(list(captions), device)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, samples, durations, captions, encode_and_save=True, memory_cache=None, samples_fast=None):
+        _lib.lib()  # fail loudly if libtdb.so is missing: there is no PyTorch fallback
+        if encode_and_save:
+            assert memory_cache is None
+            return self._encode(samples, durations, captions, samples_fast)
+        assert memory_cache is not None
+        return self._decode(memory_cache)
+
+    def _encode(self, samples, durations, captions, samples_fast):
+        tr = self.transformer
+        frames, fmask = samples.decompose()
+        if not frames.is_cuda:
+            raise RuntimeError("tubedetr_b200 runs on CUDA (sm_100a) only; move the inputs to the GPU")
+        dev = frames.device
+        B, T, k = len(durations), max(durations), self.stride
+        n_clips = math.ceil(T / k)
+        sd = self._backbone_tensors()
+        W = self._engine.prepare(sd)
+        names = [n for n, p in sd.items() if isinstance(p, nn.Parameter) and p.requires_grad]
+        if names and torch.is_grad_enabled():
+            feat = ops.BackboneFn.apply(frames.float(), self._engine, W, names, "slow", *[sd[n] for n in names])
+            h, w = self._engine.last_hw
+        else:
+            feat, h, w, _ = self._engine.forward(frames.float(), W, save=False, tag="slow")
+        n, HW = frames.shape[0], h * w
+        assert n == B * n_clips, "with temporal stride every video of the batch needs the same number of clips"
+        with torch.no_grad():
+            m_s = self._resize_mask(fmask, h, w).clone()
+            m_s[:, 0, 0] = False
+            pos = self.backbone[1](m_s).view(n, HW, D_MODEL)
+            dur = torch.tensor(durations, device=dev)
+            tt = torch.arange(T, device=dev)
+            valid = tt[None] < dur[:, None]
+            clip_of_t = (torch.arange(B, device=dev)[:, None] * n_clips + tt[None] // k).flatten()
+        Win, bin_ = self.input_proj.weight.view(D_MODEL, 2048), self.input_proj.bias
+        src = ops.linear(feat, Win, bin_, out_fp32=True).view(n, HW, D_MODEL)
+
+        fsrc = None
+        if self.fast:
+            ff, fm_ = samples_fast.decompose()
+            with torch.no_grad():
+                feat_f, hf, wf, _ = self._engine.forward(ff.float(), W, save=False, tag="fast")
+                m_f = self._resize_mask(fm_, hf, wf)
+            fsrc_all = ops.linear(feat_f, Win, bin_).view(-1, HW, D_MODEL)       # input_proj gets weight-grad here too
+            ragged = any(d != T for d in durations)
+            if ragged:
+                idx = ((torch.cumsum(dur, 0) - dur)[:, None] + tt[None]).clamp(max=ff.shape[0] - 1).flatten()
+                fsrc = fsrc_all[idx] * valid.flatten()[:, None, None].to(fsrc_all.dtype)
+                m_t = torch.where(valid.flatten()[:, None], m_f.flatten(1)[idx], torch.ones((), dtype=torch.bool, device=dev))
+            else:
+                fsrc, m_t = fsrc_all, m_f.flatten(1)
+        else:
+            m_t = torch.where(valid.flatten()[:, None], m_s.flatten(1)[clip_of_t], torch.ones((), dtype=torch.bool, device=dev))
+        m_t = m_t.clone()
+        m_t[:, 0] = False
+
+        # time queries + masks (reference transformer.py:211-238)
+        qp = (self.query_embed.weight[0][None, None, :] + tr.time_embed.te[:T, 0][None]).expand(B, T, D_MODEL)
+        q_kpm = ~valid
+        q_kpm[:, 0] = False
+
+        # text (library call, reference transformer.py:250-263) + resizer on our kernels
+        ids, am = self._tokenize(captions, dev)
+        hid = tr.text_encoder(input_ids=ids, attention_mask=am).last_hidden_state        # (B,L,768)
+        L = hid.shape[1]
+        r = ops.linear(hid.reshape(B * L, 768).to(torch.bfloat16), tr.resizer.fc.weight, tr.resizer.fc.bias, out_fp32=True)
+        txt, _ = ops.add_layernorm(r, None, tr.resizer.layer_norm.weight, tr.resizer.layer_norm.bias, eps=1e-12)
+        txt = txt.view(B, L, D_MODEL)
+        txt_kpm = am.ne(1)
+        txt_rep = txt.repeat_interleave(n_clips, 0)                                      # (n,L,d)
+
+        S = HW + L
+        x32 = torch.cat([src, txt_rep], 1).reshape(n * S, D_MODEL)
+        pe = torch.cat([pos, torch.zeros(n, L, D_MODEL, device=dev)], 1).reshape(n * S, D_MODEL)
+        kpm_enc_b = torch.cat([m_s.flatten(1), txt_kpm.repeat_interleave(n_clips, 0)], 1)
+        kpm_enc = kpm_enc_b.to(torch.uint8).contiguous()
+        xb, xpb = x32.to(torch.bfloat16), (x32 + pe).to(torch.bfloat16)
+        nl = len(tr.encoder.layers)
+        for i, l in enumerate(tr.encoder.layers):
+            x32, xb, xpb = tr._enc_layer(l, x32, xb, xpb, pe, kpm_enc, n, S, need_pos=i < nl - 1)
+
+        # temporal replication: frame (b,t) <- clip (b, t//k)  (reference transformer.py:393-427)
+        enc = x32.view(n, S, D_MODEL)
+        mem = enc[clip_of_t]
+        mem_pos = pe.view(n, S, D_MODEL)[clip_of_t]
+        kpm_dec = torch.cat([m_t, txt_kpm.repeat_interleave(T, 0)], 1)
+        kpm_dec[:, 0] = False
+        if self.fast:
+            BT = B * T
+            fm = ops.linear(fsrc.reshape(BT * HW, D_MODEL), tr.fast_encoder.weight, tr.fast_encoder.bias)
+            z = (mem[:, :HW].reshape(BT * HW, D_MODEL) + fm.float()).to(torch.bfloat16)
+            upd = ops.linear(z, tr.fast_residual.weight, tr.fast_residual.bias, out_fp32=True)
+            mem = torch.cat([mem[:, :HW] + upd.view(BT, HW, D_MODEL), mem[:, HW:]], 1)
+        return {
+            "text_memory_resized": txt_rep.transpose(0, 1), "text_memory": mem[:, HW:].transpose(0, 1),
+            "text_attention_mask": txt_kpm.repeat_interleave(n_clips, 0), "tokenized": {"input_ids": ids, "attention_mask": am},
+            "img_memory": mem.transpose(0, 1), "mask": kpm_dec, "pos_embed": mem_pos.transpose(0, 1),
+            "query_embed": qp.transpose(0, 1), "query_mask": q_kpm,
+        }
+
+    def _decode(self, mc):
+        tr = self.transformer
+        mem = mc["img_memory"].transpose(0, 1).contiguous()          # (B*T,S,d) fp32
+        mem_pos = mc["pos_embed"].transpose(0, 1)
+        qp = mc["query_embed"].transpose(0, 1).contiguous()          # (B,T,d)
+        B, T, _ = qp.shape
+        BT, S, _ = mem.shape
+        kpm_mem = mc["mask"].to(torch.uint8).contiguous()
+        kpm_q = mc["query_mask"].to(torch.uint8).contiguous()
+        memb = mem.reshape(BT * S, D_MODEL).to(torch.bfloat16)
+        mempb = (mem + mem_pos).reshape(BT * S, D_MODEL).to(torch.bfloat16)
+        qp = qp.reshape(B * T, D_MODEL).float().contiguous()
+        x32 = torch.zeros(B * T, D_MODEL, device=mem.device)          # tgt = 0 (reference transformer.py:463-464)
+        xb, xqb = x32.to(torch.bfloat16), qp.to(torch.bfloat16)
+        dn = tr.decoder.norm
+        hs, ws, cws = [], [], []
+        for l in tr.decoder.layers:
+            x32, xb, xqb, w, cw = tr._dec_layer(l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S)
+            hs.append(ops.add_layernorm(x32, None, dn.weight, dn.bias)[0])
+            ws.append(w)
+            cws.append(cw)
+        hs = torch.stack(hs).view(len(hs), B, T, D_MODEL)
+        out = {}
+        boxes = self.bbox_embed(hs.flatten(1, 2)).sigmoid()
+        out["pred_boxes"] = boxes[-1]
+        if self.sted:
+            sted = self.sted_embed(hs)
+            out["pred_sted"] = sted[-1]
+        if self.guided_attn:
+            out["weights"], out["ca_weights"] = ws[-1], cws[-1]
+        if self.aux_loss:
+            out["aux_outputs"] = []
+            for i in range(len(ws) - 1):
+                a = {"pred_boxes": boxes[i]}
+                if self.sted:
+                    a["pred_sted"] = sted[i]
+                if self.guided_attn:
+                    a["weights"], a["ca_weights"] = ws[i], cws[i]
+                out["aux_outputs"].append(a)
+        return out
+
+
+# ----------------------------------------------------------------------------- criterion
+def _box_cxcywh_to_xyxy(b):
+    cx, cy, w, h = b.unbind(-1)
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+
+
+def _giou_pairs(a, b):
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    wh = (torch.min(a[:, 2:], b[:, 2:]) - torch.max(a[:, :2], b[:, :2])).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    union = area_a + area_b - inter
+    whc = (torch.max(a[:, 2:], b[:, 2:]) - torch.min(a[:, :2], b[:, :2])).clamp(min=0)
+    areac = whc[:, 0] * whc[:, 1]
+    return inter / union - (areac - union) / areac
+
+
+class SetCriterion(nn.Module):
+    """Same API and loss values as reference models/tubedetr.py:257-460 (L1 + GIoU on kept boxes, KL on start/end,
+    guided attention), computed pairwise instead of through an NxN GIoU matrix and without the .item() host sync."""
+
+    def __init__(self, losses, sigma=1):
+        super().__init__()
+        self.losses, self.sigma = losses, sigma
+
+    def prepare(self, targets, inter_idx=None, time_mask=None, device=None):
+        """Host-side part of the loss (target tensors, Gaussian start/end distributions, negative-frame map, the
+        num_boxes all-reduce of reference models/tubedetr.py:411-413).  Hoistable: set `criterion.static = prepare(...)`
+        to keep it out of a captured CUDA graph when targets do not change."""
+        dev = device or targets[0]["boxes"].device
+        num_boxes = torch.as_tensor([float(sum(len(t["boxes"]) for t in targets))], device=dev)
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(num_boxes)
+            world = torch.distributed.get_world_size()
+        prep = {"num_boxes": torch.clamp(num_boxes / world, min=1)[0],
+                "tgt_boxes": torch.cat([t["boxes"] for t in targets], 0)}
+        if inter_idx is not None and time_mask is not None:
+            pm = torch.zeros(time_mask.shape, dtype=torch.bool)
+            for k_, idx in enumerate(inter_idx):
+                if idx[0] >= 0:
+                    pm[k_, idx[0]:idx[1] + 1] = True
+            neg = pm.to(dev) | ~time_mask
+            prep["neg"], prep["nneg"] = neg, (~neg).sum(1) + 1e-6
+            tt = torch.arange(time_mask.shape[1])
+            gs = []
+            for c in range(2):
+                tgt = torch.tensor([x[c] for x in inter_idx])
+                g = (-((tt[None] - tgt[:, None]) ** 2) / (2 * self.sigma ** 2)).exp()
+                gs.append(F.normalize(g + 1e-6, p=1, dim=1).to(dev))
+            prep["gauss"] = gs
+        return prep
+
+    def forward(self, outputs, targets, inter_idx=None, time_mask=None):
+        prep = getattr(self, "static", None) or self.prepare(targets, inter_idx, time_mask, outputs["pred_boxes"].device)
+        losses = self._one(outputs, prep, time_mask)
+        for i, aux in enumerate(outputs.get("aux_outputs", [])):
+            losses.update({f"{k_}_{i}": v for k_, v in self._one(aux, prep, time_mask).items()})
+        return losses
+
+    def _one(self, o, prep, time_mask):
+        l, eps = {}, 1e-6
+        if "boxes" in self.losses:
+            pb, tb = o["pred_boxes"], prep["tgt_boxes"]
+            l["loss_bbox"] = (pb - tb).abs().sum() / prep["num_boxes"]
+            l["loss_giou"] = (1 - _giou_pairs(_box_cxcywh_to_xyxy(pb), _box_cxcywh_to_xyxy(tb))).sum() / prep["num_boxes"]
+        if "sted" in self.losses:
+            sted = o["pred_sted"].masked_fill(~time_mask[:, :, None], -1e32)
+            tot = 0
+            for c in range(2):
+                p = sted[:, :, c].softmax(1)
+                tot = tot + p * ((p + eps) / prep["gauss"][c]).log() * time_mask
+            l["loss_sted"] = tot.mean()
+        if "guided_attn" in self.losses:
+            ga = -(1 - o["weights"] + eps).log()
+            ga = ga.masked_fill(prep["neg"][:, :, None], 0)
+            l["loss_guided_attn"] = (ga.sum(2) / prep["nneg"][:, None]).sum(1).mean()
+        return l
+
+
+# ----------------------------------------------------------------------------- factory
+_UNSUPPORTED = {"fast_mode": "", "no_time_embed": False, "learn_time_embed": False, "dilation": False,
+                "position_embedding": "sine", "hidden_dim": 256, "nheads": 8, "dim_feedforward": 2048,
+                "num_queries": 1, "backbone": "resnet101", "pass_pos_and_query": True}
+
+
+def build(args):
+    """reference models/tubedetr.py:463-506; supports the default value of every architecture flag plus
+    --stride/--resolution/--no_fast/--no_tsa/--no_guided_attn/--no_sted/--no_aux_loss; anything else raises."""
+    for k_, v in _UNSUPPORTED.items():
+        if hasattr(args, k_) and getattr(args, k_) != v:
+            raise NotImplementedError(f"tubedetr_b200: --{k_}={getattr(args, k_)} is not implemented (only {v!r})")
+    if not getattr(args, "stride", 5):
+        raise NotImplementedError("tubedetr_b200: stride=0 (no temporal sampling) is not implemented")
+    model = TubeDETR(num_queries=args.num_queries, aux_loss=args.aux_loss, video_max_len=args.video_max_len_train,
+                     stride=args.stride, guided_attn=args.guided_attn, fast=args.fast, fast_mode=args.fast_mode,
+                     sted=args.sted, no_tsa=args.no_tsa, enc_layers=args.enc_layers, dec_layers=args.dec_layers,
+                     train_backbone=args.lr_backbone > 0)
+    if getattr(args, "freeze_backbone", False):
+        for p in model.backbone.parameters():
+            p.requires_grad_(False)
+    if getattr(args, "freeze_text_encoder", False):
+        for p in model.transformer.text_encoder.parameters():
+            p.requires_grad_(False)
+    weight_dict = {"loss_bbox": args.bbox_loss_coef, "loss_giou": args.giou_loss_coef, "loss_sted": args.sted_loss_coef}
+    if args.guided_attn:
+        weight_dict["loss_guided_attn"] = args.guided_attn_loss_coef
+    if args.aux_loss:
+        weight_dict.update({f"{k_}_{i}": v for i in range(args.dec_layers - 1) for k_, v in list(weight_dict.items())})
+    losses = (["boxes", "sted"] if args.sted else ["boxes"]) + (["guided_attn"] if args.guided_attn else [])
+    criterion = SetCriterion(losses=losses, sigma=args.sigma).to(torch.device(args.device))
+    return model, criterion, weight_dict

@@ -1,0 +1,231 @@
+"""torch.autograd glue around the C-ABI kernels.  Each Function only marshals buffers: forward and backward math
+runs in libtdb.so (tcgen05 GEMM, attention, LayerNorm kernels).  Activations that feed a GEMM are bf16, the residual
+stream and normalisation statistics are fp32, parameters/gradients stay fp32 (master weights)."""
+import torch
+
+from . import kernels as K
+from .gemm import effective_splits, gemm, splitk_reduce
+
+_WCACHE = {}
+
+
+def bf16_weight(w):
+    """bf16 copy of an fp32 parameter, refreshed when the parameter changes (optimizer steps bump _version)."""
+    key = (w.data_ptr(), tuple(w.shape))
+    ck = (w._version,)
+    ent = _WCACHE.get(key)
+    if ent is None or ent[0] != ck:
+        wb = ent[1] if (ent is not None and ent[1].shape == w.shape) else torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+        K.cast_add_bf16(w.detach().contiguous(), None, wb)
+        ent = (ck, wb)
+        _WCACHE[key] = ent
+    return ent[1]
+
+
+def _as_bf16(t):
+    return t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
+
+
+def wgrad_into(dy_b, x_b, out):
+    """out[N,K] (fp32, contiguous) = dy_b[R,N]^T @ x_b[R,K]   (both operands read MN-major by the GEMM)."""
+    R, N = dy_b.shape
+    Kd = x_b.shape[1]
+    tiles = ((N + 127) // 128) * max(1, Kd // 256 if Kd % 256 == 0 else Kd // 64)
+    want = max(1, min((2 * 148 + tiles - 1) // tiles, 64))
+    s = effective_splits(R, want)
+    part = torch.empty(s, N, Kd, dtype=torch.float32, device=dy_b.device)
+    gemm(dy_b, x_b, part, N, Kd, R, a_major=1, b_major=1, splits=want)
+    splitk_reduce(part, s, N, Kd, out)
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """y = relu?(x @ W^T + b): x bf16 [R,K], W fp32 [N,K] (bf16 copy cached), y bf16 or fp32 [R,N]."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu, out_fp32):
+        assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+        Wb = bf16_weight(W)
+        R, Kd = x.shape
+        N = W.shape[0]
+        y = torch.empty(R, N, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
+        gemm(x, Wb, y, R, N, Kd, bias=b, relu=relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x, W, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        Wb = bf16_weight(W)
+        dyb = _as_bf16(dy)
+        if ctx.relu:
+            dyb = dyb * (y > 0)
+        dyb = dyb.contiguous()
+        R, Kd = x.shape
+        N = W.shape[0]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(R, Kd, dtype=torch.bfloat16, device=x.device)
+            gemm(dyb, Wb, dx, R, Kd, N, b_major=1)
+        if ctx.needs_input_grad[1]:
+            dW = wgrad_into(dyb, x, torch.empty(N, Kd, dtype=torch.float32, device=x.device))
+        if ctx.needs_input_grad[2]:
+            db = K.colsum_bf16(dyb, torch.empty(N, dtype=torch.float32, device=x.device))
+        return dx, dW, db, None, None
+
+
+def linear(x, W, b, relu=False, out_fp32=False):
+    return LinearFn.apply(x, W, b, relu, out_fp32)
+
+
+class InProjFn(torch.autograd.Function):
+    """Packed attention in-projection (torch MultiheadAttention in_proj_weight [3d,d], in_proj_bias [3d]).
+    segs = ((lo, hi), ...) row ranges of W applied to xs[i]; returns one bf16 tensor per segment.
+    Reference call sites: models/transformer.py:637-640, 698-719, 734-740 (q/k share an input, v differs)."""
+
+    @staticmethod
+    def forward(ctx, W, b, segs, *xs):
+        Wb = bf16_weight(W)
+        outs = []
+        for (lo, hi), x in zip(segs, xs):
+            y = torch.empty(x.shape[0], hi - lo, dtype=torch.bfloat16, device=x.device)
+            gemm(x, Wb[lo:hi], y, x.shape[0], hi - lo, x.shape[1], bias=b[lo:hi])
+            outs.append(y)
+        ctx.segs = segs
+        ctx.save_for_backward(W, *xs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        W, *xs = ctx.saved_tensors
+        Wb = bf16_weight(W)
+        dW = torch.zeros_like(W) if ctx.needs_input_grad[0] else None
+        db = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device) if ctx.needs_input_grad[1] else None
+        dxs = []
+        for i, ((lo, hi), x, dy) in enumerate(zip(ctx.segs, xs, dys)):
+            if dy is None:
+                dxs.append(None)
+                continue
+            dyb = _as_bf16(dy).contiguous()
+            if dW is not None:
+                wgrad_into(dyb, x, dW[lo:hi])
+            if db is not None:
+                K.colsum_bf16(dyb, db[lo:hi])
+            if ctx.needs_input_grad[3 + i]:
+                dx = torch.empty_like(x)
+                gemm(dyb, Wb[lo:hi], dx, x.shape[0], x.shape[1], hi - lo, b_major=1)
+                dxs.append(dx)
+            else:
+                dxs.append(None)
+        return (dW, db, None) + tuple(dxs)
+
+
+def in_proj(W, b, segs, *xs):
+    return InProjFn.apply(W, b, tuple(segs), *xs)
+
+
+class MHAFn(torch.autograd.Function):
+    """Attention core on projected q/k/v (bf16 [B*L, 256]); returns (o bf16 [B*Lq,256], pbar fp32 [B,Lq,Lk]).
+    qk_packed: q and k are the two halves of one [R,512] tensor (self-attention)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, kpm, B, H, Lq, Lk, scale, packed):
+        if packed:
+            qv, kv = q[:, :256], q[:, 256:]
+        else:
+            qv, kv = q, k
+        o = torch.empty(B * Lq, H * 32, dtype=torch.bfloat16, device=q.device)
+        p = torch.empty(B, H, Lq, Lk, dtype=torch.float32, device=q.device)
+        pbar = torch.empty(B, Lq, Lk, dtype=torch.float32, device=q.device)
+        K.mha_fwd(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale)
+        ctx.cfg = (B, H, Lq, Lk, scale, packed)
+        ctx.save_for_backward(q, k if not packed else None, v, p)
+        return o, pbar
+
+    @staticmethod
+    def backward(ctx, do, dpbar):
+        q, k, v, p = ctx.saved_tensors
+        B, H, Lq, Lk, scale, packed = ctx.cfg
+        if do is None:
+            do = torch.zeros(B * Lq, H * 32, dtype=torch.bfloat16, device=q.device)
+        do = _as_bf16(do).contiguous()
+        if dpbar is not None:
+            dpbar = dpbar.contiguous().float()
+        ds = torch.empty_like(p)
+        dv = torch.empty_like(v)
+        if packed:
+            dqk = torch.empty_like(q)
+            K.mha_bwd(q[:, :256], q[:, 256:], v, do, p, dpbar, ds, dqk[:, :256], dqk[:, 256:], dv, B, H, Lq, Lk, scale)
+            return dqk, None, dv, None, None, None, None, None, None, None
+        dq, dk = torch.empty_like(q), torch.empty_like(k)
+        K.mha_bwd(q, k, v, do, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale)
+        return dq, dk, dv, None, None, None, None, None, None, None
+
+
+def mha(q, k, v, kpm, B, H, Lq, Lk, scale, packed=False):
+    return MHAFn.apply(q, k, v, kpm, B, H, Lq, Lk, scale, packed)
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x + r) over d=256 (fp32 statistics).  Returns (y fp32, y bf16, (y + pos) bf16 or None)."""
+
+    @staticmethod
+    def forward(ctx, x, r, gamma, beta, pos, eps):
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        rows, D = x.shape
+        if r is not None:
+            r = r.contiguous()
+            assert r.dtype == torch.float32
+        y = torch.empty_like(x)
+        yb = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
+        ypb = torch.empty_like(yb) if pos is not None else None
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        K.layernorm_fwd(x, r, gamma, beta, pos, y, yb, ypb, mean, rstd, rows, D, eps)
+        ctx.save_for_backward(x, r, gamma, mean, rstd)
+        ctx.has_r = r is not None
+        if ypb is None:
+            return y, yb
+        return y, yb, ypb
+
+    @staticmethod
+    def backward(ctx, dy, dyb, dypb=None):
+        x, r, gamma, mean, rstd = ctx.saved_tensors
+        rows, D = x.shape
+        g = None
+        for t in (dy, dyb, dypb):
+            if t is not None:
+                g = t.float() if g is None else g + t.float()
+        if g is None:
+            return None, None, None, None, None, None
+        g = g.contiguous()
+        dz = torch.empty_like(x)
+        dg = torch.empty(D, dtype=torch.float32, device=x.device)
+        db = torch.empty(D, dtype=torch.float32, device=x.device)
+        K.layernorm_bwd(g, x, r, gamma, mean, rstd, dz, dg, db, rows, D)
+        return dz, (dz if ctx.has_r else None), dg, db, None, None
+
+
+def add_layernorm(x, r, gamma, beta, pos=None, eps=1e-5):
+    return AddLayerNormFn.apply(x, r, gamma, beta, pos, eps)
+
+
+class BackboneFn(torch.autograd.Function):
+    """ResNet-101 layer4 features WITH grad for layer2-4 conv weights (reference models/backbone.py:82-89)."""
+
+    @staticmethod
+    def forward(ctx, frames, engine, W, names, tag, *params):
+        feat, h, w, bctx = engine.forward(frames, W, save=True, tag=tag)
+        ctx.engine, ctx.W, ctx.names, ctx.bctx = engine, W, names, bctx
+        ctx.save_for_backward(feat, *params)
+        ctx.hw = (h, w)
+        return feat
+
+    @staticmethod
+    def backward(ctx, g):
+        feat, *params = ctx.saved_tensors
+        g = (_as_bf16(g) * (feat > 0)).contiguous()
+        grads = {n: torch.empty_like(p, dtype=torch.float32) for n, p in zip(ctx.names, params)}
+        ctx.engine.backward(ctx.bctx, ctx.W, g, grads)
+        return (None, None, None, None, None) + tuple(grads[n] for n in ctx.names)

@@ -1,0 +1,226 @@
+"""ResNet-101 + FrozenBatchNorm2d feature extractor on the tcgen05 GEMM (forward, dgrad, wgrad).
+
+Replaces reference models/backbone.py:60-70 (FrozenBatchNorm2d), :73-124 (BackboneBase/Backbone over torchvision
+resnet101).  Topology restated from torchvision ResNet v1.5: stem 7x7/2 + maxpool, bottlenecks (3,4,23,3), stride on the
+3x3 conv of the first block of layer2-4.  Trainable: conv weights of layer2-4 only (reference :82-89).
+
+Data layout: NHWC bf16 "pixel rows" [N*H*W][C].  The input of every stride-1 3x3 conv lives in a zero-haloed
+[N*(H+2)*(W+2)][C] buffer so the convolution is 9 row-shifted taps of one GEMM.  FrozenBN is an epilogue
+(scale,shift per channel) in forward and folded into the weights (dgrad) / the split-K reduce (wgrad) in backward; ReLU
+backward is the `mask` epilogue of the producing dgrad GEMM, so no elementwise pass ever touches HBM on its own.
+This module only sequences kernel launches; every FLOP runs in libtdb.so.
+"""
+import torch
+
+from . import kernels as K
+from .gemm import REMAP_C2P, REMAP_P2C, effective_splits, gemm, splitk_reduce
+
+STAGES = ((64, 3, 1), (128, 4, 2), (256, 23, 2), (512, 3, 2))  # width, blocks, stride of first block
+BN_EPS = 1e-5
+
+
+def conv_out(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+class ResNet101Engine:
+    def __init__(self):
+        self._bufs = {}
+        self._wcache = {}
+        self._bn = None
+        self._bn_key = None
+        self.last_hw = None
+
+    def __deepcopy__(self, memo):  # EMA copies of the model (reference main.py:370) get a fresh, empty engine
+        return ResNet101Engine()
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, tag, shape, dtype=torch.bfloat16, zero=False, device="cuda"):
+        key = (tag, tuple(shape), dtype)
+        b = self._bufs.get(key)
+        if b is None:
+            b = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+            self._bufs[key] = b
+        return b
+
+    # ------------------------------------------------------------------ weights
+    def prepare(self, sd, prefix="backbone.0.body."):
+        """sd: name -> tensor (module parameters/buffers, fp32 cuda).  Builds bf16 GEMM-layout weights
+        (cached on tensor version) and folded FrozenBN scale/shift."""
+        names = [("conv1", "bn1", 3, 64, 49)]
+        for li, (width, nb, _) in enumerate(STAGES, start=1):
+            cin = 64 if li == 1 else STAGES[li - 2][0] * 4
+            for bi in range(nb):
+                p = f"layer{li}.{bi}."
+                bc = cin if bi == 0 else width * 4
+                names += [(p + "conv1", p + "bn1", bc, width, 1), (p + "conv2", p + "bn2", width, width, 9),
+                          (p + "conv3", p + "bn3", width, width * 4, 1)]
+                if bi == 0:
+                    names.append((p + "downsample.0", p + "downsample.1", bc, width * 4, 1))
+        bn_key = tuple(sd[prefix + bn + ".running_var"]._version + sd[prefix + bn + ".weight"]._version
+                       + sd[prefix + bn + ".bias"]._version + sd[prefix + bn + ".running_mean"]._version
+                       for _, bn, _, _, _ in names) + (sd[prefix + "bn1.weight"].data_ptr(),)
+        if self._bn is None or self._bn_key != bn_key:
+            self._bn = {}
+            for conv, bn, _, _, _ in names:
+                q = prefix + bn
+                scale = (sd[q + ".weight"] * torch.rsqrt(sd[q + ".running_var"] + BN_EPS)).float().contiguous()
+                shift = (sd[q + ".bias"] - sd[q + ".running_mean"] * scale).float().contiguous()
+                self._bn[conv] = (scale, shift)
+            self._bn_key = bn_key
+            self._wcache = {}
+        W = {}
+        for conv, bn, cin, cout, taps in names:
+            w = sd[prefix + conv + ".weight"]
+            ck = (w.data_ptr(), w._version)
+            ent = self._wcache.get(conv)
+            if ent is None or ent[0] != ck:
+                kpad = 192 if taps == 49 else taps * cin
+                wb = self.buf("w:" + conv, (cout, kpad))
+                ws = self.buf("ws:" + conv, (cout, kpad))
+                K.prep_weight(w.detach().float().contiguous(), wb, ws, self._bn[conv][0], cout, cin, taps, kpad)
+                ent = (ck, wb, ws)
+                self._wcache[conv] = ent
+            W[conv] = (ent[1], ent[2], self._bn[conv][0], self._bn[conv][1])
+        return W
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, frames, W, save, tag):
+        """frames fp32 [N,3,H,W] cuda.  Returns (feat rows bf16 [N*h*w, 2048], h, w, ctx or None)."""
+        N, _, H, Wd = frames.shape
+        frames = frames.contiguous()
+        H1, W1 = conv_out(H, 7, 2, 3), conv_out(Wd, 7, 2, 3)
+        H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
+        wb, _, sc, sh = W["conv1"]
+        stem = self.buf(tag + ":stem", (N * H1 * W1, 64))
+        chunk = max(1, min(N, (1 << 28) // (H1 * W1 * 192 * 2)))
+        col = self.buf(tag + ":stemcol", (chunk * H1 * W1, 192))
+        for n0 in range(0, N, chunk):
+            n = min(chunk, N - n0)
+            K.stem_im2col(frames[n0:n0 + n], col, n, H, Wd)
+            gemm(col, wb, stem[n0 * H1 * W1:(n0 + n) * H1 * W1], n * H1 * W1, 64, 192, scale=sc, bias=sh, relu=True)
+        x = self.buf(tag + ":pool", (N * H2 * W2, 64))
+        K.maxpool3x3s2(stem, x, N, H1, W1, 64)
+
+        ctx = {"N": N, "blocks": [], "tag": tag} if save else None
+        h, w = H2, W2
+        for li, (width, nb, stride0) in enumerate(STAGES, start=1):
+            for bi in range(nb):
+                name = f"layer{li}.{bi}."
+                stride = stride0 if bi == 0 else 1
+                keep = save and li >= 2                     # frozen stem/layer1 are never differentiated
+                btag = f"{tag}:{name}" if keep else f"{tag}:L{li}"
+                cin = x.shape[1]
+                cout = width * 4
+                ho, wo = (conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)) if stride == 2 else (h, w)
+                R, Ro = N * h * w, N * ho * wo
+                w1, _, s1, b1 = W[name + "conv1"]
+                w2, _, s2, b2 = W[name + "conv2"]
+                w3, _, s3, b3 = W[name + "conv3"]
+                rec = {"name": name, "x": x, "h": h, "w": w, "ho": ho, "wo": wo, "stride": stride, "width": width,
+                       "cin": cin, "cout": cout, "first": bi == 0}
+                if stride == 1:
+                    Rp = N * (h + 2) * (w + 2)
+                    y1 = self.buf(btag + "y1p", (Rp, width), zero=True)
+                    gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, remap=REMAP_C2P, img_hw=(h, w))
+                    y2 = self.buf(btag + "y2", (R, width))
+                    wp = w + 2
+                    taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
+                    gemm(y1, w2, y2, Rp, width, width, ntaps=9, a_off1=taps, b_off0=[t * width for t in range(9)],
+                         scale=s2, bias=b2, relu=True, remap=REMAP_P2C, img_hw=(h, w))
+                else:
+                    y1 = self.buf(btag + "y1", (R, width))
+                    gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True)
+                    colb = self.buf(btag + "col", (Ro, 9 * width))
+                    K.im2col3x3s2(y1, colb, N, h, w, width)
+                    y2 = self.buf(btag + "y2", (Ro, width))
+                    gemm(colb, w2, y2, Ro, width, 9 * width, scale=s2, bias=b2, relu=True)
+                    rec["col"] = colb
+                if bi == 0:
+                    wd, _, sd_, bd = W[name + "downsample.0"]
+                    xs = x
+                    if stride == 2:
+                        xs = self.buf(btag + "xs", (Ro, cin))
+                        K.subsample2(x, xs, N, h, w, cin)
+                    idt = self.buf(btag + "idt", (Ro, cout))
+                    gemm(xs, wd, idt, Ro, cout, cin, scale=sd_, bias=bd)
+                    rec["xs"] = xs
+                else:
+                    idt = x
+                # ping-pong the block output so the no-grad pass needs two buffers per stage
+                out = self.buf(f"{btag}out{0 if keep else bi % 2}", (Ro, cout))
+                gemm(y2, w3, out, Ro, cout, width, scale=s3, bias=b3, residual=idt, relu=True)
+                rec.update(y1=y1, y2=y2, out=out)
+                if keep:
+                    ctx["blocks"].append(rec)
+                x, h, w = out, ho, wo
+        self.last_hw = (h, w)
+        return x, h, w, ctx
+
+    # ------------------------------------------------------------------ backward
+    def _wgrad(self, g, xin, M, Ncols, Kred, rowscale, out, taps=1, z_b_off1=None):
+        """out (fp32, torch weight layout) = rowscale[:,None] * g^T @ xin  (both operands read MN-major)."""
+        nz = 9 if z_b_off1 is not None else 0
+        ntot = Ncols * (9 if nz else 1)
+        work = ((M + 127) // 128) * max(1, Ncols // 256 if Ncols % 256 == 0 else Ncols // 64) * max(nz, 1)
+        want = max(1, (2 * 148 + work - 1) // work)
+        s = effective_splits(Kred, want)
+        part = torch.empty(s, M, ntot, dtype=torch.float32, device=g.device)
+        gemm(g, xin, part, M, Ncols, Kred, a_major=1, b_major=1, nz=nz, z_b_off1=z_b_off1,
+             z_out_col=[t * Ncols for t in range(9)] if nz else None, splits=want)
+        splitk_reduce(part, s, M, ntot, out, rowscale=rowscale, taps=9 if (nz or taps == 9) else 1)
+
+    def backward(self, ctx, W, g_out, grads, prefix="backbone.0.body."):
+        """g_out: bf16 [N*h*w, 2048] = dL/d(pre-ReLU output of layer4.2), already masked by (feat > 0).
+        grads: dict name -> fp32 tensor (torch layout) written in place for every layer2-4 conv weight."""
+        N, tag = ctx["N"], ctx["tag"]
+        blocks = ctx["blocks"]
+        for i in range(len(blocks) - 1, -1, -1):
+            r = blocks[i]
+            name, h, w, ho, wo, width, cin, cout = (r[k] for k in ("name", "h", "w", "ho", "wo", "width", "cin", "cout"))
+            R, Ro = N * h * w, N * ho * wo
+            _, w1s, s1, _ = W[name + "conv1"]
+            _, w2s, s2, _ = W[name + "conv2"]
+            _, w3s, s3, _ = W[name + "conv3"]
+            x, y1, y2 = r["x"], r["y1"], r["y2"]
+            last = i == 0                                   # layer2.0: its input is the frozen layer1 output
+            # ---- conv3
+            self._wgrad(g_out, y2, cout, width, Ro, s3, grads[prefix + name + "conv3.weight"])
+            if r["stride"] == 1:
+                Rp = N * (h + 2) * (w + 2)
+                wp = w + 2
+                taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
+                g2 = self.buf(f"{tag}:g2p", (Rp, width), zero=True)
+                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=REMAP_C2P, img_hw=(h, w))
+                # ---- conv2 (implicit 3x3 over the haloed grid)
+                self._wgrad(g2, y1, width, width, Rp, s2, grads[prefix + name + "conv2.weight"], z_b_off1=taps)
+                g1 = self.buf(f"{tag}:g1", (R, width))
+                gemm(g2, w2s, g1, Rp, width, width, b_major=1, ntaps=9, a_off1=[-t for t in taps],
+                     b_off0=[t * width for t in range(9)], mask=y1, remap=REMAP_P2C, img_hw=(h, w))
+            else:
+                g2 = self.buf(f"{tag}:g2c", (Ro, width))
+                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2)
+                self._wgrad(g2, r["col"], width, 9 * width, Ro, s2, grads[prefix + name + "conv2.weight"], taps=9)
+                dcol = self.buf(f"{tag}:dcol", (Ro, 9 * width))
+                gemm(g2, w2s, dcol, Ro, 9 * width, width, b_major=1)
+                g1 = self.buf(f"{tag}:g1", (R, width))
+                K.col2im3x3s2_mask(dcol, y1, g1, N, h, w, width)
+            # ---- conv1
+            self._wgrad(g1, x, width, cin, R, s1, grads[prefix + name + "conv1.weight"])
+            resid = g_out
+            if r["first"]:
+                _, wds, sdn, _ = W[name + "downsample.0"]
+                self._wgrad(g_out, r["xs"], cout, cin, Ro, sdn, grads[prefix + name + "downsample.0.weight"])
+                if not last:
+                    dxs = self.buf(f"{tag}:dxs", (Ro, cin))
+                    gemm(g_out, wds, dxs, Ro, cin, cout, b_major=1)
+                    resid = dxs
+                    if r["stride"] == 2:
+                        resid = self.buf(f"{tag}:dxsu", (R, cin))
+                        K.upsample2_zero(dxs, resid, N, h, w, cin)
+            if last:
+                break
+            gprev = self.buf(f"{tag}:gout{i % 2}", (R, cin))
+            gemm(g1, w1s, gprev, R, cin, width, b_major=1, residual=resid, mask=x)
+            g_out = gprev
+        return grads
