@@ -157,12 +157,9 @@ class Step:
         self.inter_idx, self.time_mask = b["inter_idx"], b["time_mask"].to(device)
         self.crit.static = self.crit.prepare(self.targets, self.inter_idx, self.time_mask)
         # flat gradient buffer: every .grad is a view into it => ONE all-reduce, static addresses for graph replay
-        ps = [p for p in model.parameters() if p.requires_grad]
-        self.flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=device)
-        o = 0
-        for p in ps:
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
-            o += p.numel()
+        from tubedetr_b200.parallel import FlatGradBuffer
+        self.fgb = FlatGradBuffer(model.parameters(), device)
+        self.flat = self.fgb.flat
         self.loss = torch.zeros((), device=device)
         self.host_loss = torch.zeros((), pin_memory=True)
         self.copy_stream = torch.cuda.Stream()
@@ -214,7 +211,7 @@ class Step:
         else:
             self.body()
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat)      # the single gradient collective (sum; scale folded into lr)
+            self.fgb.all_reduce()                        # the single gradient collective of the step
 
     def run_e2e(self, prefetched):
         """inputs come from pinned host memory: H2D on a copy stream (overlapping the previous step), D2H of the loss."""

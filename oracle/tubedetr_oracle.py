@@ -253,7 +253,8 @@ def forward(sd, frames_slow, mask_slow, frames_fast, mask_fast, durations, input
                            for i in range(nlayers - 1)]}
     cache = {"img_memory": mem.transpose(0, 1), "pos_embed": mem_pos.transpose(0, 1), "mask": kpm_dec,
              "query_embed": qp.transpose(0, 1), "query_mask": q_kpm, "text_memory_resized": txt_rep.transpose(0, 1),
-             "text_attention_mask": txt_kpm.repeat_interleave(n_clips, 0), "feat_slow": feat_slow, "hs": hs}
+             "text_attention_mask": txt_kpm.repeat_interleave(n_clips, 0), "feat_slow": feat_slow, "hs": hs,
+             "src": src, "enc": xe, "mem": mem}
     return out, cache
 
 

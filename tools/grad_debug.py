@@ -1,0 +1,82 @@
+"""GPU-box diagnostic: per-parameter-group gradient error (signed) vs the reference fixture, and intermediate-tensor
+gradients (feat, src, enc, mem) vs the CPU oracle.  Writes gpurun_out/grad_debug.txt"""
+import collections
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import batch_for, load_gold, run_oracle, state_dict  # noqa: E402
+import test_model_gpu as T  # noqa: E402
+
+os.makedirs("gpurun_out", exist_ok=True)
+log = open("gpurun_out/grad_debug.txt", "w")
+
+
+def P(*a):
+    s = " ".join(str(x) for x in a)
+    print(s)
+    log.write(s + "\n")
+    log.flush()
+
+
+def group(k):
+    if k.startswith("backbone"):
+        parts = k.split(".")
+        return "backbone." + parts[3] + "." + parts[5].split(".")[0] if parts[3].startswith("layer") else "backbone.stem"
+    if "text_encoder" in k:
+        return "text_encoder"
+    if "encoder.layers" in k:
+        return "enc." + k.split(".")[3] + "." + ".".join(k.split(".")[4:6])
+    if "decoder.layers" in k:
+        return "dec." + k.split(".")[3] + "." + ".".join(k.split(".")[4:6])
+    return k
+
+
+def main(name="cfg1b"):
+    g = load_gold(name)
+    cfg = g["cfg"]
+    # intermediate grads: hook my tensors
+    from tubedetr_b200 import ops
+    captured = {}
+    orig_linear = ops.linear
+    model, crit, wd, b, mc, out = T._run(cfg)
+    keep = b["keep"].cuda()
+    o = dict(out, pred_boxes=out["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in out["aux_outputs"]])
+    targets = [{"boxes": bx[None].cuda()} for bx in b["target_boxes"]]
+    losses = crit(o, targets, b["inter_idx"], b["time_mask"].cuda())
+    total = sum(losses[k] * wd[k] for k in losses if k in wd)
+    mem = mc["img_memory"]
+    mem.retain_grad()
+    model.zero_grad()
+    total.backward()
+    P("loss", total.item(), "ref", g["loss_total"].item())
+    rows = collections.defaultdict(list)
+    for k, p in model.named_parameters():
+        if k in g["grad_norm"] and p.grad is not None and g["grad_norm"][k] > 1e-5:
+            rows[group(k)].append(p.grad.float().norm().item() / g["grad_norm"][k] - 1.0)
+    for grp in sorted(rows):
+        v = rows[grp]
+        P(f"{grp:50s} n={len(v):3d} mean signed rel err {sum(v) / len(v):+.4f}  min {min(v):+.4f} max {max(v):+.4f}")
+    # oracle intermediate gradients on CPU
+    from oracle import tubedetr_oracle as O
+    sd = {k: v.clone() for k, v in state_dict().items()}
+    if "--no_fast" in cfg["flags"]:
+        sd = {k: v for k, v in sd.items() if "fast_" not in k}
+    for k in ("input_proj.weight",):
+        sd[k].requires_grad_(True)
+    oout, cache, ob = run_oracle(cfg, sd=sd)
+    ol = O.criterion(oout, ob["target_boxes"], ob["inter_idx"], ob["time_mask"], ob["keep"])
+    owd = O.weight_dict()
+    ototal = sum(ol[k] * owd[k] for k in ol)
+    gs = torch.autograd.grad(ototal, [cache["src"], cache["enc"], cache["mem"]], allow_unused=True)
+    P("oracle d/dsrc norm", gs[0].norm().item(), "d/denc", gs[1].norm().item(), "d/dmem", gs[2].norm().item())
+    mg = mem.grad.transpose(0, 1).float().cpu()
+    P("mine   d/dmem norm", mg.norm().item(), "cos", torch.nn.functional.cosine_similarity(mg.flatten(), gs[2].flatten(), dim=0).item())
+
+
+if __name__ == "__main__":
+    main(*sys.argv[1:])

@@ -321,6 +321,21 @@ class TubeDETR(nn.Module):
         jj = (torch.arange(w, device=mask.device) * (W / w)).floor().long().clamp(max=W - 1)
         return mask[:, ii][:, :, jj]
 
+    def _index_tensors(self, durations, k, dev):
+        """duration-dependent index tensors, built on the host once per (durations, stride) and cached on the device so a
+        steady-state step issues no host->device copies (CUDA-graph capturable)."""
+        key = (durations, k, str(dev))
+        c = self.__dict__.setdefault("_idx_cache", {})
+        if key not in c:
+            B, T = len(durations), max(durations)
+            n_clips = math.ceil(T / k)
+            dur = torch.tensor(durations)
+            tt = torch.arange(T)
+            valid = tt[None] < dur[:, None]
+            clip_of_t = (torch.arange(B)[:, None] * n_clips + tt[None] // k).flatten()
+            c[key] = tuple(t.to(dev) for t in (dur, tt, valid, clip_of_t))
+        return c[key]
+
     def _tokenize(self, captions, device):
         if isinstance(captions, (tuple, list)) and len(captions) == 2 and torch.is_tensor(captions[0]):
             return captions[0].to(device), captions[1].to(device)  # pre-tokenised (input_ids, attention_mask)
@@ -357,10 +372,7 @@ class TubeDETR(nn.Module):
             m_s = self._resize_mask(fmask, h, w).clone()
             m_s[:, 0, 0] = False
             pos = self.backbone[1](m_s).view(n, HW, D_MODEL)
-            dur = torch.tensor(durations, device=dev)
-            tt = torch.arange(T, device=dev)
-            valid = tt[None] < dur[:, None]
-            clip_of_t = (torch.arange(B, device=dev)[:, None] * n_clips + tt[None] // k).flatten()
+            dur, tt, valid, clip_of_t = self._index_tensors(tuple(durations), k, dev)
         Win, bin_ = self.input_proj.weight.view(D_MODEL, 2048), self.input_proj.bias
         src = ops.linear(feat, Win, bin_, out_fp32=True).view(n, HW, D_MODEL)
 

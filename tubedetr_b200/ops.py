@@ -185,6 +185,7 @@ class AddLayerNormFn(torch.autograd.Function):
         K.layernorm_fwd(x, r, gamma, beta, pos, y, yb, ypb, mean, rstd, rows, D, eps)
         ctx.save_for_backward(x, r, gamma, mean, rstd)
         ctx.has_r = r is not None
+        ctx.pos_dtype = pos.dtype if pos is not None else None
         if ypb is None:
             return y, yb
         return y, yb, ypb
@@ -204,7 +205,10 @@ class AddLayerNormFn(torch.autograd.Function):
         dg = torch.empty(D, dtype=torch.float32, device=x.device)
         db = torch.empty(D, dtype=torch.float32, device=x.device)
         K.layernorm_bwd(g, x, r, gamma, mean, rstd, dz, dg, db, rows, D)
-        return dz, (dz if ctx.has_r else None), dg, db, None, None
+        dpos = None
+        if ctx.needs_input_grad[4] and dypb is not None:   # (y + pos): pos is the time-query embedding in the decoder
+            dpos = dypb.to(ctx.pos_dtype)
+        return dz, (dz if ctx.has_r else None), dg, db, dpos, None
 
 
 def add_layernorm(x, r, gamma, beta, pos=None, eps=1e-5):
