@@ -168,7 +168,10 @@ class Step:
         self.launches_per_step = None
 
     def body(self):
-        self.flat.zero_()
+        # grads start as None so autograd ASSIGNS them (no per-parameter accumulate kernels); for N>1 they are packed into
+        # the flat buffer by one multi-tensor copy right before the single all-reduce
+        for p in self.fgb.params:
+            p.grad = None
         mc = self.model(self.samples, [T_FRAMES], self.caps, encode_and_save=True, samples_fast=self.fast)
         out = self.model(self.samples, [T_FRAMES], self.caps, encode_and_save=False, memory_cache=mc)
         out = dict(out, pred_boxes=out["pred_boxes"][self.keep],
@@ -176,6 +179,8 @@ class Step:
         losses = self.crit(out, self.targets, self.inter_idx, self.time_mask)
         total = sum(losses[k] * self.wd[k] for k in losses if k in self.wd)
         total.backward()
+        if self.world > 1:
+            self.fgb.pack()
         self.loss.copy_(total.detach())
 
     def capture(self):

@@ -213,8 +213,10 @@ def forward(sd, frames_slow, mask_slow, frames_fast, mask_fast, durations, input
     kpm_enc = torch.cat([m_s.flatten(1), txt_kpm.repeat_interleave(n_clips, 0)], 1)
     xe = torch.cat([x, txt_rep], 1)
     pe = torch.cat([pos, torch.zeros_like(txt_rep)], 1)
+    enc_layers = [xe]
     for l in range(nlayers):
         xe = encoder_layer(xe, pe, kpm_enc, sd, f"transformer.encoder.layers.{l}")
+        enc_layers.append(xe)
 
     # temporal replication (transformer.py:393-427): frame (b,t) <- clip (b, t//k)
     clip_of_t = (torch.arange(B)[:, None] * n_clips + tt[None, :] // stride).flatten()
@@ -254,7 +256,7 @@ def forward(sd, frames_slow, mask_slow, frames_fast, mask_fast, durations, input
     cache = {"img_memory": mem.transpose(0, 1), "pos_embed": mem_pos.transpose(0, 1), "mask": kpm_dec,
              "query_embed": qp.transpose(0, 1), "query_mask": q_kpm, "text_memory_resized": txt_rep.transpose(0, 1),
              "text_attention_mask": txt_kpm.repeat_interleave(n_clips, 0), "feat_slow": feat_slow, "hs": hs,
-             "src": src, "enc": xe, "mem": mem}
+             "src": src, "enc": xe, "mem": mem, "enc_layers": enc_layers, "txt": txt}
     return out, cache
 
 

@@ -156,6 +156,9 @@ def test_mha_fwd_bwd(B, Lq, Lk):
     _close(dq.view_as(q), qf.grad, 2e-2)
     _close(dk.view_as(k), kf.grad, 2e-2)
     _close(dv.view_as(v), vf.grad, 2e-2)
+    for got, ref in ((dq.view_as(q), qf.grad), (dk.view_as(k), kf.grad), (dv.view_as(v), vf.grad)):
+        a = (got.float() * ref).sum() / (ref * ref).sum()      # no systematic scaling of the gradient
+        assert abs(a.item() - 1) < 5e-3, a.item()
 
 
 def test_colsum_and_cast():

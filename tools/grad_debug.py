@@ -43,7 +43,22 @@ def main(name="cfg1b"):
     from tubedetr_b200 import ops
     captured = {}
     orig_linear = ops.linear
+    model0, *_ = T._model(cfg)
+    tr = model0.transformer
+    enc_io = []
+    orig = tr._enc_layer
+
+    def wrapped(l, x32, *a, **k):
+        if not enc_io:
+            x32.retain_grad()
+            enc_io.append(x32)
+        res = orig(l, x32, *a, **k)
+        res[0].retain_grad()
+        enc_io.append(res[0])
+        return res
+    tr._enc_layer = wrapped
     model, crit, wd, b, mc, out = T._run(cfg)
+    tr._enc_layer = orig
     keep = b["keep"].cuda()
     o = dict(out, pred_boxes=out["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in out["aux_outputs"]])
     targets = [{"boxes": bx[None].cuda()} for bx in b["target_boxes"]]
@@ -72,6 +87,14 @@ def main(name="cfg1b"):
     ol = O.criterion(oout, ob["target_boxes"], ob["inter_idx"], ob["time_mask"], ob["keep"])
     owd = O.weight_dict()
     ototal = sum(ol[k] * owd[k] for k in ol)
+    gl = torch.autograd.grad(ototal, cache["enc_layers"], retain_graph=True)
+    for i, (mine, ref) in enumerate(zip(enc_io, gl)):
+        m = mine.grad.float().cpu().view_as(ref)
+        a = (m * ref).sum() / (ref * ref).sum()
+        cos = torch.nn.functional.cosine_similarity(m.flatten(), ref.flatten(), dim=0)
+        fm, fr = (mine.detach().float().cpu().view_as(ref) - cache["enc_layers"][i].detach()), cache["enc_layers"][i].detach()
+        P(f"enc boundary {i}: grad proj a={a.item():.4f} cos={cos.item():.4f} norm mine {m.norm().item():.4f} ref {ref.norm().item():.4f}"
+          f" | fwd act rel err {fm.norm().item() / fr.norm().item():.4f}")
     gs = torch.autograd.grad(ototal, [cache["src"], cache["enc"], cache["mem"]], allow_unused=True)
     P("oracle d/dsrc norm", gs[0].norm().item(), "d/denc", gs[1].norm().item(), "d/dmem", gs[2].norm().item())
     mg = mem.grad.transpose(0, 1).float().cpu()

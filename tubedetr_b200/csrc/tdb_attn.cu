@@ -161,24 +161,59 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
   }
 }
 
-// column pass: one warp per key j: dV[j] = sum_i P[i][j] dO[i];  dK[j] = scale * sum_i dS[i][j] Q[i]
+// column pass: dV[j] = sum_i P[i][j] dO[i];  dK[j] = scale * sum_i dS[i][j] Q[i].
+// CTA = (sequence, head, 64-key slab).  Query rows stream through shared memory in chunks of 32: the P / dS sub-tiles
+// [32][64] are loaded with coalesced 256-byte row segments, dO / Q chunks [32][32] as fp32; warp w owns keys 8w..8w+7 of the
+// slab and lane d owns head-dim d, so every shared-memory read is a broadcast (P, dS) or conflict-free (dO, Q).
+constexpr int kColKeys = 64;
+constexpr int kColRows = 32;
 __global__ void __launch_bounds__(kAttnThreads) mha_bwd_col_kernel(const AttnBwdParams a) {
+  __shared__ float ps[kColRows][kColKeys];
+  __shared__ float dss[kColRows][kColKeys];
+  __shared__ float dos[kColRows][HD];
+  __shared__ float qs[kColRows][HD];
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int j0 = blockIdx.y * kColKeys;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* pb = a.p + ((long long)b * a.H + h) * a.Lq * a.Lk;
   const float* dsb = a.ds + ((long long)b * a.H + h) * a.Lq * a.Lk;
-  for (int j = blockIdx.y * nwarps + warp; j < a.Lk; j += gridDim.y * nwarps) {
-    float av = 0.f, ak = 0.f;
-    for (int i = 0; i < a.Lq; ++i) {
-      float pij = __ldg(pb + (long long)i * a.Lk + j);
-      float dsij = __ldg(dsb + (long long)i * a.Lk + j);
-      float dod = __bfloat162float(a.dout[((long long)b * a.Lq + i) * a.lddo + h * HD + lane]);
-      float qd = __bfloat162float(a.q[((long long)b * a.Lq + i) * a.ldq + h * HD + lane]);
-      av += pij * dod;
-      ak += dsij * qd;
+  float av[8], ak[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) av[t] = ak[t] = 0.f;
+  for (int i0 = 0; i0 < a.Lq; i0 += kColRows) {
+    for (int e = threadIdx.x; e < kColRows * kColKeys; e += blockDim.x) {
+      int r = e / kColKeys, c = e % kColKeys;
+      int i = i0 + r, j = j0 + c;
+      bool ok = i < a.Lq && j < a.Lk;
+      ps[r][c] = ok ? __ldg(pb + (long long)i * a.Lk + j) : 0.f;
+      dss[r][c] = ok ? __ldg(dsb + (long long)i * a.Lk + j) : 0.f;
     }
-    a.dv[((long long)b * a.Lk + j) * a.lddv + h * HD + lane] = __float2bfloat16(av);
-    a.dk[((long long)b * a.Lk + j) * a.lddk + h * HD + lane] = __float2bfloat16(ak * a.scale);
+    for (int e = threadIdx.x; e < kColRows * HD; e += blockDim.x) {
+      int r = e / HD, d = e % HD;
+      int i = i0 + r;
+      bool ok = i < a.Lq;
+      dos[r][d] = ok ? __bfloat162float(a.dout[((long long)b * a.Lq + i) * a.lddo + h * HD + d]) : 0.f;
+      qs[r][d] = ok ? __bfloat162float(a.q[((long long)b * a.Lq + i) * a.ldq + h * HD + d]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < kColRows; ++r) {
+      float dod = dos[r][lane], qd = qs[r][lane];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        av[t] += ps[r][warp * 8 + t] * dod;
+        ak[t] += dss[r][warp * 8 + t] * qd;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    int j = j0 + warp * 8 + t;
+    if (j < a.Lk) {
+      a.dv[((long long)b * a.Lk + j) * a.lddv + h * HD + lane] = __float2bfloat16(av[t]);
+      a.dk[((long long)b * a.Lk + j) * a.lddk + h * HD + lane] = __float2bfloat16(ak[t] * a.scale);
+    }
   }
 }
 
@@ -242,7 +277,7 @@ extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
                   ds_scratch, (bf16*)dq, (bf16*)dk, (bf16*)dv, lddq, lddk, lddv, B, H, Lq, Lk, scale};
   dim3 g1(B * H, attn_grid_y(B * H, Lq));
   mha_bwd_row_kernel<<<g1, kAttnThreads, smem, (cudaStream_t)stream_>>>(a);
-  dim3 g2(B * H, attn_grid_y(B * H, Lk));
+  dim3 g2(B * H, (Lk + kColKeys - 1) / kColKeys);
   mha_bwd_col_kernel<<<g2, kAttnThreads, 0, (cudaStream_t)stream_>>>(a);
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(2);

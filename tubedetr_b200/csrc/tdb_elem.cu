@@ -311,15 +311,20 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, int np
   out[c] = accumulate ? out[c] + s : s;
 }
 
-// column sums of a bf16 [rows][N] matrix (bias gradients): stage 1 -> partial [nb][N] fp32
+// column sums of a bf16 [rows][N] matrix (bias gradients): stage 1 -> partial [nb][N] fp32.  Thread = 2 adjacent columns.
 __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, int rows, int N, float* __restrict__ partial, int rows_per_block) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (c >= N) return;
   int r0 = blockIdx.y * rows_per_block;
   int r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) s += __bfloat162float(x[(long long)r * ld + c]);
-  partial[(long long)blockIdx.y * N + c] = s;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + (long long)r * ld + c));
+    s0 += v.x;
+    s1 += v.y;
+  }
+  partial[(long long)blockIdx.y * N + c] = s0;
+  partial[(long long)blockIdx.y * N + c + 1] = s1;
 }
 
 }  // namespace tdb
@@ -408,8 +413,8 @@ extern "C" int tdb_layernorm_bwd(const float* dy, const float* x, const float* r
   int blocks = tdb_layernorm_bwd_blocks(rows);
   layernorm_bwd_kernel<256><<<blocks, 256, 0, STREAM>>>(dy, x, r, gamma, mean, rstd, dz, partial, rows);
   TDB_CHECK_CUDA(cudaGetLastError());
-  if (dgamma) colsum_partials_kernel<<<1, 256, 0, STREAM>>>(partial, blocks, 2 * D, D, dgamma, accumulate);
-  if (dbeta) colsum_partials_kernel<<<1, 256, 0, STREAM>>>(partial + D, blocks, 2 * D, D, dbeta, accumulate);
+  if (dgamma) colsum_partials_kernel<<<4, 64, 0, STREAM>>>(partial, blocks, 2 * D, D, dgamma, accumulate);
+  if (dbeta) colsum_partials_kernel<<<4, 64, 0, STREAM>>>(partial + D, blocks, 2 * D, D, dbeta, accumulate);
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(3);
   return TDB_OK;
@@ -417,10 +422,11 @@ extern "C" int tdb_layernorm_bwd(const float* dy, const float* x, const float* r
 extern "C" int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* partial, int nparts, float* out,
                                int accumulate, void* stream_) {
   TDB_REQUIRE(x && partial && out && rows > 0 && N > 0 && nparts > 0, "tdb_colsum_bf16: bad args");
+  TDB_REQUIRE(N % 2 == 0 && ld % 2 == 0, "tdb_colsum_bf16: N and ld must be even");
   int rpb = (rows + nparts - 1) / nparts;
-  dim3 grid((N + 127) / 128, nparts);
+  dim3 grid((N / 2 + 127) / 128, nparts);
   colsum_bf16_kernel<<<grid, 128, 0, STREAM>>>((const bf16*)x, ld, rows, N, partial, rpb);
-  colsum_partials_kernel<<<(N + 255) / 256, 256, 0, STREAM>>>(partial, nparts, N, N, out, accumulate);
+  colsum_partials_kernel<<<(N + 63) / 64, 64, 0, STREAM>>>(partial, nparts, N, N, out, accumulate);
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(2);
   return TDB_OK;

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/tubedetr_b200.h"
 #include "tdb_common.cuh"
@@ -498,6 +499,19 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   }
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
+  static FILE* logf = nullptr;
+  static bool log_checked = false;
+  if (!log_checked) {  // TDB_GEMM_LOG=<path>: one line per launch (profiling aid, joins with the ncu launch list)
+    log_checked = true;
+    const char* lp = getenv("TDB_GEMM_LOG");
+    if (lp) logf = fopen(lp, "w");
+  }
+  if (logf) {
+    fprintf(logf, "M=%d N=%d K=%d taps=%d nz=%d splits=%d bn=%d amaj=%d bmaj=%d grid=%d epi=%d%d%d%d remap=%d f32=%d\n", d->M, d->N,
+            d->K, d->ntaps, nz, splits, bn, p.a_major, p.b_major, grid, d->scale != nullptr, d->residual != nullptr, d->relu,
+            d->mask != nullptr, d->remap, p.out_f32);
+    fflush(logf);
+  }
   return TDB_OK;
 }
 

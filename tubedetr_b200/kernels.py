@@ -57,7 +57,7 @@ def layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dgamma, dbeta, rows, D, accum
 
 def colsum_bf16(x, out, accumulate=False):
     rows, N = x.shape
-    nparts = max(1, min(64, rows // 64))
+    nparts = max(1, min(296, rows // 32))
     partial = torch.empty(nparts * N, dtype=torch.float32, device=x.device)
     check(lib().tdb_colsum_bf16(ptr(x), _i64(x.stride(0)), rows, N, ptr(partial), nparts, ptr(out), int(accumulate),
                                 stream_ptr()), "colsum_bf16")

@@ -308,6 +308,7 @@ class TubeDETR(nn.Module):
             self.sted_embed = _MLP(D_MODEL, D_MODEL, 2, 2)
             self.sted_embed.dropout = 0.5  # reference applies Dropout(0.5) here in train mode (not applied yet)
         self._engine = ResNet101Engine()
+        self.text_autocast = True   # RoBERTa (library call) runs its GEMMs in bf16 like the rest of the path
 
     # ------------------------------------------------------------------ helpers
     def _backbone_tensors(self):
@@ -402,9 +403,10 @@ class TubeDETR(nn.Module):
 
         # text (library call, reference transformer.py:250-263) + resizer on our kernels
         ids, am = self._tokenize(captions, dev)
-        hid = tr.text_encoder(input_ids=ids, attention_mask=am).last_hidden_state        # (B,L,768)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.text_autocast):
+            hid = tr.text_encoder(input_ids=ids, attention_mask=am).last_hidden_state    # (B,L,768)
         L = hid.shape[1]
-        r = ops.linear(hid.reshape(B * L, 768).to(torch.bfloat16), tr.resizer.fc.weight, tr.resizer.fc.bias, out_fp32=True)
+        r = ops.linear(hid.float().reshape(B * L, 768).to(torch.bfloat16), tr.resizer.fc.weight, tr.resizer.fc.bias, out_fp32=True)
         txt, _ = ops.add_layernorm(r, None, tr.resizer.layer_norm.weight, tr.resizer.layer_norm.bias, eps=1e-12)
         txt = txt.view(B, L, D_MODEL)
         txt_kpm = am.ne(1)

@@ -23,6 +23,24 @@ class FlatGradBuffer:
     def zero(self):
         self.flat.zero_()
 
+    def views(self):
+        out, o = [], 0
+        for p in self.params:
+            out.append(self.flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+        return out
+
+    def pack(self):
+        """copy freshly assigned .grad tensors into the flat buffer with one multi-tensor copy (missing grads -> 0)."""
+        if not hasattr(self, "_views"):
+            self._views = self.views()
+        have = [(v, p.grad) for v, p in zip(self._views, self.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        for v, p in zip(self._views, self.params):
+            if p.grad is None:
+                v.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+
     def all_reduce(self, average=True):
         """sum over ranks (then / world): after this every rank holds the gradient of the mean loss over all clips."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
