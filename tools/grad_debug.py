@@ -57,8 +57,18 @@ def main(name="cfg1b"):
         enc_io.append(res[0])
         return res
     tr._enc_layer = wrapped
+    feat_g = {}
+    orig_lin = ops.linear
+
+    def lin_wrapped(x, W, b, relu=False, out_fp32=False):
+        if "feat" not in feat_g and x.shape[1] == 2048 and x.requires_grad:
+            feat_g["feat"] = x
+            x.register_hook(lambda g: feat_g.__setitem__("g", g.detach().float().cpu()))
+        return orig_lin(x, W, b, relu, out_fp32)
+    ops.linear = lin_wrapped
     model, crit, wd, b, mc, out = T._run(cfg)
     tr._enc_layer = orig
+    ops.linear = orig_lin
     keep = b["keep"].cuda()
     o = dict(out, pred_boxes=out["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in out["aux_outputs"]])
     targets = [{"boxes": bx[None].cuda()} for bx in b["target_boxes"]]
@@ -95,6 +105,27 @@ def main(name="cfg1b"):
         fm, fr = (mine.detach().float().cpu().view_as(ref) - cache["enc_layers"][i].detach()), cache["enc_layers"][i].detach()
         P(f"enc boundary {i}: grad proj a={a.item():.4f} cos={cos.item():.4f} norm mine {m.norm().item():.4f} ref {ref.norm().item():.4f}"
           f" | fwd act rel err {fm.norm().item() / fr.norm().item():.4f}")
+    gfeat = torch.autograd.grad(ototal, cache["feat_slow"], retain_graph=True)[0]          # (n,2048,h,w)
+    ref_f = gfeat.permute(0, 2, 3, 1).reshape(-1, 2048)
+    mine_f = feat_g["g"].view_as(ref_f)
+    a = (mine_f * ref_f).sum() / (ref_f * ref_f).sum()
+    P(f"d/d feat (backbone output, before ReLU mask): proj a={a.item():.4f} cos={torch.nn.functional.cosine_similarity(mine_f.flatten(), ref_f.flatten(), dim=0).item():.4f}"
+      f" norm mine {mine_f.norm().item():.5f} ref {ref_f.norm().item():.5f}")
+    gsrc = torch.autograd.grad(ototal, cache["src"], retain_graph=True)[0]                 # (n,256,h,w)
+    ref_s = gsrc.flatten(2).transpose(1, 2)
+    HW = ref_s.shape[1]
+    mine_s = enc_io[0].grad.float().cpu().view(ref_s.shape[0], -1, 256)[:, :HW]
+    a = (mine_s * ref_s).sum() / (ref_s * ref_s).sum()
+    P(f"d/d src (visual rows of encoder input): proj a={a.item():.4f} norm mine {mine_s.norm().item():.5f} ref {ref_s.norm().item():.5f}")
+    # isolate LinearFn.backward: feed the oracle's exact d src and feat through our dgrad GEMM
+    from tubedetr_b200.gemm import gemm
+    Wv = model.input_proj.weight.detach().view(256, 2048)
+    dyb = ref_s.reshape(-1, 256).to(torch.bfloat16).cuda().contiguous()
+    dx = torch.empty(dyb.shape[0], 2048, dtype=torch.bfloat16, device="cuda")
+    gemm(dyb, Wv.to(torch.bfloat16).contiguous(), dx, dyb.shape[0], 2048, 256, b_major=1)
+    iso = dx.float().cpu()
+    a = (iso * ref_f).sum() / (ref_f * ref_f).sum()
+    P(f"isolated dgrad GEMM on oracle d src: proj a={a.item():.4f} norm {iso.norm().item():.5f} ref {ref_f.norm().item():.5f}")
     gs = torch.autograd.grad(ototal, [cache["src"], cache["enc"], cache["mem"]], allow_unused=True)
     P("oracle d/dsrc norm", gs[0].norm().item(), "d/denc", gs[1].norm().item(), "d/dmem", gs[2].norm().item())
     mg = mem.grad.transpose(0, 1).float().cpu()

@@ -54,7 +54,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 32 * 64 * 4;  // per epilogue warp: 32 rows x 64 fp32 columns
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
 
 struct WorkItem {
@@ -212,6 +213,7 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int wq = warp & 3;
+    float* stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + wq * (32 * 64);
     int acc = 0;
     uint32_t acc_phase = 0;
     const int Hp = p.img_h + 2, Wp = p.img_w + 2;
@@ -242,70 +244,63 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(wq * 32) << 16);
+      const int valid_i = valid ? 1 : 0;
+      // Each warp transposes its own 32 rows x 64 columns through a private XOR-swizzled smem tile so that global
+      // traffic is row-contiguous: phase 1 = thread-per-row TMEM -> smem (float4, conflict-free),
+      // phase 2 = half-warp-per-row: 16 lanes x 4 columns = 128 B (bf16) / 256 B (fp32) contiguous per row.
+      float4* st4 = reinterpret_cast<float4*>(stage);
+      const int hl = lane & 15;        // column group (4 columns) within the 64-column chunk
+      const int hsel = lane >> 4;      // which of the two rows this half-warp handles
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-        if (valid) {
-          float v[32];
+      for (int c = 0; c < BN; c += 64) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          const int col = wi.n0 + c;  // column in scale/bias/mask/residual space
-          if (p.scale != nullptr) {
-            const float4* sp = reinterpret_cast<const float4*>(p.scale + col);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c + half * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 s = __ldg(sp + i);
-              v[4 * i] *= s.x; v[4 * i + 1] *= s.y; v[4 * i + 2] *= s.z; v[4 * i + 3] *= s.w;
+          for (int q = 0; q < 8; ++q)
+            st4[lane * 16 + ((half * 8 + q) ^ (lane & 15))] =
+                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                            __uint_as_float(r[4 * q + 3]));
+        }
+        __syncwarp();
+        const int col = wi.n0 + c + hl * 4;       // column in scale/bias/mask/residual space
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.scale != nullptr) sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+        if (p.bias != nullptr) bi = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll 4
+        for (int rr = 0; rr < 32; rr += 2) {
+          const int myr = rr + hsel;
+          const int v_ok = __shfl_sync(0xffffffffu, valid_i, myr);
+          const long long orow = __shfl_sync(0xffffffffu, out_row, myr);
+          if (v_ok) {
+            float4 v = st4[myr * 16 + (hl ^ (myr & 15))];
+            v.x = v.x * sc.x + bi.x; v.y = v.y * sc.y + bi.y; v.z = v.z * sc.z + bi.z; v.w = v.w * sc.w + bi.w;
+            if (p.residual != nullptr) {
+              uint2 u = __ldg(reinterpret_cast<const uint2*>(p.residual + orow * p.ldr + col));
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+              v.x += f0.x; v.y += f0.y; v.z += f1.x; v.w += f1.y;
             }
-          }
-          if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 s = __ldg(bp + i);
-              v[4 * i] += s.x; v[4 * i + 1] += s.y; v[4 * i + 2] += s.z; v[4 * i + 3] += s.w;
+            if (p.relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
             }
-          }
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u = __ldg(rp + i);
-              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-              v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
-              v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+            if (p.mask != nullptr) {
+              const long long trow = (long long)(wi.m0 + wq * 32 + myr);
+              uint2 u = __ldg(reinterpret_cast<const uint2*>(p.mask + trow * p.ldmask + col));
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
+              v.x = f0.x > 0.f ? v.x : 0.f; v.y = f0.y > 0.f ? v.y : 0.f;
+              v.z = f1.x > 0.f ? v.z : 0.f; v.w = f1.y > 0.f ? v.w : 0.f;
             }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.mask != nullptr) {
-            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (long long)row_t * p.ldmask + col);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u = __ldg(mp + i);
-              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-              v[8 * i] = f0.x > 0.f ? v[8 * i] : 0.f;         v[8 * i + 1] = f0.y > 0.f ? v[8 * i + 1] : 0.f;
-              v[8 * i + 2] = f1.x > 0.f ? v[8 * i + 2] : 0.f; v[8 * i + 3] = f1.y > 0.f ? v[8 * i + 3] : 0.f;
-              v[8 * i + 4] = f2.x > 0.f ? v[8 * i + 4] : 0.f; v[8 * i + 5] = f2.y > 0.f ? v[8 * i + 5] : 0.f;
-              v[8 * i + 6] = f3.x > 0.f ? v[8 * i + 6] : 0.f; v[8 * i + 7] = f3.y > 0.f ? v[8 * i + 7] : 0.f;
+            const long long o = orow * p.ldo + out_col0 + c + hl * 4;
+            if (p.out_f32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = v;
+            } else {
+              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
             }
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + out_col0 + c);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + out_col0 + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
