@@ -11,37 +11,46 @@ namespace tdb {
 static inline unsigned nblocks(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 // ------------------------------------------------------------------ stem: fp32 NCHW frames -> bf16 im2col rows [N*Ho*Wo][192]
-// column = c*49 + kh*7 + kw (torch weight flatten order), zero padded 147 -> 192; conv 7x7 / stride 2 / pad 3
-__global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int Ho, int Wo) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, group of 8 columns)
-  long long total = (long long)N * Ho * Wo * 24;
-  if (idx >= total) return;
-  int g = (int)(idx % 24);
-  long long row = idx / 24;
-  int wo = (int)(row % Wo);
-  long long t = row / Wo;
-  int ho = (int)(t % Ho);
-  int n = (int)(t / Ho);
-  uint32_t packed[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float v[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      int cidx = g * 8 + i * 2 + j;
-      float val = 0.f;
-      if (cidx < 147) {
-        int c = cidx / 49;
-        int r = cidx - c * 49;
-        int kh = r / 7, kw = r - kh * 7;
-        int hi = ho * 2 - 3 + kh, wi = wo * 2 - 3 + kw;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) val = __ldg(x + (((long long)n * 3 + c) * H + hi) * W + wi);
-      }
-      v[j] = val;
-    }
-    packed[i] = pack_bf16x2(v[0], v[1]);
+// column = c*49 + kh*7 + kw (torch weight flatten order), zero padded 147 -> 192; conv 7x7 / stride 2 / pad 3.
+// One CTA per (frame, output row): the 7 input rows x 3 channels it needs are staged in shared memory with coalesced
+// loads (zero padded by 3 on both sides), then every output pixel's 192-column row is written as 24 x 16-byte stores.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ col, int N, int H, int W,
+                                                          int Ho, int Wo) {
+  extern __shared__ float srow[];           // [3][7][W + 6]
+  const int Wp = W + 6;
+  const int n = blockIdx.x / Ho, ho = blockIdx.x % Ho;
+  for (int e = threadIdx.x; e < 21 * Wp; e += blockDim.x) {
+    int ck = e / Wp, wi = e % Wp - 3;
+    int c = ck / 7, kh = ck % 7;
+    int hi = ho * 2 - 3 + kh;
+    float v = 0.f;
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(x + (((long long)n * 3 + c) * H + hi) * W + wi);
+    srow[e] = v;
   }
-  *reinterpret_cast<uint4*>(col + row * 192 + g * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  __syncthreads();
+  bf16* out = col + ((long long)n * Ho + ho) * Wo * 192;
+  for (int e = threadIdx.x; e < Wo * 24; e += blockDim.x) {
+    int wo = e / 24, g = e % 24;
+    uint32_t packed[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        int cidx = g * 8 + i * 2 + j;
+        float val = 0.f;
+        if (cidx < 147) {
+          int c = cidx / 49;
+          int r = cidx - c * 49;
+          int kh = r / 7, kw = r - kh * 7;
+          val = srow[(c * 7 + kh) * Wp + wo * 2 + kw];
+        }
+        v[j] = val;
+      }
+      packed[i] = pack_bf16x2(v[0], v[1]);
+    }
+    *reinterpret_cast<uint4*>(out + (long long)wo * 192 + g * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
 }
 
 // ------------------------------------------------------------------ 3x3 / stride 2 / pad 1 max pool, NHWC bf16, 8 channels per thread
@@ -252,7 +261,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 // backward: given dy (fp32), z recomputed from (x, r), mean, rstd: dz = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma
 // writes dz (fp32; it is the gradient of BOTH x and r) and per-block partial dgamma/dbeta [blocks][2][D] for a fixed-order reduce.
 template <int D>
-__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ r,
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ dy3,
+                                     const float* __restrict__ x, const float* __restrict__ r,
                                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                                      float* __restrict__ dz, float* __restrict__ partial, int rows) {
   constexpr int PER = D / 32;
@@ -272,7 +282,9 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
       long long o = (long long)row * D + c;
       float z = x[o] + (r ? r[o] : 0.f);
       xh[i] = (z - m) * rs;
-      float d = dy[o];
+      float d = dy ? dy[o] : 0.f;
+      if (dy2) d += __bfloat162float(dy2[o]);
+      if (dy3) d += __bfloat162float(dy3[o]);
       g[i] = d * gamma[c];
       ag[i] += d * xh[i];
       ab[i] += d;
@@ -341,8 +353,9 @@ using namespace tdb;
 extern "C" int tdb_stem_im2col(const float* x, void* col, int N, int H, int W, void* stream_) {
   TDB_REQUIRE(x && col && N > 0 && H > 0 && W > 0, "tdb_stem_im2col: bad args");
   int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  long long total = (long long)N * Ho * Wo * 24;
-  stem_im2col_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>(x, (bf16*)col, N, H, W, Ho, Wo);
+  size_t smem = (size_t)21 * (W + 6) * sizeof(float);
+  TDB_REQUIRE(smem <= 48 * 1024, "tdb_stem_im2col: frame width %d too large", W);
+  stem_im2col_kernel<<<(unsigned)(N * Ho), 256, smem, STREAM>>>(x, (bf16*)col, N, H, W, Ho, Wo);
   LAUNCH_OK();
 }
 extern "C" int tdb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
@@ -406,12 +419,12 @@ extern "C" int tdb_layernorm_bwd_blocks(int rows) {
   int b = (rows + 7) / 8;
   return b > 296 ? 296 : b;
 }
-extern "C" int tdb_layernorm_bwd(const float* dy, const float* x, const float* r, const float* gamma, const float* mean,
-                                 const float* rstd, float* dz, float* dgamma, float* dbeta, float* partial, int rows, int D,
-                                 int accumulate, void* stream_) {
-  TDB_REQUIRE(dy && x && gamma && mean && rstd && dz && partial && rows > 0 && D == 256, "tdb_layernorm_bwd: bad args");
+extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void* dy3_bf, const float* x, const float* r,
+                                 const float* gamma, const float* mean, const float* rstd, float* dz, float* dgamma,
+                                 float* dbeta, float* partial, int rows, int D, int accumulate, void* stream_) {
+  TDB_REQUIRE((dy || dy2_bf || dy3_bf) && x && gamma && mean && rstd && dz && partial && rows > 0 && D == 256, "tdb_layernorm_bwd: bad args");
   int blocks = tdb_layernorm_bwd_blocks(rows);
-  layernorm_bwd_kernel<256><<<blocks, 256, 0, STREAM>>>(dy, x, r, gamma, mean, rstd, dz, partial, rows);
+  layernorm_bwd_kernel<256><<<blocks, 256, 0, STREAM>>>(dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, partial, rows);
   TDB_CHECK_CUDA(cudaGetLastError());
   if (dgamma) colsum_partials_kernel<<<4, 64, 0, STREAM>>>(partial, blocks, 2 * D, D, dgamma, accumulate);
   if (dbeta) colsum_partials_kernel<<<4, 64, 0, STREAM>>>(partial + D, blocks, 2 * D, D, dbeta, accumulate);

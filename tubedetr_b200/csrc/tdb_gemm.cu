@@ -47,6 +47,7 @@ struct GemmKParams {
   long long ldo;
   int remap, img_h, img_w;
   int debug_flags;
+  int epi_mode;
 };
 
 template <int BN>
@@ -84,7 +85,7 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKParams& p, int w, int
   return it;
 }
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmKParams p) {
@@ -244,63 +245,180 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(wq * 32) << 16);
-      const int valid_i = valid ? 1 : 0;
-      // Each warp transposes its own 32 rows x 64 columns through a private XOR-swizzled smem tile so that global
-      // traffic is row-contiguous: phase 1 = thread-per-row TMEM -> smem (float4, conflict-free),
-      // phase 2 = half-warp-per-row: 16 lanes x 4 columns = 128 B (bf16) / 256 B (fp32) contiguous per row.
-      float4* st4 = reinterpret_cast<float4*>(stage);
-      const int hl = lane & 15;        // column group (4 columns) within the 64-column chunk
-      const int hsel = lane >> 4;      // which of the two rows this half-warp handles
+      if constexpr (EPI == 0) {
+        // ---- mode 0: thread-per-row, registers -> global (16-byte stores, row-strided)
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 64) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int c = 0; c < BN; c += 32) {
           uint32_t r[32];
-          tmem_ld_32x32(taddr + c + half * 32, r);
+          tmem_ld_32x32(taddr + c, r);
           tmem_ld_wait();
+          if (valid) {
+            float v[32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            st4[lane * 16 + ((half * 8 + q) ^ (lane & 15))] =
-                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                            __uint_as_float(r[4 * q + 3]));
-        }
-        __syncwarp();
-        const int col = wi.n0 + c + hl * 4;       // column in scale/bias/mask/residual space
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.scale != nullptr) sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
-        if (p.bias != nullptr) bi = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll 4
-        for (int rr = 0; rr < 32; rr += 2) {
-          const int myr = rr + hsel;
-          const int v_ok = __shfl_sync(0xffffffffu, valid_i, myr);
-          const long long orow = __shfl_sync(0xffffffffu, out_row, myr);
-          if (v_ok) {
-            float4 v = st4[myr * 16 + (hl ^ (myr & 15))];
-            v.x = v.x * sc.x + bi.x; v.y = v.y * sc.y + bi.y; v.z = v.z * sc.z + bi.z; v.w = v.w * sc.w + bi.w;
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            const int col = wi.n0 + c;  // column in scale/bias/mask/residual space
+            if (p.scale != nullptr) {
+              const float4* sp = reinterpret_cast<const float4*>(p.scale + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 s = __ldg(sp + i);
+                v[4 * i] *= s.x; v[4 * i + 1] *= s.y; v[4 * i + 2] *= s.z; v[4 * i + 3] *= s.w;
+              }
+            }
+            if (p.bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 s = __ldg(bp + i);
+                v[4 * i] += s.x; v[4 * i + 1] += s.y; v[4 * i + 2] += s.z; v[4 * i + 3] += s.w;
+              }
+            }
             if (p.residual != nullptr) {
-              uint2 u = __ldg(reinterpret_cast<const uint2*>(p.residual + orow * p.ldr + col));
-              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
-              v.x += f0.x; v.y += f0.y; v.z += f1.x; v.w += f1.y;
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + out_row * p.ldr + col);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u = __ldg(rp + i);
+                float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
+                v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+              }
             }
             if (p.relu) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
             if (p.mask != nullptr) {
-              const long long trow = (long long)(wi.m0 + wq * 32 + myr);
-              uint2 u = __ldg(reinterpret_cast<const uint2*>(p.mask + trow * p.ldmask + col));
-              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y);
-              v.x = f0.x > 0.f ? v.x : 0.f; v.y = f0.y > 0.f ? v.y : 0.f;
-              v.z = f1.x > 0.f ? v.z : 0.f; v.w = f1.y > 0.f ? v.w : 0.f;
+              const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (long long)row_t * p.ldmask + col);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u = __ldg(mp + i);
+                float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                v[8 * i] = f0.x > 0.f ? v[8 * i] : 0.f;         v[8 * i + 1] = f0.y > 0.f ? v[8 * i + 1] : 0.f;
+                v[8 * i + 2] = f1.x > 0.f ? v[8 * i + 2] : 0.f; v[8 * i + 3] = f1.y > 0.f ? v[8 * i + 3] : 0.f;
+                v[8 * i + 4] = f2.x > 0.f ? v[8 * i + 4] : 0.f; v[8 * i + 5] = f2.y > 0.f ? v[8 * i + 5] : 0.f;
+                v[8 * i + 6] = f3.x > 0.f ? v[8 * i + 6] : 0.f; v[8 * i + 7] = f3.y > 0.f ? v[8 * i + 7] : 0.f;
+              }
             }
-            const long long o = orow * p.ldo + out_col0 + c + hl * 4;
             if (p.out_f32) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = v;
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             } else {
-              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
             }
           }
         }
-        __syncwarp();
+      } else {
+        // ---- mode 1: each warp transposes its own 32 rows x 64 columns through a private XOR-swizzled smem tile so that
+        // global traffic is row-contiguous: phase 1 = thread-per-row TMEM -> smem (float4, conflict-free), phase 2 =
+        // quarter-warp-per-row: 8 lanes x 8 columns = 128 B (bf16) / 256 B (fp32) contiguous per row, 4 rows per instruction.
+        // The residual / mask operands of a chunk are prefetched (8 independent 16-byte loads per lane) before phase 1.
+        float4* st4 = reinterpret_cast<float4*>(stage);
+        const int hl = lane & 7;         // column group (8 columns) within the 64-column chunk
+        const int g = lane >> 3;         // row within each group of 4 rows
+        int orow_k[8];                   // output rows (32-bit: row counts stay far below 2^31)
+        uint32_t vmask = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int tr = wi.m0 + wq * 32 + 4 * k + g;
+          bool ok = tr < p.M;
+          long long orow = tr;
+          if (p.remap == TDB_REMAP_COMPACT_TO_PADDED) {
+            int hw = p.img_h * p.img_w;
+            int n = tr / hw;
+            int rem = tr - n * hw;
+            int h = rem / p.img_w;
+            int x = rem - h * p.img_w;
+            orow = ((long long)n * Hp + h + 1) * Wp + x + 1;
+          } else if (p.remap == TDB_REMAP_PADDED_TO_COMPACT) {
+            int hw = Hp * Wp;
+            int n = tr / hw;
+            int rem = tr - n * hw;
+            int h = rem / Wp;
+            int x = rem - h * Wp;
+            ok = ok && h >= 1 && h <= p.img_h && x >= 1 && x <= p.img_w;
+            orow = ((long long)n * p.img_h + (h - 1)) * p.img_w + (x - 1);
+          }
+          if (p.splits > 1) orow += (long long)wi.split * p.M;
+          orow_k[k] = (int)orow;
+          vmask |= (ok ? 1u : 0u) << k;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          const int col = wi.n0 + c + hl * 8;       // column in scale/bias/mask/residual space
+          uint4 res[8], msk[8];
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              res[k] = ((vmask >> k) & 1) ? __ldg(reinterpret_cast<const uint4*>(p.residual + (long long)orow_k[k] * p.ldr + col))
+                                          : make_uint4(0, 0, 0, 0);
+          }
+          if (p.mask != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              msk[k] = ((vmask >> k) & 1)
+                           ? __ldg(reinterpret_cast<const uint4*>(p.mask + (long long)(wi.m0 + wq * 32 + 4 * k + g) * p.ldmask + col))
+                           : make_uint4(0, 0, 0, 0);
+          }
+          float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0, bi0 = make_float4(0.f, 0.f, 0.f, 0.f), bi1 = bi0;
+          if (p.scale != nullptr) {
+            sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+            sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + col + 4));
+          }
+          if (p.bias != nullptr) {
+            bi0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            bi1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c + half * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              st4[lane * 16 + ((half * 8 + q) ^ (lane & 15))] =
+                  make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                              __uint_as_float(r[4 * q + 3]));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if ((vmask >> k) & 1) {
+              const int myr = 4 * k + g;
+              float4 v0 = st4[myr * 16 + ((2 * hl) ^ (myr & 15))];
+              float4 v1 = st4[myr * 16 + ((2 * hl + 1) ^ (myr & 15))];
+              v0.x = v0.x * sc0.x + bi0.x; v0.y = v0.y * sc0.y + bi0.y; v0.z = v0.z * sc0.z + bi0.z; v0.w = v0.w * sc0.w + bi0.w;
+              v1.x = v1.x * sc1.x + bi1.x; v1.y = v1.y * sc1.y + bi1.y; v1.z = v1.z * sc1.z + bi1.z; v1.w = v1.w * sc1.w + bi1.w;
+              if (p.residual != nullptr) {
+                float2 f0 = unpack_bf16x2(res[k].x), f1 = unpack_bf16x2(res[k].y), f2 = unpack_bf16x2(res[k].z), f3 = unpack_bf16x2(res[k].w);
+                v0.x += f0.x; v0.y += f0.y; v0.z += f1.x; v0.w += f1.y; v1.x += f2.x; v1.y += f2.y; v1.z += f3.x; v1.w += f3.y;
+              }
+              if (p.relu) {
+                v0.x = fmaxf(v0.x, 0.f); v0.y = fmaxf(v0.y, 0.f); v0.z = fmaxf(v0.z, 0.f); v0.w = fmaxf(v0.w, 0.f);
+                v1.x = fmaxf(v1.x, 0.f); v1.y = fmaxf(v1.y, 0.f); v1.z = fmaxf(v1.z, 0.f); v1.w = fmaxf(v1.w, 0.f);
+              }
+              if (p.mask != nullptr) {
+                float2 f0 = unpack_bf16x2(msk[k].x), f1 = unpack_bf16x2(msk[k].y), f2 = unpack_bf16x2(msk[k].z), f3 = unpack_bf16x2(msk[k].w);
+                v0.x = f0.x > 0.f ? v0.x : 0.f; v0.y = f0.y > 0.f ? v0.y : 0.f; v0.z = f1.x > 0.f ? v0.z : 0.f; v0.w = f1.y > 0.f ? v0.w : 0.f;
+                v1.x = f2.x > 0.f ? v1.x : 0.f; v1.y = f2.y > 0.f ? v1.y : 0.f; v1.z = f3.x > 0.f ? v1.z : 0.f; v1.w = f3.y > 0.f ? v1.w : 0.f;
+              }
+              const long long o = (long long)orow_k[k] * p.ldo + out_col0 + c + hl * 8;
+              if (p.out_f32) {
+                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+                op[0] = v0;
+                op[1] = v1;
+              } else {
+                *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + o) =
+                    make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+              }
+            }
+          }
+          __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -387,9 +505,12 @@ int tdb_init_once() {
     return TDB_ERR_DRIVER;
   }
   g_num_sms = prop.multiProcessorCount;
-  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
-  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
-  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   g_encode = (EncodeTiledFn)fn;
   return TDB_OK;
 }
@@ -477,6 +598,12 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   p.relu = d->relu; p.out = d->out; p.out_f32 = d->out_dtype == TDB_OUT_F32; p.ldo = d->ldo;
   p.remap = d->remap; p.img_h = d->img_h; p.img_w = d->img_w;
   p.debug_flags = d->debug_flags;
+  {
+    static int env_mode = -2;
+    if (env_mode == -2) { const char* e = getenv("TDB_EPI_MODE"); env_mode = e ? atoi(e) : -1; }
+    int m = (d->debug_flags >> 1) & 3;            // 0 = auto, 1 = force direct, 2 = force staged
+    p.epi_mode = m == 1 ? 0 : (m == 2 ? 1 : (env_mode >= 0 ? env_mode : 0));
+  }
   TDB_REQUIRE(p.ldo % 8 == 0 && (!p.residual || p.ldr % 8 == 0) && (!p.mask || p.ldmask % 8 == 0), "tdb_gemm: leading dims must be multiples of 8");
 
   CUtensorMap tmA, tmB;
@@ -487,11 +614,21 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
 
   int grid = p.total_work < g_num_sms ? p.total_work : g_num_sms;
   if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-  switch (bn) {
-    case 64: tdb_gemm_kernel<64><<<grid, kGemmThreads, GemmCfg<64>::kSmemBytes, stream>>>(tmA, tmB, p); break;
-    case 128: tdb_gemm_kernel<128><<<grid, kGemmThreads, GemmCfg<128>::kSmemBytes, stream>>>(tmA, tmB, p); break;
-    default: tdb_gemm_kernel<256><<<grid, kGemmThreads, GemmCfg<256>::kSmemBytes, stream>>>(tmA, tmB, p); break;
+#define TDB_LAUNCH(BN_, EPI_) tdb_gemm_kernel<BN_, EPI_><<<grid, kGemmThreads, GemmCfg<BN_>::kSmemBytes, stream>>>(tmA, tmB, p)
+  if (p.epi_mode == 0) {
+    switch (bn) {
+      case 64: TDB_LAUNCH(64, 0); break;
+      case 128: TDB_LAUNCH(128, 0); break;
+      default: TDB_LAUNCH(256, 0); break;
+    }
+  } else {
+    switch (bn) {
+      case 64: TDB_LAUNCH(64, 1); break;
+      case 128: TDB_LAUNCH(128, 1); break;
+      default: TDB_LAUNCH(256, 1); break;
+    }
   }
+#undef TDB_LAUNCH
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   static FILE* logf = nullptr;

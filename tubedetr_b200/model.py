@@ -261,8 +261,8 @@ class Transformer(nn.Module):
         o, _ = ops.mha(qk, None, v, kpm, n, NHEAD, S, S, 32 ** -0.5, packed=True)
         att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
         x32, xb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias)
-        hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True)
-        f = ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True)
+        hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True, masked_by_consumer=True)
+        f = ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True, mask_dx=True)
         if need_pos:
             return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias, pos)
         return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias) + (None,)
@@ -284,8 +284,8 @@ class Transformer(nn.Module):
         o, cw = ops.mha(q, k, v, kpm_mem, B * T, NHEAD, 1, S, 32 ** -0.5)
         att = ops.linear(o, c.out_proj.weight, c.out_proj.bias, out_fp32=True)
         x32, xb = ops.add_layernorm(x32, att, l.norm3.weight, l.norm3.bias)
-        hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True)
-        f = ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True)
+        hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True, masked_by_consumer=True)
+        f = ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True, mask_dx=True)
         x32, xb, xqb = ops.add_layernorm(x32, f, l.norm4.weight, l.norm4.bias, qp)
         return x32, xb, xqb, w, cw
 

@@ -43,7 +43,10 @@ class LinearFn(torch.autograd.Function):
     """y = relu?(x @ W^T + b): x bf16 [R,K], W fp32 [N,K] (bf16 copy cached), y bf16 or fp32 [R,N]."""
 
     @staticmethod
-    def forward(ctx, x, W, b, relu, out_fp32):
+    def forward(ctx, x, W, b, relu, out_fp32, mask_dx=False, masked_by_consumer=False):
+        # mask_dx: x is a post-ReLU activation -> dgrad applies (x > 0) in its epilogue (ReLU backward of the producer);
+        # masked_by_consumer: this op's own ReLU backward is done by the consumer that way.
+        ctx.mask_dx, ctx.masked_by_consumer = mask_dx, masked_by_consumer
         assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
         Wb = bf16_weight(W)
         R, Kd = x.shape
@@ -59,7 +62,7 @@ class LinearFn(torch.autograd.Function):
         x, W, y = ctx.saved_tensors
         Wb = bf16_weight(W)
         dyb = _as_bf16(dy)
-        if ctx.relu:
+        if ctx.relu and not ctx.masked_by_consumer:
             dyb = dyb * (y > 0)
         dyb = dyb.contiguous()
         R, Kd = x.shape
@@ -67,16 +70,16 @@ class LinearFn(torch.autograd.Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(R, Kd, dtype=torch.bfloat16, device=x.device)
-            gemm(dyb, Wb, dx, R, Kd, N, b_major=1)
+            gemm(dyb, Wb, dx, R, Kd, N, b_major=1, mask=x if ctx.mask_dx else None)
         if ctx.needs_input_grad[1]:
             dW = wgrad_into(dyb, x, torch.empty(N, Kd, dtype=torch.float32, device=x.device))
         if ctx.needs_input_grad[2]:
             db = K.colsum_bf16(dyb, torch.empty(N, dtype=torch.float32, device=x.device))
-        return dx, dW, db, None, None
+        return dx, dW, db, None, None, None, None
 
 
-def linear(x, W, b, relu=False, out_fp32=False):
-    return LinearFn.apply(x, W, b, relu, out_fp32)
+def linear(x, W, b, relu=False, out_fp32=False, mask_dx=False, masked_by_consumer=False):
+    return LinearFn.apply(x, W, b, relu, out_fp32, mask_dx, masked_by_consumer)
 
 
 class InProjFn(torch.autograd.Function):
@@ -194,17 +197,15 @@ class AddLayerNormFn(torch.autograd.Function):
     def backward(ctx, dy, dyb, dypb=None):
         x, r, gamma, mean, rstd = ctx.saved_tensors
         rows, D = x.shape
-        g = None
-        for t in (dy, dyb, dypb):
-            if t is not None:
-                g = t.float() if g is None else g + t.float()
-        if g is None:
+        if dy is None and dyb is None and dypb is None:
             return None, None, None, None, None, None
-        g = g.contiguous()
+        dy = dy.contiguous() if dy is not None else None
+        dyb = dyb.contiguous() if dyb is not None else None
+        dypb = dypb.contiguous() if dypb is not None else None
         dz = torch.empty_like(x)
         dg = torch.empty(D, dtype=torch.float32, device=x.device)
         db = torch.empty(D, dtype=torch.float32, device=x.device)
-        K.layernorm_bwd(g, x, r, gamma, mean, rstd, dz, dg, db, rows, D)
+        K.layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dg, db, rows, D, dy2=dyb, dy3=dypb)   # sums the three grads in-kernel
         dpos = None
         if ctx.needs_input_grad[4] and dypb is not None:   # (y + pos): pos is the time-query embedding in the decoder
             dpos = dypb.to(ctx.pos_dtype)
