@@ -131,6 +131,22 @@ int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
                 int64_t lddo, const float* p, const float* dpbar, float* ds_scratch, void* dq, int64_t lddq, void* dk,
                 int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused time-aligned cross-attention of the space-time decoder (reference models/transformer.py:724-745):
+ * K/V projection of the frame memories on tcgen05 (accumulators in TMEM) + scores + softmax + context in ONE kernel, K and V
+ * never written to HBM; a small merge kernel combines the per-tile segments of each frame.
+ *   q      [F][256] bf16   projected (bias included), unscaled queries, one per frame
+ *   mempb  [F*S][256] bf16 memory + position embedding (key input);  memb [F*S][256] bf16 memory (value input)
+ *   wkv    [512][256] bf16 rows 256..767 of in_proj_weight (Wk then Wv);  bv [256] fp32 value bias (bk cancels in softmax)
+ *   kpm    [F][S] nonzero = padded key
+ *   o [F][256] bf16 context (before out_proj);  p [F][8][S] fp32 probabilities;  pbar [F][S] head mean (may be NULL)
+ * S must be >= 43 (a 128-row tile may touch at most 4 frames).
+ * ------------------------------------------------------------------------------------------------ */
+int64_t tdb_xattn_workspace_bytes(int F, int S);
+int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, const void* wkv, const float* bv,
+                        const uint8_t* kpm, void* o, float* p, float* pbar, void* workspace, int64_t ws_bytes, int F, int S,
+                        float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,3 +171,31 @@ def test_colsum_and_cast():
     y = torch.empty(300, 256, dtype=torch.bfloat16, device="cuda")
     K.cast_add_bf16(a, b, y)
     assert torch.equal(y, (a + b).bfloat16())
+
+
+@pytest.mark.parametrize("F,S", [(100, 141), (8, 59), (3, 43), (37, 200)])
+def test_xattn_fused_matches_unfused_math(F, S):
+    """fused KV-projection + cross-attention (tcgen05/TMEM) vs fp32 torch on the same bf16 operands."""
+    from tubedetr_b200 import kernels as K
+    d, H = 256, 8
+    scale = 1 / math.sqrt(32)
+    q = _r((F, d), 40)
+    mem, pos = _r((F * S, d), 41), _r((F * S, d), 42) * 0.5
+    memb, mempb = mem, (mem.float() + pos.float()).bfloat16()
+    W = (_r((3 * d, d), 43, torch.float32) / 16).bfloat16()
+    b = _r((3 * d,), 44, torch.float32) * 0.1
+    kpm = torch.zeros(F, S, dtype=torch.uint8, device="cuda")
+    kpm[:, S - S // 4:] = 1
+    kpm[0] = 0
+    kpm[1, 1:] = 1          # a frame with a single visible key
+    o = torch.empty(F, d, dtype=torch.bfloat16, device="cuda")
+    p = torch.empty(F, H, 1, S, device="cuda")
+    pbar = torch.empty(F, 1, S, device="cuda")
+    K.xattn_fused_fwd(q, mempb, memb, W[d:], b[2 * d:], kpm, o, p, pbar, F, S, scale)
+    kk = (mempb.float() @ W[d:2 * d].float().t() + b[d:2 * d]).view(F, S, d)
+    vv = (memb.float() @ W[2 * d:].float().t() + b[2 * d:]).view(F, S, d)
+    ro, rp = _ref_attn(q.float().view(F, 1, d), kk, vv, kpm, H, scale)
+    _close(p, rp, 2e-2)
+    _close(pbar, rp.mean(1), 2e-2)
+    _close(o.view(F, 1, d), ro, 2e-2)
+    assert torch.isfinite(o.float()).all()

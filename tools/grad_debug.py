@@ -60,11 +60,11 @@ def main(name="cfg1b"):
     feat_g = {}
     orig_lin = ops.linear
 
-    def lin_wrapped(x, W, b, relu=False, out_fp32=False):
+    def lin_wrapped(x, W, b, *a, **k):
         if "feat" not in feat_g and x.shape[1] == 2048 and x.requires_grad:
             feat_g["feat"] = x
             x.register_hook(lambda g: feat_g.__setitem__("g", g.detach().float().cpu()))
-        return orig_lin(x, W, b, relu, out_fp32)
+        return orig_lin(x, W, b, *a, **k)
     ops.linear = lin_wrapped
     model, crit, wd, b, mc, out = T._run(cfg)
     tr._enc_layer = orig

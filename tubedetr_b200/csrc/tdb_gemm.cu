@@ -242,10 +242,105 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int out_col0 = wi.n0 + p.z_out_col[wi.z];
       if (p.splits > 1) out_row += (long long)wi.split * p.M;
 
+      // mode 2: software-pipelined register prefetch of the row-wise epilogue operands (residual, ReLU mask).  The first
+      // chunks are requested BEFORE the accumulator is ready, so their HBM latency hides behind this tile's main loop.
+      constexpr int NCH = BN / 32;
+      constexpr int PFR = NCH < 4 ? NCH : 4;   // residual prefetch depth (chunks of 32 columns = 4 x 16 B per thread)
+      constexpr int PFM = NCH < 2 ? NCH : 2;   // mask prefetch depth
+      uint4 rbuf[PFR][4], mbuf[PFM][4];
+      const bf16* res_row = p.residual ? p.residual + out_row * p.ldr + wi.n0 : nullptr;
+      const bf16* msk_row = p.mask ? p.mask + (long long)row_t * p.ldmask + wi.n0 : nullptr;
+      if constexpr (EPI == 2) {
+        if (valid && res_row) {
+#pragma unroll
+          for (int ci = 0; ci < PFR; ++ci)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rbuf[ci][i] = __ldg(reinterpret_cast<const uint4*>(res_row + ci * 32) + i);
+        }
+        if (valid && msk_row) {
+#pragma unroll
+          for (int ci = 0; ci < PFM; ++ci)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mbuf[ci][i] = __ldg(reinterpret_cast<const uint4*>(msk_row + ci * 32) + i);
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(wq * 32) << 16);
-      if constexpr (EPI == 0) {
+      if constexpr (EPI == 2) {
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = ci * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            const int col = wi.n0 + c;
+            if (p.scale != nullptr) {
+              const float4* sp = reinterpret_cast<const float4*>(p.scale + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 s = __ldg(sp + i);
+                v[4 * i] *= s.x; v[4 * i + 1] *= s.y; v[4 * i + 2] *= s.z; v[4 * i + 3] *= s.w;
+              }
+            }
+            if (p.bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 s = __ldg(bp + i);
+                v[4 * i] += s.x; v[4 * i + 1] += s.y; v[4 * i + 2] += s.z; v[4 * i + 3] += s.w;
+              }
+            }
+            if (res_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u = rbuf[ci % PFR][i];
+                float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
+                v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+              }
+              if (ci + PFR < NCH) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rbuf[ci % PFR][i] = __ldg(reinterpret_cast<const uint4*>(res_row + (ci + PFR) * 32) + i);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (msk_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u = mbuf[ci % PFM][i];
+                float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                v[8 * i] = f0.x > 0.f ? v[8 * i] : 0.f;         v[8 * i + 1] = f0.y > 0.f ? v[8 * i + 1] : 0.f;
+                v[8 * i + 2] = f1.x > 0.f ? v[8 * i + 2] : 0.f; v[8 * i + 3] = f1.y > 0.f ? v[8 * i + 3] : 0.f;
+                v[8 * i + 4] = f2.x > 0.f ? v[8 * i + 4] : 0.f; v[8 * i + 5] = f2.y > 0.f ? v[8 * i + 5] : 0.f;
+                v[8 * i + 6] = f3.x > 0.f ? v[8 * i + 6] : 0.f; v[8 * i + 7] = f3.y > 0.f ? v[8 * i + 7] : 0.f;
+              }
+              if (ci + PFM < NCH) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mbuf[ci % PFM][i] = __ldg(reinterpret_cast<const uint4*>(msk_row + (ci + PFM) * 32) + i);
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            }
+          }
+        }
+      } else if constexpr (EPI == 0) {
         // ---- mode 0: thread-per-row, registers -> global (16-byte stores, row-strided)
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
@@ -507,10 +602,13 @@ int tdb_init_once() {
   g_num_sms = prop.multiProcessorCount;
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   g_encode = (EncodeTiledFn)fn;
   return TDB_OK;
 }
@@ -601,8 +699,8 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   {
     static int env_mode = -2;
     if (env_mode == -2) { const char* e = getenv("TDB_EPI_MODE"); env_mode = e ? atoi(e) : -1; }
-    int m = (d->debug_flags >> 1) & 3;            // 0 = auto, 1 = force direct, 2 = force staged
-    p.epi_mode = m == 1 ? 0 : (m == 2 ? 1 : (env_mode >= 0 ? env_mode : 0));
+    int m = (d->debug_flags >> 1) & 3;            // 0 = auto, 1 = direct, 2 = smem-staged, 3 = direct + register prefetch
+    p.epi_mode = m ? m - 1 : (env_mode >= 0 ? env_mode : 2);
   }
   TDB_REQUIRE(p.ldo % 8 == 0 && (!p.residual || p.ldr % 8 == 0) && (!p.mask || p.ldmask % 8 == 0), "tdb_gemm: leading dims must be multiples of 8");
 
@@ -621,11 +719,17 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
       case 128: TDB_LAUNCH(128, 0); break;
       default: TDB_LAUNCH(256, 0); break;
     }
-  } else {
+  } else if (p.epi_mode == 1) {
     switch (bn) {
       case 64: TDB_LAUNCH(64, 1); break;
       case 128: TDB_LAUNCH(128, 1); break;
       default: TDB_LAUNCH(256, 1); break;
+    }
+  } else {
+    switch (bn) {
+      case 64: TDB_LAUNCH(64, 2); break;
+      case 128: TDB_LAUNCH(128, 2); break;
+      default: TDB_LAUNCH(256, 2); break;
     }
   }
 #undef TDB_LAUNCH

@@ -1,0 +1,364 @@
+// tubedetr_b200 -- fused time-aligned cross-attention of the space-time decoder (sm_100a, tcgen05 + TMEM + TMA).
+//
+// Reference: models/transformer.py:724-745 (cross_attn_image): per frame f ONE query attends to that frame's S memory
+// tokens; K = (memory + pos) Wk^T + bk, V = memory Wv^T + bv.  The K/V projections are 92 % of the decoder FLOPs
+// (SURVEY.md 7.H1).  This kernel computes, per 128-row tile of the flat [frames*S][256] memory matrix,
+//     K tile = mempb[128x256] x Wk^T  -> TMEM columns [0,256)      (tcgen05.mma, bf16 x bf16 -> fp32)
+//     V tile = memb [128x256] x Wv^T  -> TMEM columns [256,512)
+// and consumes them straight out of TMEM: scores s[j,h] = scale * q[f(j),h,:] . K[j,h,:] (+ key padding mask), a
+// segment-local softmax over the rows of each frame inside the tile, and the partial context sum_j p[j,h] V[j,h,:].
+// K and V never go to HBM.  Frames straddle tiles (S = 141 does not divide 128), so every (tile, frame) segment emits
+// flash-style partials (m, l, o[256]) that tdb_xattn_merge combines (<= 3 segments per frame), also normalising the
+// probabilities that the backward pass and the `ca_weights` output need.
+// The K bias bk only shifts all scores of a frame by q.bk, which the softmax cancels, so it is not applied; bv is added
+// after normalisation (sum_j p = 1).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = consumers (one TMEM lane = one memory token).
+#include "../../include/tubedetr_b200.h"
+#include "tdb_common.cuh"
+
+void tdb_count_launch(int n);
+int tdb_init_once();
+int tdb_make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+int tdb_num_sms();
+
+namespace tdb {
+
+constexpr int XD = 256;            // model width
+constexpr int XH = 8;              // heads (head dim 32)
+constexpr int XBM = 128;           // memory rows per tile
+constexpr int XMAXF = 4;           // max frames touched by one tile (needs S >= 43)
+constexpr int XSTAGES = 4;
+constexpr int XSTAGE_BYTES = XBM * 64 * 2 + XD * 64 * 2;   // A 16 KB + B 32 KB per 64-wide k-block
+constexpr int XTHREADS = 256;
+
+struct XattnSmem {
+  // after the stage ring
+  uint64_t full[XSTAGES], empty[XSTAGES], kfull, vfull;
+  uint32_t tmem_slot, pad;
+  float qs[XMAXF][XD];             // scale * q of the frames in this tile
+  float owarp[4][XMAXF][XD];       // per-consumer-warp partial contexts
+  float wmax[4][XMAXF][XH];
+  float wsum[4][XMAXF][XH];
+};
+constexpr int XSMEM_BYTES = XSTAGES * XSTAGE_BYTES + 1024 + (int)sizeof(XattnSmem);
+
+struct XattnParams {
+  const bf16* q;        // [F][256] projected queries (bias included), unscaled
+  const uint8_t* kpm;   // [F][S] nonzero = padded key
+  float* p;             // [F][8][S]  out: exp(s - m_tile) (normalised later by the merge kernel)
+  float* part_m;        // [tiles][XMAXF][8]
+  float* part_l;        // [tiles][XMAXF][8]
+  float* part_o;        // [tiles][XMAXF][256]
+  int R, S, F;
+  float scale;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(XTHREADS, 1)
+xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ XattnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  XattnSmem& sh = *reinterpret_cast<XattnSmem*>(smem + XSTAGES * XSTAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int row0 = tile * XBM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < XSTAGES; ++s) {
+      mbar_init(&sh.full[s], 1);
+      mbar_init(&sh.empty[s], 1);
+    }
+    mbar_init(&sh.kfull, 1);
+    mbar_init(&sh.vfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&sh.tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < 8; ++it) {        // 4 k-blocks for K, then 4 for V
+        const int kk = it & 3;
+        mbar_wait(&sh.empty[stage], phase ^ 1, 11);
+        mbar_expect_tx(&sh.full[stage], XSTAGE_BYTES);
+        uint8_t* sA = smem + stage * XSTAGE_BYTES;
+        uint8_t* sB = sA + XBM * 64 * 2;
+        tma_load_2d(sA, it < 4 ? &tmK : &tmV, &sh.full[stage], kk * 64, row0);
+        tma_load_2d(sB, &tmW, &sh.full[stage], kk * 64, it < 4 ? 0 : XD);   // Wk rows [0,256), Wv rows [256,512)
+        if (++stage == XSTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(XBM, XD, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < 8; ++it) {
+        mbar_wait(&sh.full[stage], phase, 12);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * XSTAGE_BYTES);
+        const uint32_t b_base = a_base + XBM * 64 * 2;
+        const uint32_t d_tmem = tmem_base + (it < 4 ? 0 : XD);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma_bf16(d_tmem, umma_smem_desc(a_base + s * 32, 16, 1024), umma_smem_desc(b_base + s * 32, 16, 1024), idesc,
+                    ((it & 3) > 0 || s > 0) ? 1u : 0u);
+        umma_commit(&sh.empty[stage]);
+        if (it == 3) umma_commit(&sh.kfull);
+        if (it == 7) umma_commit(&sh.vfull);
+        if (++stage == XSTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ consumers: thread = memory token (TMEM lane)
+    const int wq = warp & 3;
+    const int tid = threadIdx.x - 128;                    // 0..127
+    const int j = row0 + wq * 32 + lane;                  // flat memory row
+    const bool valid = j < p.R;
+    const int f0 = row0 / p.S;                            // first frame of the tile
+    const int f = valid ? j / p.S : 0x3fffffff;
+    const int tok = valid ? j - f * p.S : 0;
+    const int fl = valid ? f - f0 : XMAXF;                // local frame index, XMAXF = "none"
+    const int last_row = (row0 + XBM - 1 < p.R - 1) ? row0 + XBM - 1 : p.R - 1;
+    const int nfr = last_row / p.S - f0 + 1;              // frames in this tile (<= XMAXF, checked on the host)
+    // stage scale*q of the tile's frames, clear accumulators
+    for (int e = tid; e < XMAXF * XD; e += 128) {
+      int ff = e / XD, c = e - ff * XD;
+      float v = 0.f;
+      if (ff < nfr) v = __bfloat162float(p.q[(long long)(f0 + ff) * XD + c]) * p.scale;
+      sh.qs[ff][c] = v;
+    }
+    for (int e = tid; e < 4 * XMAXF * XD; e += 128) (&sh.owarp[0][0][0])[e] = 0.f;
+    named_bar_sync(1, 128);
+    const bool masked = valid ? (p.kpm != nullptr && p.kpm[(long long)f * p.S + tok] != 0) : true;
+    // warp-uniform range of local frames present in this warp
+    const int fl_lo = __shfl_sync(0xffffffffu, fl, 0);
+    int fl_hi_l = valid ? fl : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fl_hi_l = max(fl_hi_l, __shfl_xor_sync(0xffffffffu, fl_hi_l, o));
+    const int fl_hi = fl_hi_l;
+
+    // ---- scores from the K accumulator
+    mbar_wait(&sh.kfull, 0, 13);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    float s[XH];
+    const float* qrow = sh.qs[fl < XMAXF ? fl : 0];
+#pragma unroll
+    for (int h = 0; h < XH; ++h) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + h * 32, r);
+      tmem_ld_wait();
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) acc += __uint_as_float(r[d]) * qrow[h * 32 + d];
+      s[h] = (masked || !valid) ? -INFINITY : acc;
+    }
+    // ---- segment-local softmax statistics: per (local frame, head) max and sum over this tile's rows
+#pragma unroll
+    for (int h = 0; h < XH; ++h) {
+      for (int ff = fl_lo; ff <= fl_hi; ++ff) {
+        float m = warp_max(fl == ff ? s[h] : -INFINITY);
+        if (lane == 0) sh.wmax[wq][ff][h] = m;
+      }
+    }
+    if (lane < XH) {
+      for (int ff = 0; ff < XMAXF; ++ff)
+        if (ff < fl_lo || ff > fl_hi) sh.wmax[wq][ff][lane] = -INFINITY;
+    }
+    named_bar_sync(1, 128);
+    float pt[XH];
+#pragma unroll
+    for (int h = 0; h < XH; ++h) {
+      float m = -INFINITY;
+      if (fl < XMAXF) m = fmaxf(fmaxf(sh.wmax[0][fl][h], sh.wmax[1][fl][h]), fmaxf(sh.wmax[2][fl][h], sh.wmax[3][fl][h]));
+      pt[h] = (s[h] == -INFINITY) ? 0.f : __expf(s[h] - m);
+    }
+#pragma unroll
+    for (int h = 0; h < XH; ++h) {
+      for (int ff = fl_lo; ff <= fl_hi; ++ff) {
+        float l = warp_sum(fl == ff ? pt[h] : 0.f);
+        if (lane == 0) sh.wsum[wq][ff][h] = l;
+      }
+    }
+    if (lane < XH) {
+      for (int ff = 0; ff < XMAXF; ++ff)
+        if (ff < fl_lo || ff > fl_hi) sh.wsum[wq][ff][lane] = 0.f;
+    }
+    if (valid) {
+#pragma unroll
+      for (int h = 0; h < XH; ++h) p.p[((long long)f * XH + h) * p.S + tok] = pt[h];
+    }
+    // ---- partial context from the V accumulator: o[ff][h*32+d] += sum_j pt[j,h] V[j,h,d]
+    mbar_wait(&sh.vfull, 0, 14);
+    tc_fence_after();
+#pragma unroll 1
+    for (int h = 0; h < XH; ++h) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + XD + h * 32, r);
+      tmem_ld_wait();
+      for (int ff = fl_lo; ff <= fl_hi; ++ff) {
+        float v[32];
+        const float wgt = (fl == ff) ? pt[h] : 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) v[d] = wgt * __uint_as_float(r[d]);
+        // butterfly reduce-scatter: afterwards lane d holds sum over the 32 rows of column d
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            float send = up ? v[i] : v[i + off];
+            float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        sh.owarp[wq][ff][h * 32 + lane] = v[0];
+      }
+    }
+    named_bar_sync(1, 128);
+    // ---- emit the (tile, frame) partials
+    for (int e = tid; e < XMAXF * XD; e += 128) {
+      int ff = e / XD, c = e - ff * XD;
+      float o = sh.owarp[0][ff][c] + sh.owarp[1][ff][c] + sh.owarp[2][ff][c] + sh.owarp[3][ff][c];
+      p.part_o[((long long)tile * XMAXF + ff) * XD + c] = o;
+    }
+    if (tid < XMAXF * XH) {
+      int ff = tid / XH, h = tid - ff * XH;
+      float m = fmaxf(fmaxf(sh.wmax[0][ff][h], sh.wmax[1][ff][h]), fmaxf(sh.wmax[2][ff][h], sh.wmax[3][ff][h]));
+      float l = sh.wsum[0][ff][h] + sh.wsum[1][ff][h] + sh.wsum[2][ff][h] + sh.wsum[3][ff][h];
+      p.part_m[((long long)tile * XMAXF + ff) * XH + h] = m;
+      p.part_l[((long long)tile * XMAXF + ff) * XH + h] = l;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// one CTA per frame: combine the <= 3 tile segments, normalise probabilities, add bv, emit head-mean weights
+__global__ void __launch_bounds__(256) xattn_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                                                          const float* __restrict__ part_o, const float* __restrict__ bv,
+                                                          float* __restrict__ p, float* __restrict__ pbar, bf16* __restrict__ o,
+                                                          int S, int F) {
+  __shared__ float Ms[XH], Ls[XH];
+  __shared__ float fac[4][XH];       // exp(m_t - M) per segment
+  const int f = blockIdx.x;
+  const int t0 = (f * S) / XBM, t1 = (f * S + S - 1) / XBM;
+  const int h = threadIdx.x >> 5, d = threadIdx.x & 31;
+  if (d == 0) {
+    float M = -INFINITY;
+    for (int t = t0; t <= t1; ++t) {
+      int ff = f - (t * XBM) / S;
+      M = fmaxf(M, part_m[((long long)t * XMAXF + ff) * XH + h]);
+    }
+    float L = 0.f;
+    for (int t = t0; t <= t1; ++t) {
+      int ff = f - (t * XBM) / S;
+      float m = part_m[((long long)t * XMAXF + ff) * XH + h];
+      float e = (m == -INFINITY) ? 0.f : __expf(m - M);
+      fac[t - t0][h] = e;
+      L += part_l[((long long)t * XMAXF + ff) * XH + h] * e;
+    }
+    Ms[h] = M;
+    Ls[h] = L;
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int t = t0; t <= t1; ++t) {
+    int ff = f - (t * XBM) / S;
+    acc += part_o[((long long)t * XMAXF + ff) * XD + h * 32 + d] * fac[t - t0][h];
+  }
+  const float invL = 1.f / Ls[h];
+  o[(long long)f * XD + h * 32 + d] = __float2bfloat16(acc * invL + (bv ? bv[h * 32 + d] : 0.f));
+  for (int tok = d; tok < S; tok += 32) {
+    int t = (f * S + tok) / XBM;
+    long long idx = ((long long)f * XH + h) * S + tok;
+    p[idx] = p[idx] * fac[t - t0][h] * invL;
+  }
+  __syncthreads();
+  if (pbar) {
+    for (int tok = threadIdx.x; tok < S; tok += blockDim.x) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < XH; ++hh) sacc += p[((long long)f * XH + hh) * S + tok];
+      pbar[(long long)f * S + tok] = sacc * (1.f / XH);
+    }
+  }
+}
+
+}  // namespace tdb
+
+using namespace tdb;
+
+extern "C" int64_t tdb_xattn_workspace_bytes(int F, int S) {
+  int64_t tiles = ((int64_t)F * S + XBM - 1) / XBM;
+  return tiles * XMAXF * (XH * 2 + XD) * (int64_t)sizeof(float);
+}
+
+extern "C" int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, const void* wkv, const float* bv,
+                                   const uint8_t* kpm, void* o, float* p, float* pbar, void* workspace, int64_t ws_bytes,
+                                   int F, int S, float scale, void* stream_) {
+  int rc = tdb_init_once();
+  if (rc) return rc;
+  TDB_REQUIRE(q && mempb && memb && wkv && o && p && workspace && F > 0, "tdb_xattn_fused_fwd: null argument");
+  TDB_REQUIRE(S >= 43 && S <= 4096, "tdb_xattn_fused_fwd: S=%d unsupported (a 128-row tile may touch at most %d frames)", S, XMAXF);
+  TDB_REQUIRE(ws_bytes >= tdb_xattn_workspace_bytes(F, S), "tdb_xattn_fused_fwd: workspace too small");
+  static bool attr = false;
+  if (!attr) {
+    TDB_CHECK_CUDA(cudaFuncSetAttribute(xattn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XSMEM_BYTES));
+    attr = true;
+  }
+  const int64_t R = (int64_t)F * S;
+  const int tiles = (int)((R + XBM - 1) / XBM);
+  CUtensorMap tmK, tmV, tmW;
+  if ((rc = tdb_make_tmap_bf16(&tmK, mempb, R, XD, XD, XBM))) return rc;
+  if ((rc = tdb_make_tmap_bf16(&tmV, memb, R, XD, XD, XBM))) return rc;
+  if ((rc = tdb_make_tmap_bf16(&tmW, wkv, 2 * XD, XD, XD, XD))) return rc;
+  XattnParams prm;
+  prm.q = (const bf16*)q;
+  prm.kpm = kpm;
+  prm.p = p;
+  float* ws = (float*)workspace;
+  prm.part_m = ws;
+  prm.part_l = ws + (int64_t)tiles * XMAXF * XH;
+  prm.part_o = ws + (int64_t)tiles * XMAXF * XH * 2;
+  prm.R = (int)R;
+  prm.S = S;
+  prm.F = F;
+  prm.scale = scale;
+  cudaStream_t st = (cudaStream_t)stream_;
+  xattn_fused_kernel<<<tiles, XTHREADS, XSMEM_BYTES, st>>>(tmK, tmV, tmW, prm);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  xattn_merge_kernel<<<F, 256, 0, st>>>(prm.part_m, prm.part_l, prm.part_o, bv, p, pbar, (bf16*)o, S, F);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(2);
+  return TDB_OK;
+}

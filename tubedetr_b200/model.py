@@ -248,6 +248,7 @@ class Transformer(nn.Module):
         self.resizer = _Resizer()
         self.d_model, self.nhead, self.stride, self.no_tsa = D_MODEL, NHEAD, stride, no_tsa
         self.video_max_len = video_max_len
+        self.fused_xattn = True
 
     def _reset_temporal_parameters(self):  # called by reference main.py:545 after loading MDETR weights
         if self.fast:
@@ -280,8 +281,12 @@ class Transformer(nn.Module):
             att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
         x32, xb, xqb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, qp)
         c = l.cross_attn_image
-        q, k, v = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256), (256, 512), (512, 768)), xqb, mempb, memb)
-        o, cw = ops.mha(q, k, v, kpm_mem, B * T, NHEAD, 1, S, 32 ** -0.5)
+        if self.fused_xattn and S >= 43:    # K/V projection fused into the attention kernel (K, V never reach HBM)
+            (q,) = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256),), xqb)
+            o, cw = ops.xattn_fused(q, mempb, memb, c.in_proj_weight, c.in_proj_bias, kpm_mem, B * T, S, 32 ** -0.5)
+        else:
+            q, k, v = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256), (256, 512), (512, 768)), xqb, mempb, memb)
+            o, cw = ops.mha(q, k, v, kpm_mem, B * T, NHEAD, 1, S, 32 ** -0.5)
         att = ops.linear(o, c.out_proj.weight, c.out_proj.bias, out_fp32=True)
         x32, xb = ops.add_layernorm(x32, att, l.norm3.weight, l.norm3.bias)
         hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True, masked_by_consumer=True)

@@ -170,6 +170,61 @@ def mha(q, k, v, kpm, B, H, Lq, Lk, scale, packed=False):
     return MHAFn.apply(q, k, v, kpm, B, H, Lq, Lk, scale, packed)
 
 
+class XAttnFusedFn(torch.autograd.Function):
+    """Time-aligned cross-attention with the K/V projections fused into the attention kernel (tcgen05 + TMEM):
+    q [F,256] bf16 (already projected), mempb/memb [F*S,256] bf16, W/b = packed in_proj (rows 256:768 used here).
+    Returns (o bf16 [F,256], pbar fp32 [F,1,S]).  Backward re-projects K/V with tdb_gemm (they were never stored)."""
+
+    @staticmethod
+    def forward(ctx, q, mempb, memb, W, b, kpm, F, S, scale):
+        Wb = bf16_weight(W)
+        o = torch.empty(F, 256, dtype=torch.bfloat16, device=q.device)
+        p = torch.empty(F, 8, 1, S, dtype=torch.float32, device=q.device)
+        pbar = torch.empty(F, 1, S, dtype=torch.float32, device=q.device)
+        K.xattn_fused_fwd(q, mempb, memb, Wb[256:768], b[512:768], kpm, o, p, pbar, F, S, scale)
+        ctx.cfg = (F, S, scale)
+        ctx.save_for_backward(q, mempb, memb, W, b, p)
+        return o, pbar
+
+    @staticmethod
+    def backward(ctx, do, dpbar):
+        q, mempb, memb, W, b, p = ctx.saved_tensors
+        F, S, scale = ctx.cfg
+        Wb = bf16_weight(W)
+        R = F * S
+        kp = torch.empty(R, 256, dtype=torch.bfloat16, device=q.device)
+        vp = torch.empty(R, 256, dtype=torch.bfloat16, device=q.device)
+        gemm(mempb, Wb[256:512], kp, R, 256, 256, bias=b[256:512])
+        gemm(memb, Wb[512:768], vp, R, 256, 256, bias=b[512:768])
+        if do is None:
+            do = torch.zeros(F, 256, dtype=torch.bfloat16, device=q.device)
+        do = _as_bf16(do).contiguous()
+        dpbar = dpbar.contiguous().float() if dpbar is not None else None
+        ds = torch.empty_like(p)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(kp), torch.empty_like(vp)
+        K.mha_bwd(q, kp, vp, do, p, dpbar, ds, dq, dk, dv, F, 8, 1, S, scale)
+        dW = torch.zeros_like(W) if ctx.needs_input_grad[3] else None
+        db = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device) if ctx.needs_input_grad[4] else None
+        if dW is not None:
+            wgrad_into(dk, mempb, dW[256:512])
+            wgrad_into(dv, memb, dW[512:768])
+        if db is not None:
+            K.colsum_bf16(dk, db[256:512])
+            K.colsum_bf16(dv, db[512:768])
+        dmp = dmb = None
+        if ctx.needs_input_grad[1]:
+            dmp = torch.empty_like(mempb)
+            gemm(dk, Wb[256:512], dmp, R, 256, 256, b_major=1)
+        if ctx.needs_input_grad[2]:
+            dmb = torch.empty_like(memb)
+            gemm(dv, Wb[512:768], dmb, R, 256, 256, b_major=1)
+        return dq, dmp, dmb, dW, db, None, None, None, None
+
+
+def xattn_fused(q, mempb, memb, W, b, kpm, F, S, scale):
+    return XAttnFusedFn.apply(q, mempb, memb, W, b, kpm, F, S, scale)
+
+
 class AddLayerNormFn(torch.autograd.Function):
     """y = LayerNorm(x + r) over d=256 (fp32 statistics).  Returns (y fp32, y bf16, (y + pos) bf16 or None)."""
 
