@@ -131,6 +131,7 @@ def build_everything(device, seed=0):
     model, crit, wd = build_model(a)
     sd = {k: seeded_tensor(seed, k, v.shape, v.dtype) for k, v in model.state_dict().items()}
     model.load_state_dict(sd, strict=True)
+    model.text_autocast = True                     # whole path in bf16 tensor-core math, incl. the RoBERTa library call
     return model.to(device).eval(), crit, wd      # eval(): dropout is not implemented in the kernels yet
 
 

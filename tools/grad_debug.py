@@ -91,7 +91,7 @@ def main(name="cfg1b"):
     sd = {k: v.clone() for k, v in state_dict().items()}
     if "--no_fast" in cfg["flags"]:
         sd = {k: v for k, v in sd.items() if "fast_" not in k}
-    for k in ("input_proj.weight",):
+    for k in ("input_proj.weight", "backbone.0.body.layer2.0.conv1.weight"):
         sd[k].requires_grad_(True)
     oout, cache, ob = run_oracle(cfg, sd=sd)
     ol = O.criterion(oout, ob["target_boxes"], ob["inter_idx"], ob["time_mask"], ob["keep"])

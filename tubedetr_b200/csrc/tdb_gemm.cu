@@ -35,6 +35,7 @@ struct GemmKParams {
   int nz, splits, kb_per_split;
   int z_b_off1[TDB_MAX_TAPS], z_out_col[TDB_MAX_TAPS];
   int m_tiles, n_tiles, total_work;
+  int m_tile0;  // first M tile of this launch (tail launches start past the full waves)
   const float* scale;
   const float* bias;
   const bf16* residual;
@@ -71,7 +72,7 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKParams& p, int w, int
   r /= p.m_tiles;
   it.split = r % p.splits;
   it.z = r / p.splits;
-  it.m0 = mt * BM;
+  it.m0 = (p.m_tile0 + mt) * BM;
   it.n0 = nt * BN;
   if (p.splits == 1) {
     it.kb_begin = 0;
@@ -710,31 +711,64 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : bn);
   if (rc) return rc;
 
-  int grid = p.total_work < g_num_sms ? p.total_work : g_num_sms;
-  if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-#define TDB_LAUNCH(BN_, EPI_) tdb_gemm_kernel<BN_, EPI_><<<grid, kGemmThreads, GemmCfg<BN_>::kSmemBytes, stream>>>(tmA, tmB, p)
-  if (p.epi_mode == 0) {
-    switch (bn) {
-      case 64: TDB_LAUNCH(64, 0); break;
-      case 128: TDB_LAUNCH(128, 0); break;
-      default: TDB_LAUNCH(256, 0); break;
+  // Wave quantisation: a persistent grid of g CTAs finishes in ceil(tiles/g) tile-times.  When the last wave would be less
+  // than half full, the launch is split: full waves with the chosen tile width, and the remaining M tiles with narrower
+  // (faster) tiles spread over more CTAs.  (e.g. layer3 3x3 conv on 100 frames: 450 tiles on 148 SMs = 3.04 -> 3 + 0.25 waves.)
+  auto launch = [&](int bn_, const CUtensorMap& tmB_, const GemmKParams& q) -> int {
+    int grid = q.total_work < g_num_sms ? q.total_work : g_num_sms;
+    if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
+#define TDB_LAUNCH(BN_, EPI_) tdb_gemm_kernel<BN_, EPI_><<<grid, kGemmThreads, GemmCfg<BN_>::kSmemBytes, stream>>>(tmA, tmB_, q)
+    if (q.epi_mode == 0) {
+      switch (bn_) {
+        case 64: TDB_LAUNCH(64, 0); break;
+        case 128: TDB_LAUNCH(128, 0); break;
+        default: TDB_LAUNCH(256, 0); break;
+      }
+    } else if (q.epi_mode == 1) {
+      switch (bn_) {
+        case 64: TDB_LAUNCH(64, 1); break;
+        case 128: TDB_LAUNCH(128, 1); break;
+        default: TDB_LAUNCH(256, 1); break;
+      }
+    } else {
+      switch (bn_) {
+        case 64: TDB_LAUNCH(64, 2); break;
+        case 128: TDB_LAUNCH(128, 2); break;
+        default: TDB_LAUNCH(256, 2); break;
+      }
     }
-  } else if (p.epi_mode == 1) {
-    switch (bn) {
-      case 64: TDB_LAUNCH(64, 1); break;
-      case 128: TDB_LAUNCH(128, 1); break;
-      default: TDB_LAUNCH(256, 1); break;
-    }
-  } else {
-    switch (bn) {
-      case 64: TDB_LAUNCH(64, 2); break;
-      case 128: TDB_LAUNCH(128, 2); break;
-      default: TDB_LAUNCH(256, 2); break;
+#undef TDB_LAUNCH
+    tdb_count_launch(1);
+    return grid;
+  };
+  int grid = 0, tail_m = 0, tail_bn = 0;
+  const int g = (d->max_ctas > 0 && d->max_ctas < g_num_sms) ? d->max_ctas : g_num_sms;
+  static int tail_split = -1;
+  if (tail_split < 0) { const char* e = getenv("TDB_TAIL_SPLIT"); tail_split = e ? atoi(e) : 1; }
+  if (tail_split && splits == 1 && nz == 1 && bn > 64 && p.total_work > g && d->block_n == 0) {
+    const int full = (p.total_work / g) * g;
+    const int rem = p.total_work - full;
+    const int m_main = full / p.n_tiles;                 // whole M tiles covered by the full waves
+    if (rem > 0 && rem * 2 <= g && m_main > 0 && m_main < p.m_tiles) {
+      tail_m = p.m_tiles - m_main;
+      tail_bn = bn / 4 < 64 ? 64 : bn / 4;
+      GemmKParams pm = p;
+      pm.m_tiles = m_main;
+      pm.total_work = m_main * p.n_tiles;
+      grid = launch(bn, tmB, pm);
+      GemmKParams pt = p;
+      pt.m_tile0 = m_main;
+      pt.m_tiles = tail_m;
+      pt.n_tiles = d->N / tail_bn;
+      pt.total_work = pt.m_tiles * pt.n_tiles;
+      CUtensorMap tmBt;
+      rc = tdb_make_tmap_bf16(&tmBt, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : tail_bn);
+      if (rc) return rc;
+      launch(tail_bn, tmBt, pt);
     }
   }
-#undef TDB_LAUNCH
+  if (grid == 0) grid = launch(bn, tmB, p);
   TDB_CHECK_CUDA(cudaGetLastError());
-  tdb_count_launch(1);
   static FILE* logf = nullptr;
   static bool log_checked = false;
   if (!log_checked) {  // TDB_GEMM_LOG=<path>: one line per launch (profiling aid, joins with the ncu launch list)
@@ -743,8 +777,11 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
     if (lp) logf = fopen(lp, "w");
   }
   if (logf) {
-    fprintf(logf, "M=%d N=%d K=%d taps=%d nz=%d splits=%d bn=%d amaj=%d bmaj=%d grid=%d epi=%d%d%d%d remap=%d f32=%d\n", d->M, d->N,
+    fprintf(logf, "M=%d N=%d K=%d taps=%d nz=%d splits=%d bn=%d amaj=%d bmaj=%d grid=%d epi=%d%d%d%d remap=%d f32=%d tail=%dx%d\n", d->M, d->N,
             d->K, d->ntaps, nz, splits, bn, p.a_major, p.b_major, grid, d->scale != nullptr, d->residual != nullptr, d->relu,
+            d->mask != nullptr, d->remap, p.out_f32, tail_m, tail_bn);
+    if (tail_m) fprintf(logf, "M=%d N=%d K=%d taps=%d nz=%d splits=%d bn=%d amaj=%d bmaj=%d grid=%d epi=%d%d%d%d remap=%d f32=%d tail=-1x0\n", tail_m * 128, d->N,
+            d->K, d->ntaps, nz, splits, tail_bn, p.a_major, p.b_major, grid, d->scale != nullptr, d->residual != nullptr, d->relu,
             d->mask != nullptr, d->remap, p.out_f32);
     fflush(logf);
   }

@@ -313,7 +313,7 @@ class TubeDETR(nn.Module):
             self.sted_embed = _MLP(D_MODEL, D_MODEL, 2, 2)
             self.sted_embed.dropout = 0.5  # reference applies Dropout(0.5) here in train mode (not applied yet)
         self._engine = ResNet101Engine()
-        self.text_autocast = True   # RoBERTa (library call) runs its GEMMs in bf16 like the rest of the path
+        self.text_autocast = False  # True: RoBERTa (library call) runs its GEMMs under bf16 autocast (bench.py sets it)
 
     # ------------------------------------------------------------------ helpers
     def _backbone_tensors(self):
