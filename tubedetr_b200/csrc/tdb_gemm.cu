@@ -251,7 +251,16 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint4 rbuf[PFR][4], mbuf[PFM][4];
       const bf16* res_row = p.residual ? p.residual + out_row * p.ldr + wi.n0 : nullptr;
       const bf16* msk_row = p.mask ? p.mask + (long long)row_t * p.ldmask + wi.n0 : nullptr;
-      if constexpr (EPI == 2) {
+      float* ssc = stage;            // mode 3: per-warp private copy of this tile's scale / bias columns (L1 has no capacity
+      float* sbi = stage + BN;       // next to ~226 KB of shared memory, so per-chunk __ldg would each pay an L2 round trip)
+      if constexpr (EPI == 3) {
+        for (int i = lane; i < BN; i += 32) {
+          ssc[i] = p.scale ? __ldg(p.scale + wi.n0 + i) : 1.f;
+          sbi[i] = p.bias ? __ldg(p.bias + wi.n0 + i) : 0.f;
+        }
+        __syncwarp();
+      }
+      if constexpr (EPI == 2 || EPI == 3) {
         if (valid && res_row) {
 #pragma unroll
           for (int ci = 0; ci < PFR; ++ci)
@@ -268,7 +277,72 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(wq * 32) << 16);
-      if constexpr (EPI == 2) {
+      if constexpr (EPI == 3) {
+        // software pipeline: the TMEM load of chunk ci+1 is in flight while chunk ci is processed
+        uint32_t r[2][32];
+        tmem_ld_32x32(taddr, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = ci * 32;
+          tmem_ld_wait();
+          if (ci + 1 < NCH) tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 s4 = *reinterpret_cast<const float4*>(ssc + c + 4 * i);
+              const float4 b4 = *reinterpret_cast<const float4*>(sbi + c + 4 * i);
+              v[4 * i] = fmaf(__uint_as_float(r[ci & 1][4 * i]), s4.x, b4.x);
+              v[4 * i + 1] = fmaf(__uint_as_float(r[ci & 1][4 * i + 1]), s4.y, b4.y);
+              v[4 * i + 2] = fmaf(__uint_as_float(r[ci & 1][4 * i + 2]), s4.z, b4.z);
+              v[4 * i + 3] = fmaf(__uint_as_float(r[ci & 1][4 * i + 3]), s4.w, b4.w);
+            }
+            if (res_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u = rbuf[ci % PFR][i];
+                float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
+                v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+              }
+              if (ci + PFR < NCH) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rbuf[ci % PFR][i] = __ldg(reinterpret_cast<const uint4*>(res_row + (ci + PFR) * 32) + i);
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (msk_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u = mbuf[ci % PFM][i];
+                float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                v[8 * i] = f0.x > 0.f ? v[8 * i] : 0.f;         v[8 * i + 1] = f0.y > 0.f ? v[8 * i + 1] : 0.f;
+                v[8 * i + 2] = f1.x > 0.f ? v[8 * i + 2] : 0.f; v[8 * i + 3] = f1.y > 0.f ? v[8 * i + 3] : 0.f;
+                v[8 * i + 4] = f2.x > 0.f ? v[8 * i + 4] : 0.f; v[8 * i + 5] = f2.y > 0.f ? v[8 * i + 5] : 0.f;
+                v[8 * i + 6] = f3.x > 0.f ? v[8 * i + 6] : 0.f; v[8 * i + 7] = f3.y > 0.f ? v[8 * i + 7] : 0.f;
+              }
+              if (ci + PFM < NCH) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mbuf[ci % PFM][i] = __ldg(reinterpret_cast<const uint4*>(msk_row + (ci + PFM) * 32) + i);
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            }
+          }
+        }
+      } else if constexpr (EPI == 2) {
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           const int c = ci * 32;
@@ -604,12 +678,15 @@ int tdb_init_once() {
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<64>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   g_encode = (EncodeTiledFn)fn;
   return TDB_OK;
 }
@@ -700,8 +777,8 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   {
     static int env_mode = -2;
     if (env_mode == -2) { const char* e = getenv("TDB_EPI_MODE"); env_mode = e ? atoi(e) : -1; }
-    int m = (d->debug_flags >> 1) & 3;            // 0 = auto, 1 = direct, 2 = smem-staged, 3 = direct + register prefetch
-    p.epi_mode = m ? m - 1 : (env_mode >= 0 ? env_mode : 2);
+    int m = (d->debug_flags >> 1) & 7;            // 0 = auto, else epilogue mode + 1 (1 direct, 2 smem-staged, 3 +prefetch, 4 pipelined)
+    p.epi_mode = m ? m - 1 : (env_mode >= 0 ? env_mode : 3);
   }
   TDB_REQUIRE(p.ldo % 8 == 0 && (!p.residual || p.ldr % 8 == 0) && (!p.mask || p.ldmask % 8 == 0), "tdb_gemm: leading dims must be multiples of 8");
 
@@ -730,11 +807,17 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
         case 128: TDB_LAUNCH(128, 1); break;
         default: TDB_LAUNCH(256, 1); break;
       }
-    } else {
+    } else if (q.epi_mode == 2) {
       switch (bn_) {
         case 64: TDB_LAUNCH(64, 2); break;
         case 128: TDB_LAUNCH(128, 2); break;
         default: TDB_LAUNCH(256, 2); break;
+      }
+    } else {
+      switch (bn_) {
+        case 64: TDB_LAUNCH(64, 3); break;
+        case 128: TDB_LAUNCH(128, 3); break;
+        default: TDB_LAUNCH(256, 3); break;
       }
     }
 #undef TDB_LAUNCH
@@ -744,7 +827,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   int grid = 0, tail_m = 0, tail_bn = 0;
   const int g = (d->max_ctas > 0 && d->max_ctas < g_num_sms) ? d->max_ctas : g_num_sms;
   static int tail_split = -1;
-  if (tail_split < 0) { const char* e = getenv("TDB_TAIL_SPLIT"); tail_split = e ? atoi(e) : 1; }
+  if (tail_split < 0) { const char* e = getenv("TDB_TAIL_SPLIT"); tail_split = e ? atoi(e) : 0; }  // measured: no gain (r01), off
   if (tail_split && splits == 1 && nz == 1 && bn > 64 && p.total_work > g && d->block_n == 0) {
     const int full = (p.total_work / g) * g;
     const int rem = p.total_work - full;
