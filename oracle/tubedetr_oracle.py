@@ -32,22 +32,37 @@ def frozen_bn(x, sd, p):
     return x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
 
 
-def resnet101_layer4(x, sd, p="backbone.0.body."):
-    """torchvision ResNet-101 v1.5 truncated at layer4 (reference models/backbone.py:93-122)."""
-    x = F.conv2d(x, sd[p + "conv1.weight"], stride=2, padding=3)
-    x = F.relu(frozen_bn(x, sd, p + "bn1"))
+def _q(t, on):
+    """straight-through bf16 rounding (forward value rounded, gradient passes unchanged)"""
+    return t + (t.to(torch.bfloat16).float() - t).detach() if on else t
+
+
+def resnet101_layer4(x, sd, p="backbone.0.body.", emulate_bf16=False):
+    """torchvision ResNet-101 v1.5 truncated at layer4 (reference models/backbone.py:93-122).
+
+    emulate_bf16=True rounds weights and every stored activation to bf16 exactly where the CUDA path does (bf16
+    operands, fp32 accumulate + FrozenBN/residual/ReLU epilogue, bf16 store).  Used only to validate the backward pass:
+    ReLU masks then agree with the CUDA forward, which a comparison against the pure-fp32 network cannot guarantee.
+    """
+    e = emulate_bf16
+
+    def conv(t, w, **kw):
+        return F.conv2d(t, _q(w, e), **kw)
+
+    x = conv(_q(x, e), sd[p + "conv1.weight"], stride=2, padding=3)
+    x = _q(F.relu(frozen_bn(x, sd, p + "bn1")), e)
     x = F.max_pool2d(x, 3, stride=2, padding=1)
     for li, nblocks in enumerate(RESNET101_BLOCKS, start=1):
         for bi in range(nblocks):
             q = f"{p}layer{li}.{bi}."
             stride = 2 if (bi == 0 and li > 1) else 1
             idt = x
-            y = F.relu(frozen_bn(F.conv2d(x, sd[q + "conv1.weight"]), sd, q + "bn1"))
-            y = F.relu(frozen_bn(F.conv2d(y, sd[q + "conv2.weight"], stride=stride, padding=1), sd, q + "bn2"))
-            y = frozen_bn(F.conv2d(y, sd[q + "conv3.weight"]), sd, q + "bn3")
+            y = _q(F.relu(frozen_bn(conv(x, sd[q + "conv1.weight"]), sd, q + "bn1")), e)
+            y = _q(F.relu(frozen_bn(conv(y, sd[q + "conv2.weight"], stride=stride, padding=1), sd, q + "bn2")), e)
+            y = frozen_bn(conv(y, sd[q + "conv3.weight"]), sd, q + "bn3")
             if bi == 0:
-                idt = frozen_bn(F.conv2d(x, sd[q + "downsample.0.weight"], stride=stride), sd, q + "downsample.1")
-            x = F.relu(y + idt)
+                idt = _q(frozen_bn(conv(x, sd[q + "downsample.0.weight"], stride=stride), sd, q + "downsample.1"), e)
+            x = _q(F.relu(y + idt), e)
     return x
 
 

@@ -1,4 +1,10 @@
-"""Isolated ResNet-101 backward (dgrad/wgrad chain on the tcgen05 GEMM) vs autograd through the CPU oracle."""
+"""Isolated ResNet-101 backward (dgrad/wgrad chain on the tcgen05 GEMM) vs autograd through the CPU oracle.
+
+The oracle runs with emulate_bf16=True (weights / stored activations rounded to bf16 where the CUDA path rounds them):
+the backward pass is only comparable when the ~100 ReLU masks of the two forwards agree.  Against the pure-fp32 network
+the bf16 forward flips the sign of a fraction of a percent of near-zero pre-activations per layer, which removes that
+share of the reference gradient at every ReLU (measured on B200: projection coefficient 0.94-0.96 with cosine 0.98-0.99
+at layer2, i.e. an apparent 5 % shrink that is a property of bf16 forward numerics, not of the backward kernels)."""
 import pytest
 import torch
 
@@ -22,7 +28,7 @@ def test_backbone_weight_gradients_match_oracle(N, H, W):
     osd = {k: v.clone() for k, v in sd.items() if k.startswith(pre)}
     for k in names:
         osd[k].requires_grad_(True)
-    feat = O.resnet101_layer4(frames, osd)                       # (N,2048,h,w)
+    feat = O.resnet101_layer4(frames, osd, emulate_bf16=True)    # (N,2048,h,w)
     gout = torch.randn(feat.shape, generator=g)
     ref = torch.autograd.grad((feat * gout).sum(), [osd[k] for k in names])
     # ours
@@ -34,7 +40,7 @@ def test_backbone_weight_gradients_match_oracle(N, H, W):
     h, w = eng.last_hw
     ref_rows = feat.detach().permute(0, 2, 3, 1).reshape(N * h * w, 2048)
     err = (f.float().cpu() - ref_rows).abs().max().item()
-    assert err <= 3e-2 * ref_rows.abs().max().item(), err
+    assert err <= 1e-2 * ref_rows.abs().max().item(), err
     gr = gout.permute(0, 2, 3, 1).reshape(N * h * w, 2048).cuda()
     (f.float() * gr).sum().backward()
     worst = []
@@ -45,5 +51,5 @@ def test_backbone_weight_gradients_match_oracle(N, H, W):
         worst.append((abs(a - 1), cos, k, a))
     worst.sort(reverse=True)
     print("worst projection coefficients:", [(k, round(a, 4), round(c, 4)) for _, c, k, a in worst[:6]])
-    assert worst[0][0] < 0.03, worst[:5]
-    assert min(c for _, c, _, _ in worst) > 0.98
+    assert worst[0][0] < 0.02, worst[:5]
+    assert min(c for _, c, _, _ in worst) > 0.99

@@ -313,14 +313,23 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
     partial[((long long)blockIdx.x * 2 + 1) * D + c] = b;
   }
 }
-// out[c] (+)= sum_b partial[b][c] in fixed order; used for dgamma/dbeta (stride 2*D) and generic column sums
+// out[c] (+)= sum_b partial[b][c] in fixed order; used for dgamma/dbeta (stride 2*D) and generic column sums.
+// block = 32 columns x 8 part-groups: part-group y sums parts y, y+8, ... then the 8 groups are combined through shared memory.
 __global__ void colsum_partials_kernel(const float* __restrict__ partial, int nparts, long long part_stride, int D,
                                        float* __restrict__ out, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int b = 0; b < nparts; ++b) s += partial[b * part_stride + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < D)
+    for (int b = threadIdx.y; b < nparts; b += 8) s += partial[b * part_stride + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // column sums of a bf16 [rows][N] matrix (bias gradients): stage 1 -> partial [nb][N] fp32.  Thread = 2 adjacent columns.
@@ -426,8 +435,8 @@ extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void
   int blocks = tdb_layernorm_bwd_blocks(rows);
   layernorm_bwd_kernel<256><<<blocks, 256, 0, STREAM>>>(dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, partial, rows);
   TDB_CHECK_CUDA(cudaGetLastError());
-  if (dgamma) colsum_partials_kernel<<<4, 64, 0, STREAM>>>(partial, blocks, 2 * D, D, dgamma, accumulate);
-  if (dbeta) colsum_partials_kernel<<<4, 64, 0, STREAM>>>(partial + D, blocks, 2 * D, D, dbeta, accumulate);
+  if (dgamma) colsum_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, STREAM>>>(partial, blocks, 2 * D, D, dgamma, accumulate);
+  if (dbeta) colsum_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, STREAM>>>(partial + D, blocks, 2 * D, D, dbeta, accumulate);
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(3);
   return TDB_OK;
@@ -439,7 +448,7 @@ extern "C" int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float
   int rpb = (rows + nparts - 1) / nparts;
   dim3 grid((N / 2 + 127) / 128, nparts);
   colsum_bf16_kernel<<<grid, 128, 0, STREAM>>>((const bf16*)x, ld, rows, N, partial, rpb);
-  colsum_partials_kernel<<<(N + 63) / 64, 64, 0, STREAM>>>(partial, nparts, N, N, out, accumulate);
+  colsum_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, STREAM>>>(partial, nparts, N, N, out, accumulate);
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(2);
   return TDB_OK;

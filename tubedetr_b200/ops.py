@@ -31,7 +31,7 @@ def wgrad_into(dy_b, x_b, out):
     R, N = dy_b.shape
     Kd = x_b.shape[1]
     tiles = ((N + 127) // 128) * max(1, Kd // 256 if Kd % 256 == 0 else Kd // 64)
-    want = max(1, min((2 * 148 + tiles - 1) // tiles, 64))
+    want = max(1, min((148 + tiles - 1) // tiles, 32))
     s = effective_splits(R, want)
     part = torch.empty(s, N, Kd, dtype=torch.float32, device=dy_b.device)
     gemm(dy_b, x_b, part, N, Kd, R, a_major=1, b_major=1, splits=want)

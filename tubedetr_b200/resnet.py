@@ -163,7 +163,7 @@ class ResNet101Engine:
         nz = 9 if z_b_off1 is not None else 0
         ntot = Ncols * (9 if nz else 1)
         work = ((M + 127) // 128) * max(1, Ncols // 256 if Ncols % 256 == 0 else Ncols // 64) * max(nz, 1)
-        want = max(1, (2 * 148 + work - 1) // work)
+        want = max(1, min((148 + work - 1) // work, 32))
         s = effective_splits(Kred, want)
         part = torch.empty(s, M, ntot, dtype=torch.float32, device=g.device)
         gemm(g, xin, part, M, Ncols, Kred, a_major=1, b_major=1, nz=nz, z_b_off1=z_b_off1,
