@@ -112,8 +112,8 @@ int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const 
 int tdb_layernorm_bwd_blocks(int rows); /* partial workspace = blocks * 2 * D floats */
 /* incoming gradient = dy (fp32, may be NULL) + dy2_bf + dy3_bf (bf16, may be NULL): grads of y, bf16(y), bf16(y+pos) */
 int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void* dy3_bf, const float* x, const float* r,
-                      const float* gamma, const float* mean, const float* rstd, float* dz, float* dgamma, float* dbeta,
-                      float* partial, int rows, int D, int accumulate, void* stream);
+                      const float* gamma, const float* mean, const float* rstd, float* dz, void* dz_bf /* optional bf16 copy */,
+                      float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate, void* stream);
 /* column sums of a bf16 [rows][N] matrix (bias gradients), two-stage fixed order; partial = nparts * N floats */
 int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* partial, int nparts, float* out, int accumulate,
                     void* stream);

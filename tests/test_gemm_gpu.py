@@ -133,3 +133,18 @@ def test_gemm_conv3x3_dgrad_and_wgrad_padded_grid():
     gemm(x.view(-1, Cin), w1, outp, Nimg * H * W, 64, Cin, remap=REMAP_C2P, img_hw=(H, W))
     ref = _pad_rows((x.view(-1, Cin).float() @ w1.float().t()).view(Nimg, H, W, 64))
     _close(outp, ref)
+
+
+@pytest.mark.parametrize("mode", [0, 2, 3, 4])
+@pytest.mark.parametrize("M,N,K", [(1500, 256, 320), (12100, 1024, 256), (130, 128, 64)])
+def test_gemm_epilogue_variants(mode, M, N, K):
+    """every epilogue implementation (direct, register-prefetch, pipelined, TMA-fed residual) gives the same result"""
+    from tubedetr_b200.gemm import gemm
+    A, B, R, Mk = _rand((M, K), 21), _rand((N, K), 22), _rand((M, N), 23), _rand((M, N), 24)
+    scale = torch.rand(N, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    ref = torch.relu((A.float() @ B.float().t()) * scale + bias + R.float()) * (Mk.float() > 0)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    gemm(A, B, out, M, N, K, scale=scale, bias=bias, residual=R, relu=True, mask=Mk, debug_flags=(mode + 1) << 1)
+    torch.cuda.synchronize()
+    _close(out, ref)

@@ -264,7 +264,7 @@ template <int D>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ dy3,
                                      const float* __restrict__ x, const float* __restrict__ r,
                                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     float* __restrict__ dz, float* __restrict__ partial, int rows) {
+                                     float* __restrict__ dz, bf16* __restrict__ dz_bf, float* __restrict__ partial, int rows) {
   constexpr int PER = D / 32;
   __shared__ float sg[8][D];
   __shared__ float sb[8][D];
@@ -294,7 +294,11 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
     s1 = warp_sum(s1) * (1.f / D);
     s2 = warp_sum(s2) * (1.f / D);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) dz[(long long)row * D + i * 32 + lane] = rs * (g[i] - s1 - xh[i] * s2);
+    for (int i = 0; i < PER; ++i) {
+      float o = rs * (g[i] - s1 - xh[i] * s2);
+      dz[(long long)row * D + i * 32 + lane] = o;
+      if (dz_bf) dz_bf[(long long)row * D + i * 32 + lane] = __float2bfloat16(o);
+    }
   }
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
@@ -429,11 +433,11 @@ extern "C" int tdb_layernorm_bwd_blocks(int rows) {
   return b > 296 ? 296 : b;
 }
 extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void* dy3_bf, const float* x, const float* r,
-                                 const float* gamma, const float* mean, const float* rstd, float* dz, float* dgamma,
-                                 float* dbeta, float* partial, int rows, int D, int accumulate, void* stream_) {
+                                 const float* gamma, const float* mean, const float* rstd, float* dz, void* dz_bf,
+                                 float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate, void* stream_) {
   TDB_REQUIRE((dy || dy2_bf || dy3_bf) && x && gamma && mean && rstd && dz && partial && rows > 0 && D == 256, "tdb_layernorm_bwd: bad args");
   int blocks = tdb_layernorm_bwd_blocks(rows);
-  layernorm_bwd_kernel<256><<<blocks, 256, 0, STREAM>>>(dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, partial, rows);
+  layernorm_bwd_kernel<256><<<blocks, 256, 0, STREAM>>>(dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows);
   TDB_CHECK_CUDA(cudaGetLastError());
   if (dgamma) colsum_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, STREAM>>>(partial, blocks, 2 * D, D, dgamma, accumulate);
   if (dbeta) colsum_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, STREAM>>>(partial + D, blocks, 2 * D, D, dbeta, accumulate);

@@ -51,13 +51,15 @@ struct GemmKParams {
   int epi_mode;
 };
 
-template <int BN>
+template <int BN, int EPI = 0>
 struct GemmCfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  // mode 4 (TMA-fed residual, BN = 128 only) trades two pipeline stages for a double-buffered 128 x 128 residual tile
+  static constexpr int kStages = (EPI == 4) ? 4 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kOperandBytes = (EPI == 4) ? 2 * BM * BN * 2 : 0;
   static constexpr int kStagingBytes = 4 * 32 * 64 * 4;  // per epilogue warp: 32 rows x 64 fp32 columns
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOperandBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
 
 struct WorkItem {
@@ -89,15 +91,19 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKParams& p, int w, int
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* opnd = smem + Cfg::kStages * Cfg::kStageBytes;     // [2][BN/64][128 rows][128 B] residual tiles (mode 4), 1024-aligned
+  uint8_t* after = opnd + Cfg::kOperandBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* ofull_bar = tempty_bar + 2;             // [2] residual tile landed (mode 4)
+  uint64_t* oempty_bar = ofull_bar + 2;             // [2] residual tile consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,6 +120,8 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
+      mbar_init(&ofull_bar[s], 1);
+      mbar_init(&oempty_bar[s], 4);
     }
     fence_barrier_init();
   }
@@ -131,8 +139,23 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int oslot = 0;
+      uint32_t ophase = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         const WorkItem wi = decode_work(p, w, BN);
+        if constexpr (EPI == 4) {
+          // whole residual tile of this work item (128 rows x BN columns) by TMA, one tile ahead of the epilogue: its HBM
+          // latency overlaps the previous tile's epilogue and this tile's main loop, with 2 x 32 KB in flight per SM
+          mbar_wait(&oempty_bar[oslot], ophase ^ 1, 5);
+          mbar_expect_tx(&ofull_bar[oslot], BM * BN * 2);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(opnd + (oslot * (BN / 64) + j) * (BM * 128), &tmR, &ofull_bar[oslot], wi.n0 + j * 64, wi.m0);
+          if (++oslot == 2) {
+            oslot = 0;
+            ophase ^= 1;
+          }
+        }
         for (int it = 0; it < wi.iters; ++it) {
           int tap, kk;
           if (p.splits == 1) {
@@ -215,7 +238,9 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int wq = warp & 3;
-    float* stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + wq * (32 * 64);
+    float* stage = reinterpret_cast<float*>(after + 256) + wq * (32 * 64);
+    int oslot = 0;
+    uint32_t ophase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int Hp = p.img_h + 2, Wp = p.img_w + 2;
@@ -253,15 +278,15 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bf16* msk_row = p.mask ? p.mask + (long long)row_t * p.ldmask + wi.n0 : nullptr;
       float* ssc = stage;            // mode 3: per-warp private copy of this tile's scale / bias columns (L1 has no capacity
       float* sbi = stage + BN;       // next to ~226 KB of shared memory, so per-chunk __ldg would each pay an L2 round trip)
-      if constexpr (EPI == 3) {
+      if constexpr (EPI == 3 || EPI == 4) {
         for (int i = lane; i < BN; i += 32) {
           ssc[i] = p.scale ? __ldg(p.scale + wi.n0 + i) : 1.f;
           sbi[i] = p.bias ? __ldg(p.bias + wi.n0 + i) : 0.f;
         }
         __syncwarp();
       }
-      if constexpr (EPI == 2 || EPI == 3) {
-        if (valid && res_row) {
+      if constexpr (EPI == 2 || EPI == 3 || EPI == 4) {
+        if (EPI != 4 && valid && res_row) {
 #pragma unroll
           for (int ci = 0; ci < PFR; ++ci)
 #pragma unroll
@@ -277,7 +302,78 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(wq * 32) << 16);
-      if constexpr (EPI == 3) {
+      if constexpr (EPI == 4) {
+        // residual tile arrives through TMA (128-byte swizzled boxes of 64 columns); thread r reads its own row: the swizzle
+        // makes 8 consecutive rows hit 8 different 16-byte bank groups, so the row-per-thread reads are conflict free
+        mbar_wait(&ofull_bar[oslot], ophase, 6);
+        const int rloc = wq * 32 + lane;
+        const uint8_t* obase = opnd + oslot * (BN / 64) * (BM * 128) + rloc * 128;
+        uint32_t r[2][32];
+        tmem_ld_32x32(taddr, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = ci * 32;
+          tmem_ld_wait();
+          if (ci + 1 < NCH) tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 s4 = *reinterpret_cast<const float4*>(ssc + c + 4 * i);
+              const float4 b4 = *reinterpret_cast<const float4*>(sbi + c + 4 * i);
+              v[4 * i] = fmaf(__uint_as_float(r[ci & 1][4 * i]), s4.x, b4.x);
+              v[4 * i + 1] = fmaf(__uint_as_float(r[ci & 1][4 * i + 1]), s4.y, b4.y);
+              v[4 * i + 2] = fmaf(__uint_as_float(r[ci & 1][4 * i + 2]), s4.z, b4.z);
+              v[4 * i + 3] = fmaf(__uint_as_float(r[ci & 1][4 * i + 3]), s4.w, b4.w);
+            }
+            const uint8_t* box = obase + (ci >> 1) * (BM * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j16 = (ci & 1) * 4 + i;                   // 16-byte chunk within the 128-byte row
+              uint4 u = *reinterpret_cast<const uint4*>(box + ((j16 ^ (rloc & 7)) << 4));
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
+              v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (msk_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 u = mbuf[ci % PFM][i];
+                float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                v[8 * i] = f0.x > 0.f ? v[8 * i] : 0.f;         v[8 * i + 1] = f0.y > 0.f ? v[8 * i + 1] : 0.f;
+                v[8 * i + 2] = f1.x > 0.f ? v[8 * i + 2] : 0.f; v[8 * i + 3] = f1.y > 0.f ? v[8 * i + 3] : 0.f;
+                v[8 * i + 4] = f2.x > 0.f ? v[8 * i + 4] : 0.f; v[8 * i + 5] = f2.y > 0.f ? v[8 * i + 5] : 0.f;
+                v[8 * i + 6] = f3.x > 0.f ? v[8 * i + 6] : 0.f; v[8 * i + 7] = f3.y > 0.f ? v[8 * i + 7] : 0.f;
+              }
+              if (ci + PFM < NCH) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mbuf[ci % PFM][i] = __ldg(reinterpret_cast<const uint4*>(msk_row + (ci + PFM) * 32) + i);
+              }
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + out_col0 + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&oempty_bar[oslot]);
+        if (++oslot == 2) {
+          oslot = 0;
+          ophase ^= 1;
+        }
+      } else if constexpr (EPI == 3) {
         // software pipeline: the TMEM load of chunk ci+1 is in flight while chunk ci is processed
         uint32_t r[2][32];
         tmem_ld_32x32(taddr, r[0]);
@@ -683,6 +779,7 @@ int tdb_init_once() {
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128, 4>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
@@ -714,11 +811,13 @@ int tdb_make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t 
 
 static int pick_block_n(int N, long long work_per_bn1 /* m_tiles*nz*splits */, int forced) {
   if (forced == 64 || forced == 128 || forced == 256) return (N % forced == 0) ? forced : 0;
+  // Wide tiles amortise the A-operand feed (shared-memory bandwidth bounds the main loop): measured on B200 a 128x256 tile
+  // costs ~1.3x a 128x128 tile, not 2x.  So take the widest tile that still occupies at least half of the SMs.
   const int cands[3] = {256, 128, 64};
   for (int i = 0; i < 3; ++i) {
     int bn = cands[i];
     if (N % bn) continue;
-    if (work_per_bn1 * (N / bn) >= g_num_sms) return bn;
+    if (work_per_bn1 * (N / bn) * 2 >= g_num_sms) return bn;
   }
   for (int i = 2; i >= 0; --i)
     if (N % cands[i] == 0) return cands[i];
@@ -749,7 +848,18 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
     splits = (kb + kb_per_split - 1) / kb_per_split;
   }
   const int m_tiles = (d->M + BM - 1) / BM;
-  const int bn = pick_block_n(d->N, (long long)m_tiles * nz * splits, d->block_n);
+  int epi_mode;
+  {
+    static int env_mode = -2;
+    if (env_mode == -2) { const char* e = getenv("TDB_EPI_MODE"); env_mode = e ? atoi(e) : -1; }
+    int m = (d->debug_flags >> 1) & 7;   // 0 = auto, else mode + 1: 1 direct, 2 smem-staged, 3 +reg prefetch, 4 pipelined, 5 TMA residual
+    epi_mode = m ? m - 1 : (env_mode >= 0 ? env_mode : 4);
+    // mode 4 (residual tile by TMA) needs an un-remapped residual and 128-wide tiles; otherwise the pipelined register path
+    const bool tma_res_ok = d->residual && d->remap == TDB_REMAP_NONE && splits == 1 && d->N % 128 == 0 &&
+                            (d->block_n == 0 || d->block_n == 128);
+    if (epi_mode == 4 && !tma_res_ok) epi_mode = 3;
+  }
+  const int bn = epi_mode == 4 ? 128 : pick_block_n(d->N, (long long)m_tiles * nz * splits, d->block_n);
   TDB_REQUIRE(bn != 0, "tdb_gemm: no tile width for N=%d (block_n=%d)", d->N, d->block_n);
   if (d->remap != TDB_REMAP_NONE) TDB_REQUIRE(d->img_h > 0 && d->img_w > 0, "tdb_gemm: remap needs img_h/img_w");
 
@@ -774,12 +884,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   p.relu = d->relu; p.out = d->out; p.out_f32 = d->out_dtype == TDB_OUT_F32; p.ldo = d->ldo;
   p.remap = d->remap; p.img_h = d->img_h; p.img_w = d->img_w;
   p.debug_flags = d->debug_flags;
-  {
-    static int env_mode = -2;
-    if (env_mode == -2) { const char* e = getenv("TDB_EPI_MODE"); env_mode = e ? atoi(e) : -1; }
-    int m = (d->debug_flags >> 1) & 7;            // 0 = auto, else epilogue mode + 1 (1 direct, 2 smem-staged, 3 +prefetch, 4 pipelined)
-    p.epi_mode = m ? m - 1 : (env_mode >= 0 ? env_mode : 3);
-  }
+  p.epi_mode = epi_mode;
   TDB_REQUIRE(p.ldo % 8 == 0 && (!p.residual || p.ldr % 8 == 0) && (!p.mask || p.ldmask % 8 == 0), "tdb_gemm: leading dims must be multiples of 8");
 
   CUtensorMap tmA, tmB;
@@ -787,6 +892,11 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   if (rc) return rc;
   rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : bn);
   if (rc) return rc;
+  CUtensorMap tmR = tmA;   // only dereferenced in epilogue mode 4
+  if (p.epi_mode == 4) {
+    rc = tdb_make_tmap_bf16(&tmR, d->residual, d->M, d->N, d->ldr, BM);
+    if (rc) return rc;
+  }
 
   // Wave quantisation: a persistent grid of g CTAs finishes in ceil(tiles/g) tile-times.  When the last wave would be less
   // than half full, the launch is split: full waves with the chosen tile width, and the remaining M tiles with narrower
@@ -794,7 +904,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   auto launch = [&](int bn_, const CUtensorMap& tmB_, const GemmKParams& q) -> int {
     int grid = q.total_work < g_num_sms ? q.total_work : g_num_sms;
     if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-#define TDB_LAUNCH(BN_, EPI_) tdb_gemm_kernel<BN_, EPI_><<<grid, kGemmThreads, GemmCfg<BN_>::kSmemBytes, stream>>>(tmA, tmB_, q)
+#define TDB_LAUNCH(BN_, EPI_) tdb_gemm_kernel<BN_, EPI_><<<grid, kGemmThreads, GemmCfg<BN_, EPI_>::kSmemBytes, stream>>>(tmA, tmB_, tmR, q)
     if (q.epi_mode == 0) {
       switch (bn_) {
         case 64: TDB_LAUNCH(64, 0); break;
@@ -813,6 +923,8 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
         case 128: TDB_LAUNCH(128, 2); break;
         default: TDB_LAUNCH(256, 2); break;
       }
+    } else if (q.epi_mode == 4 && bn_ == 128) {
+      TDB_LAUNCH(128, 4);
     } else {
       switch (bn_) {
         case 64: TDB_LAUNCH(64, 3); break;

@@ -48,10 +48,10 @@ def layernorm_fwd(x, r, gamma, beta, pos, y, y_bf, ypos_bf, mean, rstd, rows, D,
                                   ptr(mean), ptr(rstd), rows, D, _f(eps), stream_ptr()), "layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dgamma, dbeta, rows, D, accumulate=False, dy2=None, dy3=None):
+def layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dgamma, dbeta, rows, D, accumulate=False, dy2=None, dy3=None, dz_bf=None):
     nb = int(lib().tdb_layernorm_bwd_blocks(rows))
     partial = torch.empty(nb * 2 * D, dtype=torch.float32, device=x.device)
-    check(lib().tdb_layernorm_bwd(ptr(dy), ptr(dy2), ptr(dy3), ptr(x), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), ptr(dz), ptr(dgamma),
+    check(lib().tdb_layernorm_bwd(ptr(dy), ptr(dy2), ptr(dy3), ptr(x), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), ptr(dz), ptr(dz_bf), ptr(dgamma),
                                   ptr(dbeta), ptr(partial), rows, D, int(accumulate), stream_ptr()), "layernorm_bwd")
 
 

@@ -23,7 +23,14 @@ def bf16_weight(w):
 
 
 def _as_bf16(t):
-    return t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)
+    """bf16 view of a gradient.  Kernels that produce an fp32 gradient (LayerNorm backward) also write its bf16 copy and
+    attach it as `_tdb_bf16`, so the consumer's GEMM operand needs no separate cast kernel."""
+    if t.dtype == torch.bfloat16:
+        return t
+    side = getattr(t, "_tdb_bf16", None)
+    if side is not None and side.shape == t.shape:
+        return side
+    return t.to(torch.bfloat16)
 
 
 def wgrad_into(dy_b, x_b, out):
@@ -258,9 +265,12 @@ class AddLayerNormFn(torch.autograd.Function):
         dyb = dyb.contiguous() if dyb is not None else None
         dypb = dypb.contiguous() if dypb is not None else None
         dz = torch.empty_like(x)
+        dzb = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device) if ctx.has_r else None
         dg = torch.empty(D, dtype=torch.float32, device=x.device)
         db = torch.empty(D, dtype=torch.float32, device=x.device)
-        K.layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dg, db, rows, D, dy2=dyb, dy3=dypb)   # sums the three grads in-kernel
+        K.layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dg, db, rows, D, dy2=dyb, dy3=dypb, dz_bf=dzb)   # sums the three grads in-kernel
+        if dzb is not None:
+            dz._tdb_bf16 = dzb
         dpos = None
         if ctx.needs_input_grad[4] and dypb is not None:   # (y + pos): pos is the time-query embedding in the decoder
             dpos = dypb.to(ctx.pos_dtype)
