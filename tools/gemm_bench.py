@@ -62,8 +62,27 @@ def case(name, M, N, K, scale=False, residual=False, relu=False, mask=False, bma
     P(f"{name:34s} M={M:7d} N={N:5d} K={K:5d} | " + " | ".join(res))
 
 
+def experiment():
+    """where does the epilogue time go?  mode 3 with stores / TMEM loads switched off (results are garbage on purpose)"""
+    M, N, K = 48400, 1024, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    R = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    sc, bi = torch.rand(N, device="cuda") + 0.5, torch.randn(N, device="cuda")
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    for name, kw, fl in (("full res+relu", dict(scale=sc, bias=bi, residual=R, relu=True), 0),
+                         ("no residual", dict(scale=sc, bias=bi, relu=True), 0),
+                         ("plain", dict(), 0), ("plain, no stores", dict(), 16), ("plain, no tmem ld", dict(), 32),
+                         ("plain, no stores no ld", dict(), 48)):
+        for bn in (128, 256):
+            us = bench(lambda: gemm(A, B, out, M, N, K, block_n=bn, debug_flags=(4 << 1) | fl, **kw))
+            P(f"experiment {name:24s} bn{bn}: {us:8.1f} us")
+
+
 def main():
     P(torch.cuda.get_device_name(0))
+    experiment()
     case("l3 conv3 fast (res+relu)", 48400, 1024, 256, scale=True, residual=True, relu=True)
     case("l3 conv3 slow (res+relu)", 12100, 1024, 256, scale=True, residual=True, relu=True)
     case("l3 dgrad1 slow (res+mask, Bmn)", 12100, 1024, 256, residual=True, mask=True, bmaj=1)

@@ -376,12 +376,13 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       } else if constexpr (EPI == 3) {
         // software pipeline: the TMEM load of chunk ci+1 is in flight while chunk ci is processed
         uint32_t r[2][32];
-        tmem_ld_32x32(taddr, r[0]);
+        const bool dbg_nold = (p.debug_flags & 32) != 0, dbg_nost = (p.debug_flags & 16) != 0;
+        if (!dbg_nold) tmem_ld_32x32(taddr, r[0]);
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           const int c = ci * 32;
           tmem_ld_wait();
-          if (ci + 1 < NCH) tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
+          if (ci + 1 < NCH && !dbg_nold) tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
           if (valid) {
             float v[32];
 #pragma unroll
@@ -425,7 +426,9 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int i = 0; i < 4; ++i) mbuf[ci % PFM][i] = __ldg(reinterpret_cast<const uint4*>(msk_row + (ci + PFM) * 32) + i);
               }
             }
-            if (p.out_f32) {
+            if (dbg_nost) {
+              if (v[0] == 123456.f) reinterpret_cast<float*>(p.out)[0] = v[1];   // keep the math alive
+            } else if (p.out_f32) {
               float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + out_col0 + c);
 #pragma unroll
               for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
