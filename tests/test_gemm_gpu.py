@@ -148,3 +148,42 @@ def test_gemm_epilogue_variants(mode, M, N, K):
     gemm(A, B, out, M, N, K, scale=scale, bias=bias, residual=R, relu=True, mask=Mk, debug_flags=(mode + 1) << 1)
     torch.cuda.synchronize()
     _close(out, ref)
+
+
+TWO_CTA = 64  # debug flag: force the cta_group::2 kernel
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 256, 512), (4096, 512, 1024), (300, 768, 256)])
+def test_gemm_2cta_plain_and_epilogue(M, N, K):
+    from tubedetr_b200.gemm import gemm
+    A, B, R, Mk = _rand((M, K), 31), _rand((N, K), 32), _rand((M, N), 33), _rand((M, N), 34)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    gemm(A, B, out, M, N, K, debug_flags=TWO_CTA)
+    torch.cuda.synchronize()
+    _close(out, A.float() @ B.float().t())
+    scale = torch.rand(N, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    ref = torch.relu((A.float() @ B.float().t()) * scale + bias + R.float()) * (Mk.float() > 0)
+    gemm(A, B, out, M, N, K, scale=scale, bias=bias, residual=R, relu=True, mask=Mk, debug_flags=TWO_CTA)
+    torch.cuda.synchronize()
+    _close(out, ref)
+
+
+def test_gemm_2cta_dgrad_and_implicit_conv():
+    from tubedetr_b200.gemm import REMAP_P2C, gemm
+    M, Cout, Cin = 700, 512, 256
+    dY, W = _rand((M, Cout), 35), _rand((Cout, Cin), 36)
+    out = torch.empty(M, Cin, dtype=torch.bfloat16, device="cuda")
+    gemm(dY, W, out, M, Cin, Cout, b_major=1, debug_flags=TWO_CTA)
+    _close(out, dY.float() @ W.float())
+    Nimg, H, Wd, C = 4, 11, 13, 256
+    x = _rand((Nimg, H, Wd, C), 37)
+    w = _rand((C, C, 3, 3), 38) * 0.05
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1)
+    xp = _pad_rows(x)
+    wk = w.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous()
+    taps = [(kh - 1) * (Wd + 2) + (kw - 1) for kh in range(3) for kw in range(3)]
+    o = torch.full((Nimg * H * Wd, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    gemm(xp, wk, o, xp.shape[0], C, C, ntaps=9, a_off1=taps, b_off0=[t * C for t in range(9)], remap=REMAP_P2C, img_hw=(H, Wd),
+         debug_flags=TWO_CTA)
+    _close(o.view(Nimg, H, Wd, C), ref)

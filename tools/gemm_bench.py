@@ -80,8 +80,33 @@ def experiment():
             P(f"experiment {name:24s} bn{bn}: {us:8.1f} us")
 
 
+def two_cta():
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (M, N, K) in ((16384, 2048, 2048), (48400, 256, 1024), (48400, 1024, 256)):
+        A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+        B = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+        out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        for nm, fl in (("1cta", 0), ("2cta", 64)):
+            us = bench(lambda: gemm(A, B, out, M, N, K, debug_flags=fl))
+            P(f"{nm} plain {M}x{N}x{K}: {us:8.1f} us {2.0 * M * N * K / us / 1e6:7.1f} TF")
+    N_, h, w, C = 100, 22, 22, 256
+    Rp = N_ * (h + 2) * (w + 2)
+    x = torch.randn(Rp, C, device="cuda").to(torch.bfloat16)
+    wk = (torch.randn(C, 9 * C, device="cuda") * 0.02).to(torch.bfloat16)
+    y = torch.empty(N_ * h * w, C, dtype=torch.bfloat16, device="cuda")
+    sc, sh = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    taps = [(kh - 1) * (w + 2) + (kw - 1) for kh in range(3) for kw in range(3)]
+    for nm, fl in (("1cta", 0), ("2cta", 64)):
+        us = bench(lambda: gemm(x, wk, y, Rp, C, C, ntaps=9, a_off1=taps, b_off0=[t * C for t in range(9)], scale=sc, bias=sh,
+                                relu=True, remap=REMAP_P2C, img_hw=(h, w), debug_flags=fl))
+        P(f"{nm} l3 conv2 3x3 fast: {us:8.1f} us  {2.0 * N_ * h * w * C * 9 * C / us / 1e6:7.1f} TF (algorithmic)")
+
+
 def main():
     P(torch.cuda.get_device_name(0))
+    if "--2cta" in sys.argv:
+        two_cta()
+        return
     experiment()
     case("l3 conv3 fast (res+relu)", 48400, 1024, 256, scale=True, residual=True, relu=True)
     case("l3 conv3 slow (res+relu)", 12100, 1024, 256, scale=True, residual=True, relu=True)

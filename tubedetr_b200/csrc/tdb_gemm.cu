@@ -754,6 +754,7 @@ static int g_num_sms = 0;
 static std::mutex g_init_mu;
 
 int tdb_num_sms() { return g_num_sms; }
+int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_);
 
 int tdb_init_once() {
   std::lock_guard<std::mutex> lk(g_init_mu);
@@ -889,6 +890,11 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   p.debug_flags = d->debug_flags;
   p.epi_mode = epi_mode;
   TDB_REQUIRE(p.ldo % 8 == 0 && (!p.residual || p.ldr % 8 == 0) && (!p.mask || p.ldmask % 8 == 0), "tdb_gemm: leading dims must be multiples of 8");
+  {
+    int r2 = tdb_gemm2_try(d, stream_);   // 2-CTA (cta_group::2) path for the feed-bound deep-K shapes
+    if (r2 < 0) return r2;
+    if (r2 == 1) return TDB_OK;
+  }
 
   CUtensorMap tmA, tmB;
   rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, p.a_major ? 64 : BM);

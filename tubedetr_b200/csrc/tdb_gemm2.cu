@@ -1,0 +1,392 @@
+// tubedetr_b200 -- 2-CTA (cta_group::2) variant of the tcgen05 GEMM for the compute-bound convolutions.
+//
+// Why: with one CTA per tile the 128 x 256 x 64 k-block needs 48 KB from L2 for 4 x 128 MMA cycles; measured on B200 the
+// main loop then runs at ~52 % tensor-pipe activity (profiles/r01_ncu_gemm.txt) because the L2 -> SM feed, not the MMA, is the
+// limit.  A CTA pair computes a 256 x 256 tile with ONE tcgen05.mma.cta_group::2 per k-step: each CTA loads its own 128 rows
+// of A and only HALF of B (128 of the 256 weight rows); the tensor cores of both SMs read both halves.  Per SM that is 32 KB
+// per k-block instead of 48 KB for the same MMA time.
+// Roles per CTA: warp 0 = TMA producer (both CTAs; all loads signal the LEADER's full barrier), warp 1 = MMA issuer (leader
+// CTA only; commits are multicast to both CTAs), warp 2 = TMEM allocator, warps 4-7 = epilogue of this CTA's 128 rows.
+// Supports K-major A, K- or MN-major B, implicit-conv taps, row remaps and the scale/bias/residual/ReLU/mask epilogue;
+// split-K / wgrad stay on the 1-CTA kernel.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/tubedetr_b200.h"
+#include "tdb_common.cuh"
+
+namespace tdb {
+
+constexpr int G2_BN = 256;
+constexpr int G2_STAGE_BYTES = 128 * 64 * 2 * 2;   // A 16 KB + half of B 16 KB
+constexpr int G2_STAGES = 6;
+constexpr int G2_THREADS = 256;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 1024 + 256 + 4 * 2048;
+
+struct Gemm2Params {
+  int M, N;
+  int kb_per_tap, ntaps;
+  int b_major;
+  int a_off0[TDB_MAX_TAPS], a_off1[TDB_MAX_TAPS], b_off0[TDB_MAX_TAPS], b_off1[TDB_MAX_TAPS];
+  int m_tiles, n_tiles, total_work;   // tiles of 256 x 256
+  const float* scale;
+  const float* bias;
+  const bf16* residual;
+  long long ldr;
+  const bf16* mask;
+  long long ldmask;
+  int relu;
+  void* out;
+  int out_f32;
+  long long ldo;
+  int remap, img_h, img_w;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (address bit 24 = CTA rank, masked off)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* after = smem + G2_STAGES * G2_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tfull_bar = empty_bar + G2_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);     // 4 epilogue warps of each CTA arrive on the leader's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = pair; w < p.total_work; w += npairs) {
+        const int nt = w % p.n_tiles, mt = w / p.n_tiles;
+        const int m0 = mt * 256 + (int)rank * 128;
+        const int nb = nt * G2_BN + (int)rank * 128;     // this CTA's half of the B tile
+        const int iters = p.ntaps * p.kb_per_tap;
+        for (int it = 0; it < iters; ++it) {
+          const int tap = it / p.kb_per_tap, kk = it - tap * p.kb_per_tap;
+          mbar_wait(&empty_bar[stage], phase ^ 1, 21);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          uint8_t* sA = smem + stage * G2_STAGE_BYTES;
+          uint8_t* sB = sA + 128 * 64 * 2;
+          tma_load_2d_2sm(sA, &tmA, &full_bar[stage], kk * 64 + p.a_off0[tap], m0 + p.a_off1[tap]);
+          if (p.b_major == 0) {
+            tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kk * 64 + p.b_off0[tap], nb + p.b_off1[tap]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[stage], nb + j * 64 + p.b_off0[tap], kk * 64 + p.b_off1[tap]);
+          }
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, G2_BN, 0, p.b_major);
+      const uint32_t b_kstep = p.b_major ? 2048u : 32u;
+      const uint32_t b_lbo = p.b_major ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = pair; w < p.total_work; w += npairs) {
+        const int iters = p.ntaps * p.kb_per_tap;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * G2_BN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[stage], phase, 23);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint32_t b_base = a_base + 128 * 64 * 2;
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            umma2_bf16(d_tmem, umma_smem_desc(a_base + s * 32, 16, 1024), umma_smem_desc(b_base + s * b_kstep, b_lbo, 1024),
+                       idesc, (it > 0 || s > 0) ? 1u : 0u);
+          umma2_commit_mc(&empty_bar[stage]);
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit_mc(&tfull_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    float* ssc = reinterpret_cast<float*>(after + 256) + wq * 512;
+    float* sbi = ssc + G2_BN;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int Hp = p.img_h + 2, Wp = p.img_w + 2;
+    constexpr int NCH = G2_BN / 32, PFR = 4, PFM = 2;
+    for (int w = pair; w < p.total_work; w += npairs) {
+      const int nt = w % p.n_tiles, mt = w / p.n_tiles;
+      const int n0 = nt * G2_BN;
+      const int row_t = mt * 256 + (int)rank * 128 + wq * 32 + lane;
+      bool valid = row_t < p.M;
+      long long out_row = row_t;
+      if (p.remap == TDB_REMAP_COMPACT_TO_PADDED) {
+        int hw = p.img_h * p.img_w;
+        int n = row_t / hw;
+        int rem = row_t - n * hw;
+        int h = rem / p.img_w;
+        int x = rem - h * p.img_w;
+        out_row = ((long long)n * Hp + h + 1) * Wp + x + 1;
+      } else if (p.remap == TDB_REMAP_PADDED_TO_COMPACT) {
+        int hw = Hp * Wp;
+        int n = row_t / hw;
+        int rem = row_t - n * hw;
+        int h = rem / Wp;
+        int x = rem - h * Wp;
+        valid = valid && h >= 1 && h <= p.img_h && x >= 1 && x <= p.img_w;
+        out_row = ((long long)n * p.img_h + (h - 1)) * p.img_w + (x - 1);
+      }
+      for (int i = lane; i < G2_BN; i += 32) {
+        ssc[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
+        sbi[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      }
+      __syncwarp();
+      uint4 rbuf[PFR][4], mbuf[PFM][4];
+      const bf16* res_row = p.residual ? p.residual + out_row * p.ldr + n0 : nullptr;
+      const bf16* msk_row = p.mask ? p.mask + (long long)row_t * p.ldmask + n0 : nullptr;
+      if (valid && res_row) {
+#pragma unroll
+        for (int ci = 0; ci < PFR; ++ci)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rbuf[ci][i] = __ldg(reinterpret_cast<const uint4*>(res_row + ci * 32) + i);
+      }
+      if (valid && msk_row) {
+#pragma unroll
+        for (int ci = 0; ci < PFM; ++ci)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mbuf[ci][i] = __ldg(reinterpret_cast<const uint4*>(msk_row + ci * 32) + i);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase, 24);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * G2_BN + ((uint32_t)(wq * 32) << 16);
+      uint32_t r[2][32];
+      tmem_ld_32x32(taddr, r[0]);
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = ci * 32;
+        tmem_ld_wait();
+        if (ci + 1 < NCH) tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 s4 = *reinterpret_cast<const float4*>(ssc + c + 4 * i);
+            const float4 b4 = *reinterpret_cast<const float4*>(sbi + c + 4 * i);
+            v[4 * i] = fmaf(__uint_as_float(r[ci & 1][4 * i]), s4.x, b4.x);
+            v[4 * i + 1] = fmaf(__uint_as_float(r[ci & 1][4 * i + 1]), s4.y, b4.y);
+            v[4 * i + 2] = fmaf(__uint_as_float(r[ci & 1][4 * i + 2]), s4.z, b4.z);
+            v[4 * i + 3] = fmaf(__uint_as_float(r[ci & 1][4 * i + 3]), s4.w, b4.w);
+          }
+          if (res_row != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = rbuf[ci % PFR][i];
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
+              v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+            }
+            if (ci + PFR < NCH) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rbuf[ci % PFR][i] = __ldg(reinterpret_cast<const uint4*>(res_row + (ci + PFR) * 32) + i);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (msk_row != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = mbuf[ci % PFM][i];
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * i] = f0.x > 0.f ? v[8 * i] : 0.f;         v[8 * i + 1] = f0.y > 0.f ? v[8 * i + 1] : 0.f;
+              v[8 * i + 2] = f1.x > 0.f ? v[8 * i + 2] : 0.f; v[8 * i + 3] = f1.y > 0.f ? v[8 * i + 3] : 0.f;
+              v[8 * i + 4] = f2.x > 0.f ? v[8 * i + 4] : 0.f; v[8 * i + 5] = f2.y > 0.f ? v[8 * i + 5] : 0.f;
+              v[8 * i + 6] = f3.x > 0.f ? v[8 * i + 6] : 0.f; v[8 * i + 7] = f3.y > 0.f ? v[8 * i + 7] : 0.f;
+            }
+            if (ci + PFM < NCH) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) mbuf[ci % PFM][i] = __ldg(reinterpret_cast<const uint4*>(msk_row + (ci + PFM) * 32) + i);
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0 + c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + n0 + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // both CTAs are done with each other's shared memory, barriers and TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+}  // namespace tdb
+
+int tdb_init_once();
+int tdb_make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+int tdb_num_sms();
+void tdb_count_launch(int n);
+
+// returns 1 if the descriptor was handled by the 2-CTA kernel, 0 if it does not qualify, <0 on error
+int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
+  using namespace tdb;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("TDB_GEMM2");
+    enabled = e ? atoi(e) : 0;
+  }
+  const bool forced = (d->debug_flags >> 6) & 1;
+  if (!enabled && !forced) return 0;
+  const int splits = d->splits < 1 ? 1 : d->splits;
+  const int nz = d->nz < 1 ? 1 : d->nz;
+  if (d->a_major != 0 || splits != 1 || nz != 1 || d->N % 256 != 0 || d->K % 64 != 0 || (d->block_n && d->block_n != 256)) return 0;
+  const int m_tiles = (d->M + 255) / 256;
+  const int n_tiles = d->N / 256;
+  const long long total = (long long)m_tiles * n_tiles;
+  const int pairs = tdb_num_sms() / 2;
+  // worthwhile only for deep reductions (the feed-bound regime) with enough tiles to fill the pairs
+  if (!forced && ((long long)d->K * d->ntaps < 512 || total < pairs / 2)) return 0;
+  static bool attr = false;
+  if (!attr) {
+    TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    attr = true;
+  }
+  Gemm2Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M; p.N = d->N; p.kb_per_tap = d->K / 64; p.ntaps = d->ntaps; p.b_major = d->b_major ? 1 : 0;
+  for (int i = 0; i < TDB_MAX_TAPS; ++i) {
+    p.a_off0[i] = d->a_off0[i]; p.a_off1[i] = d->a_off1[i];
+    p.b_off0[i] = d->b_off0[i]; p.b_off1[i] = d->b_off1[i];
+  }
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.total_work = (int)total;
+  p.scale = d->scale; p.bias = d->bias;
+  p.residual = (const bf16*)d->residual; p.ldr = d->ldr;
+  p.mask = (const bf16*)d->mask; p.ldmask = d->ldmask;
+  p.relu = d->relu; p.out = d->out; p.out_f32 = d->out_dtype == TDB_OUT_F32; p.ldo = d->ldo;
+  p.remap = d->remap; p.img_h = d->img_h; p.img_w = d->img_w;
+  CUtensorMap tmA, tmB;
+  int rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, 128);
+  if (rc) return rc;
+  rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : 128);
+  if (rc) return rc;
+  int np = total < pairs ? (int)total : pairs;
+  tdb_gemm2_kernel<<<np * 2, G2_THREADS, G2_SMEM, (cudaStream_t)stream_>>>(tmA, tmB, p);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(1);
+  return 1;
+}
