@@ -187,3 +187,32 @@ def test_gemm_2cta_dgrad_and_implicit_conv():
     gemm(xp, wk, o, xp.shape[0], C, C, ntaps=9, a_off1=taps, b_off0=[t * C for t in range(9)], remap=REMAP_P2C, img_hw=(H, Wd),
          debug_flags=TWO_CTA)
     _close(o.view(Nimg, H, Wd, C), ref)
+
+
+@pytest.mark.parametrize("splits", [1, 4])
+def test_gemm_2cta_wgrad_forms(splits):
+    from tubedetr_b200.gemm import effective_splits, gemm, splitk_reduce
+    R, Cout, Cin = 3000, 512, 256
+    dY, X = _rand((R, Cout), 41), _rand((R, Cin), 42)
+    s = effective_splits(R, splits)
+    part = torch.empty(s, Cout, Cin, dtype=torch.float32, device="cuda")
+    gemm(dY, X, part, Cout, Cin, R, a_major=1, b_major=1, splits=splits, debug_flags=TWO_CTA)
+    out = torch.empty(Cout, Cin, dtype=torch.float32, device="cuda")
+    splitk_reduce(part, s, Cout, Cin, out)
+    _close(out, dY.float().t() @ X.float(), tol=2e-3)
+    # z-batched 3x3 wgrad over the haloed grid
+    Nimg, H, W, C = 3, 9, 10, 256
+    x, g = _rand((Nimg, H, W, C), 43), _rand((Nimg, H, W, C), 44)
+    w = (_rand((C, C, 3, 3), 45) * 0.05).float().requires_grad_(True)
+    y = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w, padding=1)
+    y.backward(g.float().permute(0, 3, 1, 2))
+    taps = [(kh - 1) * (W + 2) + (kw - 1) for kh in range(3) for kw in range(3)]
+    gp, xp = _pad_rows(g), _pad_rows(x)
+    Rr = gp.shape[0]
+    s = effective_splits(Rr, splits)
+    part = torch.empty(s, C, 9 * C, dtype=torch.float32, device="cuda")
+    gemm(gp, xp, part, C, C, Rr, a_major=1, b_major=1, nz=9, z_b_off1=taps, z_out_col=[t * C for t in range(9)], splits=splits,
+         debug_flags=TWO_CTA)
+    dw = torch.empty(C, C, 3, 3, dtype=torch.float32, device="cuda")
+    splitk_reduce(part, s, C, 9 * C, dw, taps=9)
+    _close(dw, w.grad, tol=5e-3)

@@ -7,8 +7,8 @@
 // per k-block instead of 48 KB for the same MMA time.
 // Roles per CTA: warp 0 = TMA producer (both CTAs; all loads signal the LEADER's full barrier), warp 1 = MMA issuer (leader
 // CTA only; commits are multicast to both CTAs), warp 2 = TMEM allocator, warps 4-7 = epilogue of this CTA's 128 rows.
-// Supports K-major A, K- or MN-major B, implicit-conv taps, row remaps and the scale/bias/residual/ReLU/mask epilogue;
-// split-K / wgrad stay on the 1-CTA kernel.
+// Supports K- and MN-major operands (fprop / dgrad / wgrad), implicit-conv taps, z-batched wgrad taps, split reductions,
+// row remaps and the scale/bias/residual/ReLU/mask epilogue.
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,7 +26,9 @@ constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 1024 + 256 + 4 * 2048;
 struct Gemm2Params {
   int M, N;
   int kb_per_tap, ntaps;
-  int b_major;
+  int a_major, b_major;
+  int nz, splits, kb_per_split;
+  int z_b_off1[TDB_MAX_TAPS], z_out_col[TDB_MAX_TAPS];
   int a_off0[TDB_MAX_TAPS], a_off1[TDB_MAX_TAPS], b_off0[TDB_MAX_TAPS], b_off1[TDB_MAX_TAPS];
   int m_tiles, n_tiles, total_work;   // tiles of 256 x 256
   const float* scale;
@@ -91,6 +93,29 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
                : "memory");
 }
 
+struct Work2 {
+  int mt, nt, z, split, kb_begin, iters;
+};
+__device__ __forceinline__ Work2 decode2(const Gemm2Params& p, int w) {
+  Work2 it;
+  it.nt = w % p.n_tiles;
+  int r = w / p.n_tiles;
+  it.mt = r % p.m_tiles;
+  r /= p.m_tiles;
+  it.split = r % p.splits;
+  it.z = r / p.splits;
+  if (p.splits == 1) {
+    it.kb_begin = 0;
+    it.iters = p.ntaps * p.kb_per_tap;
+  } else {
+    it.kb_begin = it.split * p.kb_per_split;
+    int e = it.kb_begin + p.kb_per_split;
+    if (e > p.kb_per_tap) e = p.kb_per_tap;
+    it.iters = e - it.kb_begin;
+  }
+  return it;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ Gemm2Params p) {
@@ -136,23 +161,36 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int w = pair; w < p.total_work; w += npairs) {
-        const int nt = w % p.n_tiles, mt = w / p.n_tiles;
-        const int m0 = mt * 256 + (int)rank * 128;
-        const int nb = nt * G2_BN + (int)rank * 128;     // this CTA's half of the B tile
-        const int iters = p.ntaps * p.kb_per_tap;
-        for (int it = 0; it < iters; ++it) {
-          const int tap = it / p.kb_per_tap, kk = it - tap * p.kb_per_tap;
+        const Work2 wi = decode2(p, w);
+        const int m0 = wi.mt * 256 + (int)rank * 128;
+        const int nb = wi.nt * G2_BN + (int)rank * 128;     // this CTA's half of the B tile
+        for (int it = 0; it < wi.iters; ++it) {
+          int tap, kk;
+          if (p.splits == 1) {
+            tap = it / p.kb_per_tap;
+            kk = it - tap * p.kb_per_tap;
+          } else {
+            tap = 0;
+            kk = wi.kb_begin + it;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1, 21);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
           uint8_t* sA = smem + stage * G2_STAGE_BYTES;
           uint8_t* sB = sA + 128 * 64 * 2;
-          tma_load_2d_2sm(sA, &tmA, &full_bar[stage], kk * 64 + p.a_off0[tap], m0 + p.a_off1[tap]);
+          if (p.a_major == 0) {
+            tma_load_2d_2sm(sA, &tmA, &full_bar[stage], kk * 64 + p.a_off0[tap], m0 + p.a_off1[tap]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d_2sm(sA + j * 8192, &tmA, &full_bar[stage], m0 + j * 64 + p.a_off0[tap], kk * 64 + p.a_off1[tap]);
+          }
           if (p.b_major == 0) {
             tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kk * 64 + p.b_off0[tap], nb + p.b_off1[tap]);
           } else {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[stage], nb + j * 64 + p.b_off0[tap], kk * 64 + p.b_off1[tap]);
+              tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[stage], nb + j * 64 + p.b_off0[tap],
+                              kk * 64 + p.b_off1[tap] + p.z_b_off1[wi.z]);
           }
           if (++stage == G2_STAGES) {
             stage = 0;
@@ -163,7 +201,9 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(256, G2_BN, 0, p.b_major);
+      const uint32_t idesc = umma_idesc_bf16(256, G2_BN, p.a_major, p.b_major);
+      const uint32_t a_kstep = p.a_major ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_major ? 8192u : 16u;
       const uint32_t b_kstep = p.b_major ? 2048u : 32u;
       const uint32_t b_lbo = p.b_major ? 8192u : 16u;
       int stage = 0;
@@ -171,7 +211,7 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int w = pair; w < p.total_work; w += npairs) {
-        const int iters = p.ntaps * p.kb_per_tap;
+        const int iters = decode2(p, w).iters;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BN;
@@ -182,7 +222,7 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b_base = a_base + 128 * 64 * 2;
 #pragma unroll
           for (int s = 0; s < 4; ++s)
-            umma2_bf16(d_tmem, umma_smem_desc(a_base + s * 32, 16, 1024), umma_smem_desc(b_base + s * b_kstep, b_lbo, 1024),
+            umma2_bf16(d_tmem, umma_smem_desc(a_base + s * a_kstep, a_lbo, 1024), umma_smem_desc(b_base + s * b_kstep, b_lbo, 1024),
                        idesc, (it > 0 || s > 0) ? 1u : 0u);
           umma2_commit_mc(&empty_bar[stage]);
           if (++stage == G2_STAGES) {
@@ -206,9 +246,10 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int Hp = p.img_h + 2, Wp = p.img_w + 2;
     constexpr int NCH = G2_BN / 32, PFR = 4, PFM = 2;
     for (int w = pair; w < p.total_work; w += npairs) {
-      const int nt = w % p.n_tiles, mt = w / p.n_tiles;
-      const int n0 = nt * G2_BN;
-      const int row_t = mt * 256 + (int)rank * 128 + wq * 32 + lane;
+      const Work2 wi = decode2(p, w);
+      const int n0 = wi.nt * G2_BN;
+      const int out_col0 = n0 + p.z_out_col[wi.z];
+      const int row_t = wi.mt * 256 + (int)rank * 128 + wq * 32 + lane;
       bool valid = row_t < p.M;
       long long out_row = row_t;
       if (p.remap == TDB_REMAP_COMPACT_TO_PADDED) {
@@ -227,6 +268,7 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         valid = valid && h >= 1 && h <= p.img_h && x >= 1 && x <= p.img_w;
         out_row = ((long long)n * p.img_h + (h - 1)) * p.img_w + (x - 1);
       }
+      if (p.splits > 1) out_row += (long long)wi.split * p.M;
       for (int i = lane; i < G2_BN; i += 32) {
         ssc[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
         sbi[i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
@@ -301,11 +343,11 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0 + c);
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.ldo + out_col0 + c);
 #pragma unroll
             for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + n0 + c);
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + out_col0 + c);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               op[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
@@ -352,15 +394,26 @@ int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
   }
   const bool forced = (d->debug_flags >> 6) & 1;
   if (!enabled && !forced) return 0;
-  const int splits = d->splits < 1 ? 1 : d->splits;
+  int splits = d->splits < 1 ? 1 : d->splits;
   const int nz = d->nz < 1 ? 1 : d->nz;
-  if (d->a_major != 0 || splits != 1 || nz != 1 || d->N % 256 != 0 || d->K % 64 != 0 || (d->block_n && d->block_n != 256)) return 0;
+  if (d->N % 256 != 0 || (d->block_n && d->block_n != 256)) return 0;
+  if ((d->a_major == 0 || d->b_major == 0) && d->K % 64 != 0) return 0;
+  const int kb = (d->K + 63) / 64;
+  int kb_per_split = kb;
+  if (splits > 1) {       // same split arithmetic as tdb_gemm / tdb_gemm_effective_splits
+    if (d->ntaps != 1 || d->out_dtype != TDB_OUT_F32) return 0;
+    if (splits > kb) splits = kb;
+    kb_per_split = (kb + splits - 1) / splits;
+    splits = (kb + kb_per_split - 1) / kb_per_split;
+  }
   const int m_tiles = (d->M + 255) / 256;
   const int n_tiles = d->N / 256;
-  const long long total = (long long)m_tiles * n_tiles;
+  const long long total = (long long)m_tiles * n_tiles * nz * splits;
   const int pairs = tdb_num_sms() / 2;
-  // worthwhile only for deep reductions (the feed-bound regime) with enough tiles to fill the pairs
-  if (!forced && ((long long)d->K * d->ntaps < 512 || total < pairs / 2)) return 0;
+  // worthwhile only for deep reductions (the feed-bound regime) with enough tiles to fill the pairs, and when the
+  // 256-row pair tile does not waste more than a quarter of its rows
+  const long long kdepth = (splits > 1 ? (long long)kb_per_split * 64 : (long long)d->K * d->ntaps);
+  if (!forced && (kdepth < 512 || total < pairs / 2 || (long long)m_tiles * 256 * 3 > (long long)d->M * 4)) return 0;
   static bool attr = false;
   if (!attr) {
     TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
@@ -368,10 +421,14 @@ int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
   }
   Gemm2Params p;
   memset(&p, 0, sizeof(p));
-  p.M = d->M; p.N = d->N; p.kb_per_tap = d->K / 64; p.ntaps = d->ntaps; p.b_major = d->b_major ? 1 : 0;
+  p.M = d->M; p.N = d->N; p.kb_per_tap = kb; p.ntaps = d->ntaps;
+  p.a_major = d->a_major ? 1 : 0; p.b_major = d->b_major ? 1 : 0;
+  p.nz = nz; p.splits = splits; p.kb_per_split = kb_per_split;
   for (int i = 0; i < TDB_MAX_TAPS; ++i) {
     p.a_off0[i] = d->a_off0[i]; p.a_off1[i] = d->a_off1[i];
     p.b_off0[i] = d->b_off0[i]; p.b_off1[i] = d->b_off1[i];
+    p.z_b_off1[i] = d->nz >= 1 ? d->z_b_off1[i] : 0;
+    p.z_out_col[i] = d->nz >= 1 ? d->z_out_col[i] : 0;
   }
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.total_work = (int)total;
   p.scale = d->scale; p.bias = d->bias;
@@ -380,7 +437,7 @@ int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
   p.relu = d->relu; p.out = d->out; p.out_f32 = d->out_dtype == TDB_OUT_F32; p.ldo = d->ldo;
   p.remap = d->remap; p.img_h = d->img_h; p.img_w = d->img_w;
   CUtensorMap tmA, tmB;
-  int rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, 128);
+  int rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, p.a_major ? 64 : 128);
   if (rc) return rc;
   rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : 128);
   if (rc) return rc;
