@@ -135,7 +135,7 @@ def test_gemm_conv3x3_dgrad_and_wgrad_padded_grid():
     _close(outp, ref)
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 2, 3, 4, 5])
 @pytest.mark.parametrize("M,N,K", [(1500, 256, 320), (12100, 1024, 256), (130, 128, 64)])
 def test_gemm_epilogue_variants(mode, M, N, K):
     """every epilogue implementation (direct, register-prefetch, pipelined, TMA-fed residual) gives the same result"""

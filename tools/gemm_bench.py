@@ -31,7 +31,7 @@ def bench(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3  # us
 
 
-def case(name, M, N, K, scale=False, residual=False, relu=False, mask=False, bmaj=0, f32=False, check=True, modes=(4, 5)):
+def case(name, M, N, K, scale=False, residual=False, relu=False, mask=False, bmaj=0, f32=False, check=True, modes=(5, 6)):
     g = torch.Generator(device="cuda").manual_seed(0)
     A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
     B = (torch.randn(K, N, device="cuda", generator=g) if bmaj else torch.randn(N, K, device="cuda", generator=g)).to(torch.bfloat16)

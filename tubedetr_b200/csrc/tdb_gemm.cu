@@ -55,10 +55,12 @@ template <int BN, int EPI = 0>
 struct GemmCfg {
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   // mode 4 (TMA-fed residual, BN = 128 only) trades two pipeline stages for a double-buffered 128 x 128 residual tile
-  static constexpr int kStages = (EPI == 4) ? 4 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  // mode 5 (TMA residual in, TMA store out, BN = 128): three 128 x 128 tiles that hold the residual, then the output in place
+  static constexpr int kStages = (EPI == 4 || EPI == 5) ? 4 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kOperandBytes = (EPI == 4) ? 2 * BM * BN * 2 : 0;
-  static constexpr int kStagingBytes = 4 * 32 * 64 * 4;  // per epilogue warp: 32 rows x 64 fp32 columns
+  static constexpr int kOperandSlots = (EPI == 4) ? 2 : (EPI == 5 ? 3 : 0);
+  static constexpr int kOperandBytes = kOperandSlots * BM * BN * 2;
+  static constexpr int kStagingBytes = (EPI == 5) ? 1024 : 4 * 32 * 64 * 4;  // per epilogue warp 32 x 64 fp32 (mode 5: shared scale/bias)
   static constexpr int kSmemBytes = kStages * kStageBytes + kOperandBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
 
@@ -91,7 +93,8 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKParams& p, int w, int
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ GemmKParams p) {
+                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ GemmKParams p) {
   using Cfg = GemmCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -101,9 +104,9 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
-  uint64_t* ofull_bar = tempty_bar + 2;             // [2] residual tile landed (mode 4)
-  uint64_t* oempty_bar = ofull_bar + 2;             // [2] residual tile consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 2);
+  uint64_t* ofull_bar = tempty_bar + 2;             // [3] residual tile landed (modes 4, 5)
+  uint64_t* oempty_bar = ofull_bar + 3;             // [3] residual / output tile free again
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 3);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,9 +123,12 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
-      mbar_init(&ofull_bar[s], 1);
-      mbar_init(&oempty_bar[s], 4);
     }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&ofull_bar[s], 1);
+      mbar_init(&oempty_bar[s], EPI == 5 ? 1 : 4);
+    }
+    if (EPI == 5) tma_prefetch_desc(&tmO);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -143,6 +149,19 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t ophase = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         const WorkItem wi = decode_work(p, w, BN);
+        if constexpr (EPI == 5) {
+          if (p.residual != nullptr) {      // residual tile, two tiles ahead of the epilogue (3 slots)
+            mbar_wait(&oempty_bar[oslot], ophase ^ 1, 7);
+            mbar_expect_tx(&ofull_bar[oslot], BM * BN * 2);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(opnd + (oslot * (BN / 64) + j) * (BM * 128), &tmR, &ofull_bar[oslot], wi.n0 + j * 64, wi.m0);
+          }
+          if (++oslot == 3) {
+            oslot = 0;
+            ophase ^= 1;
+          }
+        }
         if constexpr (EPI == 4) {
           // whole residual tile of this work item (128 rows x BN columns) by TMA, one tile ahead of the epilogue: its HBM
           // latency overlaps the previous tile's epilogue and this tile's main loop, with 2 x 32 KB in flight per SM
@@ -238,9 +257,10 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int wq = warp & 3;
-    float* stage = reinterpret_cast<float*>(after + 256) + wq * (32 * 64);
+    float* stage = reinterpret_cast<float*>(after + 256) + (EPI == 5 ? 0 : wq * (32 * 64));
     int oslot = 0;
     uint32_t ophase = 0;
+    int tiles_done = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int Hp = p.img_h + 2, Wp = p.img_w + 2;
@@ -278,6 +298,16 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bf16* msk_row = p.mask ? p.mask + (long long)row_t * p.ldmask + wi.n0 : nullptr;
       float* ssc = stage;            // mode 3: per-warp private copy of this tile's scale / bias columns (L1 has no capacity
       float* sbi = stage + BN;       // next to ~226 KB of shared memory, so per-chunk __ldg would each pay an L2 round trip)
+      if constexpr (EPI == 5) {
+        // scale / bias of this tile, one copy shared by the 4 epilogue warps (named barrier 1 = the 128 epilogue threads)
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's readers are done with the copy
+        const int t = threadIdx.x - 128;
+        if (t < BN) {
+          ssc[t] = p.scale ? __ldg(p.scale + wi.n0 + t) : 1.f;
+          sbi[t] = p.bias ? __ldg(p.bias + wi.n0 + t) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       if constexpr (EPI == 3 || EPI == 4) {
         for (int i = lane; i < BN; i += 32) {
           ssc[i] = p.scale ? __ldg(p.scale + wi.n0 + i) : 1.f;
@@ -285,8 +315,8 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();
       }
-      if constexpr (EPI == 2 || EPI == 3 || EPI == 4) {
-        if (EPI != 4 && valid && res_row) {
+      if constexpr (EPI == 2 || EPI == 3 || EPI == 4 || EPI == 5) {
+        if (EPI != 4 && EPI != 5 && valid && res_row) {
 #pragma unroll
           for (int ci = 0; ci < PFR; ++ci)
 #pragma unroll
@@ -302,7 +332,99 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(wq * 32) << 16);
-      if constexpr (EPI == 4) {
+      if constexpr (EPI == 5) {
+        // TMA in, TMA out: thread r owns row r of the 128 x 128 tile in shared memory.  It reads the residual there (if any),
+        // overwrites it IN PLACE with the bf16 output, and one thread hands the finished tile to the TMA store engine, so no
+        // epilogue thread issues a global load or store.  The slot is recycled once the store has finished reading it.
+        if (p.residual != nullptr) mbar_wait(&ofull_bar[oslot], ophase, 8);
+        const int rloc = wq * 32 + lane;
+        uint8_t* obase = opnd + oslot * (BN / 64) * (BM * 128) + rloc * 128;
+        uint32_t r[2][32];
+        tmem_ld_32x32(taddr, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = ci * 32;
+          tmem_ld_wait();
+          if (ci + 1 < NCH) tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 s4 = *reinterpret_cast<const float4*>(ssc + c + 4 * i);
+            const float4 b4 = *reinterpret_cast<const float4*>(sbi + c + 4 * i);
+            v[4 * i] = fmaf(__uint_as_float(r[ci & 1][4 * i]), s4.x, b4.x);
+            v[4 * i + 1] = fmaf(__uint_as_float(r[ci & 1][4 * i + 1]), s4.y, b4.y);
+            v[4 * i + 2] = fmaf(__uint_as_float(r[ci & 1][4 * i + 2]), s4.z, b4.z);
+            v[4 * i + 3] = fmaf(__uint_as_float(r[ci & 1][4 * i + 3]), s4.w, b4.w);
+          }
+          uint8_t* box = obase + (ci >> 1) * (BM * 128);
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j16 = (ci & 1) * 4 + i;
+              uint4 u = *reinterpret_cast<const uint4*>(box + ((j16 ^ (rloc & 7)) << 4));
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
+              v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (msk_row != nullptr && valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = mbuf[ci % PFM][i];
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+              v[8 * i] = f0.x > 0.f ? v[8 * i] : 0.f;         v[8 * i + 1] = f0.y > 0.f ? v[8 * i + 1] : 0.f;
+              v[8 * i + 2] = f1.x > 0.f ? v[8 * i + 2] : 0.f; v[8 * i + 3] = f1.y > 0.f ? v[8 * i + 3] : 0.f;
+              v[8 * i + 4] = f2.x > 0.f ? v[8 * i + 4] : 0.f; v[8 * i + 5] = f2.y > 0.f ? v[8 * i + 5] : 0.f;
+              v[8 * i + 6] = f3.x > 0.f ? v[8 * i + 6] : 0.f; v[8 * i + 7] = f3.y > 0.f ? v[8 * i + 7] : 0.f;
+            }
+            if (ci + PFM < NCH) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) mbuf[ci % PFM][i] = __ldg(reinterpret_cast<const uint4*>(msk_row + (ci + PFM) * 32) + i);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j16 = (ci & 1) * 4 + i;
+            *reinterpret_cast<uint4*>(box + ((j16 ^ (rloc & 7)) << 4)) =
+                make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+        // accumulator fully read: hand TMEM back to the MMA warp before the store hand-off
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        const bool issuer = (warp == 4 && lane == 0);
+        if (issuer) {
+          // the store issued one tile ago has finished reading its slot -> recycle that slot for the producer
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (tiles_done > 0) mbar_arrive(&oempty_bar[(oslot + 2) % 3]);
+        }
+        fence_proxy_async();                                   // my smem writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, 128;" ::: "memory");         // whole tile written (and the previous store drained)
+        if (issuer) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmO),
+                         "r"(smem_u32(opnd + (oslot * (BN / 64) + j) * (BM * 128))), "r"(out_col0 + j * 64), "r"(wi.m0)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++tiles_done;
+        if (++oslot == 3) {
+          oslot = 0;
+          ophase ^= 1;
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      } else if constexpr (EPI == 4) {
         // residual tile arrives through TMA (128-byte swizzled boxes of 64 columns); thread r reads its own row: the swizzle
         // makes 8 consecutive rows hit 8 different 16-byte bank groups, so the row-per-thread reads are conflict free
         mbar_wait(&ofull_bar[oslot], ophase, 6);
@@ -699,6 +821,9 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
+  if constexpr (EPI == 5) {
+    if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // last output tile has left shared memory
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -784,6 +909,7 @@ int tdb_init_once() {
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128, 4>::kSmemBytes));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<128, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<128, 5>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
   TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::tdb_gemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdb::GemmCfg<256>::kSmemBytes));
@@ -857,13 +983,16 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
     static int env_mode = -2;
     if (env_mode == -2) { const char* e = getenv("TDB_EPI_MODE"); env_mode = e ? atoi(e) : -1; }
     int m = (d->debug_flags >> 1) & 7;   // 0 = auto, else mode + 1: 1 direct, 2 smem-staged, 3 +reg prefetch, 4 pipelined, 5 TMA residual
-    epi_mode = m ? m - 1 : (env_mode >= 0 ? env_mode : 4);
-    // mode 4 (residual tile by TMA) needs an un-remapped residual and 128-wide tiles; otherwise the pipelined register path
+    epi_mode = m ? m - 1 : (env_mode >= 0 ? env_mode : 5);
+    // modes 4/5 (residual tile by TMA; 5 also stores the output tile by TMA) need un-remapped rows and 128-wide tiles;
+    // otherwise the pipelined register path (3)
     const bool tma_res_ok = d->residual && d->remap == TDB_REMAP_NONE && splits == 1 && d->N % 128 == 0 &&
                             (d->block_n == 0 || d->block_n == 128);
+    const bool tma_out_ok = tma_res_ok && d->out_dtype == TDB_OUT_BF16 && nz == 1;
+    if (epi_mode == 5 && !tma_out_ok) epi_mode = 4;
     if (epi_mode == 4 && !tma_res_ok) epi_mode = 3;
   }
-  const int bn = epi_mode == 4 ? 128 : pick_block_n(d->N, (long long)m_tiles * nz * splits, d->block_n);
+  const int bn = (epi_mode == 4 || epi_mode == 5) ? 128 : pick_block_n(d->N, (long long)m_tiles * nz * splits, d->block_n);
   TDB_REQUIRE(bn != 0, "tdb_gemm: no tile width for N=%d (block_n=%d)", d->N, d->block_n);
   if (d->remap != TDB_REMAP_NONE) TDB_REQUIRE(d->img_h > 0 && d->img_w > 0, "tdb_gemm: remap needs img_h/img_w");
 
@@ -901,9 +1030,13 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   if (rc) return rc;
   rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : bn);
   if (rc) return rc;
-  CUtensorMap tmR = tmA;   // only dereferenced in epilogue mode 4
-  if (p.epi_mode == 4) {
+  CUtensorMap tmR = tmA, tmO = tmA;   // only dereferenced in epilogue modes 4 / 5
+  if (p.epi_mode == 4 || p.epi_mode == 5) {
     rc = tdb_make_tmap_bf16(&tmR, d->residual, d->M, d->N, d->ldr, BM);
+    if (rc) return rc;
+  }
+  if (p.epi_mode == 5) {
+    rc = tdb_make_tmap_bf16(&tmO, d->out, d->M, d->N, d->ldo, BM);
     if (rc) return rc;
   }
 
@@ -913,7 +1046,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   auto launch = [&](int bn_, const CUtensorMap& tmB_, const GemmKParams& q) -> int {
     int grid = q.total_work < g_num_sms ? q.total_work : g_num_sms;
     if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-#define TDB_LAUNCH(BN_, EPI_) tdb_gemm_kernel<BN_, EPI_><<<grid, kGemmThreads, GemmCfg<BN_, EPI_>::kSmemBytes, stream>>>(tmA, tmB_, tmR, q)
+#define TDB_LAUNCH(BN_, EPI_) tdb_gemm_kernel<BN_, EPI_><<<grid, kGemmThreads, GemmCfg<BN_, EPI_>::kSmemBytes, stream>>>(tmA, tmB_, tmR, tmO, q)
     if (q.epi_mode == 0) {
       switch (bn_) {
         case 64: TDB_LAUNCH(64, 0); break;
@@ -932,6 +1065,8 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
         case 128: TDB_LAUNCH(128, 2); break;
         default: TDB_LAUNCH(256, 2); break;
       }
+    } else if (q.epi_mode == 5 && bn_ == 128) {
+      TDB_LAUNCH(128, 5);
     } else if (q.epi_mode == 4 && bn_ == 128) {
       TDB_LAUNCH(128, 4);
     } else {

@@ -394,6 +394,9 @@ int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
   }
   const bool forced = (d->debug_flags >> 6) & 1;
   if (!enabled && !forced) return 0;
+  static int wgrad_ok = -1;
+  if (wgrad_ok < 0) { const char* e = getenv("TDB_GEMM2_WGRAD"); wgrad_ok = e ? atoi(e) : 1; }
+  if (!forced && !wgrad_ok && d->a_major) return 0;
   int splits = d->splits < 1 ? 1 : d->splits;
   const int nz = d->nz < 1 ? 1 : d->nz;
   if (d->N % 256 != 0 || (d->block_n && d->block_n != 256)) return 0;
