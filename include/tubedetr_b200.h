@@ -124,12 +124,17 @@ int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* partial, 
  * q/k/v/o: bf16 rows [B*L][>= H*32] with row strides ld*; kpm [B][Lk] nonzero = padded key.
  * p [B][H][Lq][Lk] probabilities (kept for backward); pbar [B][Lq][Lk] = mean over heads (guided-attention loss) or NULL.
  * Backward takes dO and optionally dPbar and returns dq/dk/dv in the layout of q/k/v.
- * ------------------------------------------------------------------------------------------------ */
+ * Attention dropout (train mode, reference nn.MultiheadAttention(dropout=0.1)): keep [B][H][Lq][Lk] (1 = kept) and
+ * keep_scale = 1/(1-p); p then holds the pre-dropout probabilities, pdrop the dropped ones (which pbar averages).
+ * keep == NULL disables it.
+ */
 int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm,
-                void* o, int64_t ldo, float* p, float* pbar, int B, int H, int Lq, int Lk, float scale, void* stream);
+                void* o, int64_t ldo, float* p, float* pbar, const uint8_t* keep, float* pdrop, float keep_scale, int B, int H,
+                int Lq, int Lk, float scale, void* stream);
 int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
-                int64_t lddo, const float* p, const float* dpbar, float* ds_scratch, void* dq, int64_t lddq, void* dk,
-                int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale, void* stream);
+                int64_t lddo, const float* p, const uint8_t* keep, float keep_scale, float* pd_scratch, const float* dpbar,
+                float* ds_scratch, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq,
+                int Lk, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused time-aligned cross-attention of the space-time decoder (reference models/transformer.py:724-745):

@@ -199,3 +199,41 @@ def test_xattn_fused_matches_unfused_math(F, S):
     _close(pbar, rp.mean(1), 2e-2)
     _close(o.view(F, 1, d), ro, 2e-2)
     assert torch.isfinite(o.float()).all()
+
+
+def test_mha_attention_dropout_fwd_bwd():
+    """attention-probability dropout with a given keep mask: forward, head-mean of the DROPPED probabilities, backward"""
+    from tubedetr_b200 import kernels as K
+    B, H, Lq, Lk, d, pd = 3, 8, 37, 59, 256, 0.1
+    scale = 1 / math.sqrt(32)
+    q, k, v = _r((B, Lq, d), 50), _r((B, Lk, d), 51), _r((B, Lk, d), 52)
+    kpm = torch.zeros(B, Lk, dtype=torch.uint8, device="cuda")
+    kpm[:, Lk - 7:] = 1
+    keep = (torch.rand(B, H, Lq, Lk, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) >= pd).to(torch.uint8)
+    o = torch.empty(B * Lq, d, dtype=torch.bfloat16, device="cuda")
+    p, pdrop = torch.empty(B, H, Lq, Lk, device="cuda"), torch.empty(B, H, Lq, Lk, device="cuda")
+    pbar = torch.empty(B, Lq, Lk, device="cuda")
+    K.mha_fwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pdrop,
+              keep_scale=1 / (1 - pd))
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    qh = (qf * scale).view(B, Lq, H, 32).transpose(1, 2)
+    kh, vh = kf.view(B, Lk, H, 32).transpose(1, 2), vf.view(B, Lk, H, 32).transpose(1, 2)
+    sc = (qh @ kh.transpose(-1, -2)).masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
+    rp = sc.softmax(-1)
+    rpd = rp * keep.float() / (1 - pd)
+    ro = (rpd @ vh).transpose(1, 2).reshape(B, Lq, d)
+    _close(p, rp, 1e-4)
+    _close(pdrop, rpd, 1e-4)
+    _close(pbar, rpd.mean(1), 1e-4)
+    _close(o.view(B, Lq, d), ro, 1e-2)
+    do = _r((B, Lq, d), 53)
+    dpbar = _r((B, Lq, Lk), 54, torch.float32)
+    (ro * do.float()).sum().add((rpd.mean(1) * dpbar).sum()).backward()
+    ds, pds = torch.empty_like(p), torch.empty_like(p)
+    dq, dk, dv = (torch.empty(t.shape[0] * t.shape[1], d, dtype=torch.bfloat16, device="cuda") for t in (q, k, v))
+    K.mha_bwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), do.view(-1, d), p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale,
+              keep=keep, keep_scale=1 / (1 - pd), pd_scratch=pds)
+    for got, ref in ((dq.view_as(q), qf.grad), (dk.view_as(k), kf.grad), (dv.view_as(v), vf.grad)):
+        _close(got, ref, 2e-2)
+        a = (got.float() * ref).sum() / (ref * ref).sum()
+        assert abs(a.item() - 1) < 5e-3, a.item()

@@ -143,3 +143,29 @@ def test_losses_and_gradients_match_reference(name):
     med = sorted(w[0] for w in worst)[len(worst) // 2]
     _log(f"{name}: grad-norm rel err median {med:.4f}, params checked {checked}")
     assert med < 0.08
+
+
+def test_train_mode_applies_dropout_and_backpropagates():
+    """train(): every dropout of the reference is live (two passes differ, eval is unchanged), gradients stay finite."""
+    g = load_gold("cfg1")
+    model, crit, wd, b, mc, out_eval = _run(g["cfg"])
+    model.train()
+    try:
+        torch.manual_seed(1)
+        _, _, _, _, _, o1 = _run(g["cfg"])
+        _, _, _, _, _, o2 = _run(g["cfg"])
+        assert torch.isfinite(o1["pred_boxes"]).all() and torch.isfinite(o2["pred_sted"]).all()
+        assert (o1["pred_boxes"] - o2["pred_boxes"]).abs().max() > 1e-4            # stochastic
+        assert (o1["pred_boxes"] - out_eval["pred_boxes"]).abs().max() < 0.5       # same network
+        keep = b["keep"].cuda()
+        o = dict(o1, pred_boxes=o1["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in o1["aux_outputs"]])
+        losses = crit(o, [{"boxes": bx[None].cuda()} for bx in b["target_boxes"]], b["inter_idx"], b["time_mask"].cuda())
+        model.zero_grad()
+        sum(losses[k] * wd[k] for k in losses if k in wd).backward()
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                assert torch.isfinite(p.grad).all(), k
+    finally:
+        model.eval()
+    _, _, _, _, _, o3 = _run(g["cfg"])
+    assert torch.equal(o3["pred_boxes"], out_eval["pred_boxes"])

@@ -24,7 +24,10 @@ struct AttnParams {
   const uint8_t* kpm;  // [B][Lk] nonzero = masked key, may be null
   bf16* o;             // [B][Lq][H*32]
   long long ldo;
-  float* p;            // [B][H][Lq][Lk]
+  float* p;            // [B][H][Lq][Lk]  softmax probabilities BEFORE dropout (backward needs them)
+  float* pdrop;        // [B][H][Lq][Lk]  probabilities after dropout (= what torch returns / averages), null when no dropout
+  const uint8_t* keep; // [B][H][Lq][Lk]  1 = kept, null = no dropout (attention dropout, reference models/transformer.py:613)
+  float keep_scale;    // 1 / (1 - p_drop)
   int B, H, Lq, Lk;
   float scale;
 };
@@ -75,10 +78,21 @@ __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams 
     sum = warp_sum(sum);
     float inv = 1.f / sum;  // all keys masked -> NaN, exactly like the reference softmax
     __syncwarp();
-    float* pg = a.p + (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    const long long prow = (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    float* pg = a.p + prow;
+    for (int j = lane; j < a.Lk; j += 32) pg[j] = pw[j] * inv;
+    if (a.keep != nullptr) {           // P <- P * keep / (1 - p); the context uses the dropped probabilities
+      const uint8_t* kp = a.keep + prow;
+      float* pd = a.pdrop + prow;
+      for (int j = lane; j < a.Lk; j += 32) {
+        float e = kp[j] ? pw[j] * a.keep_scale : 0.f;
+        pw[j] = e;
+        pd[j] = e * inv;
+      }
+      __syncwarp();
+    }
     float acc = 0.f;
     for (int j = 0; j < a.Lk; ++j) acc += pw[j] * vs[j * HD + lane];
-    for (int j = lane; j < a.Lk; j += 32) pg[j] = pw[j] * inv;
     a.o[((long long)b * a.Lq + i) * a.ldo + h * HD + lane] = __float2bfloat16(acc * inv);
     __syncwarp();
   }
@@ -97,8 +111,11 @@ __global__ void head_mean_kernel(const float* __restrict__ p, float* __restrict_
 struct AttnBwdParams {
   const bf16 *q, *k, *v, *dout;
   long long ldq, ldk, ldv, lddo;
-  const float* p;      // [B][H][Lq][Lk]
-  const float* dpbar;  // [B][Lq][Lk] gradient of the head-mean probabilities, may be null
+  const float* p;      // [B][H][Lq][Lk] pre-dropout probabilities
+  const uint8_t* keep; // dropout keep mask or null
+  float keep_scale;
+  float* pd_scratch;   // [B][H][Lq][Lk] dropped probabilities for the dV pass (only with dropout)
+  const float* dpbar;  // [B][Lq][Lk] gradient of the head-mean (post-dropout) probabilities, may be null
   float* ds;           // [B][H][Lq][Lk] scratch: dS = P o (dP - rowsum(P o dP))
   bf16 *dq, *dk, *dv;  // same layout as q/k/v (strides lddq..)
   long long lddq, lddk, lddv;
@@ -129,6 +146,7 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
     float dod = __bfloat162float(a.dout[((long long)b * a.Lq + i) * a.lddo + h * HD + lane]);
     const float* pr = a.p + (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
     const float* dpb = a.dpbar ? a.dpbar + ((long long)b * a.Lq + i) * a.Lk : nullptr;
+    const uint8_t* kr = a.keep ? a.keep + (((long long)b * a.H + h) * a.Lq + i) * a.Lk : nullptr;
     float rs = 0.f;
     for (int j0 = 0; j0 < a.Lk; j0 += 32) {
       int j = j0 + lane;
@@ -140,6 +158,7 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
       }
       if (j < a.Lk) {
         if (dpb) dp += dpb[j] * invH;
+        if (kr) dp = kr[j] ? dp * a.keep_scale : 0.f;      // d(pre-dropout P) = d(post) * keep / (1 - p)
         float pj = pr[j];
         dw[j] = dp;
         rs += pj * dp;
@@ -147,11 +166,13 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
     }
     rs = warp_sum(rs);
     float* dsg = a.ds + (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    float* pdg = kr ? a.pd_scratch + (((long long)b * a.H + h) * a.Lq + i) * a.Lk : nullptr;
     for (int j = lane; j < a.Lk; j += 32) {
       float pj = pr[j];
       float d = pj > 0.f ? pj * (dw[j] - rs) : 0.f;  // masked keys have P = 0 exactly
       dw[j] = d;
       dsg[j] = d;
+      if (pdg) pdg[j] = kr[j] ? pj * a.keep_scale : 0.f;
     }
     __syncwarp();
     float acc = 0.f;
@@ -175,7 +196,7 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_col_kernel(const AttnBwd
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int j0 = blockIdx.y * kColKeys;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* pb = a.p + ((long long)b * a.H + h) * a.Lq * a.Lk;
+  const float* pb = (a.keep ? a.pd_scratch : a.p) + ((long long)b * a.H + h) * a.Lq * a.Lk;
   const float* dsb = a.ds + ((long long)b * a.H + h) * a.Lq * a.Lk;
   float av[8], ak[8];
 #pragma unroll
@@ -243,21 +264,22 @@ static int attn_init() {
 }
 
 extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                           const uint8_t* kpm, void* o, int64_t ldo, float* p, float* pbar, int B, int H, int Lq, int Lk,
-                           float scale, void* stream_) {
+                           const uint8_t* kpm, void* o, int64_t ldo, float* p, float* pbar, const uint8_t* keep, float* pdrop,
+                           float keep_scale, int B, int H, int Lq, int Lk, float scale, void* stream_) {
+  TDB_REQUIRE(!keep || pdrop, "tdb_mha_fwd: dropout needs the pdrop output");
   TDB_REQUIRE(q && k && v && o && p && B > 0 && H > 0 && Lq > 0 && Lk > 0, "tdb_mha_fwd: bad args");
   size_t smem = attn_smem_bytes(Lk, kAttnThreads);
   TDB_REQUIRE(smem <= 200 * 1024, "tdb_mha_fwd: Lk=%d too long for the single-CTA kernel", Lk);
   int rc = attn_init();
   if (rc) return rc;
-  AttnParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, kpm, (bf16*)o, ldo, p, B, H, Lq, Lk, scale};
+  AttnParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, kpm, (bf16*)o, ldo, p, pdrop, keep, keep_scale, B, H, Lq, Lk, scale};
   dim3 grid(B * H, attn_grid_y(B * H, Lq));
   mha_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream_>>>(a);
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   if (pbar) {
     long long LL = (long long)Lq * Lk;
-    head_mean_kernel<<<(unsigned)(((long long)B * LL + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(p, pbar, B, H, LL);
+    head_mean_kernel<<<(unsigned)(((long long)B * LL + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(keep ? pdrop : p, pbar, B, H, LL);
     TDB_CHECK_CUDA(cudaGetLastError());
     tdb_count_launch(1);
   }
@@ -265,7 +287,8 @@ extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
 }
 
 extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                           const void* dout, int64_t lddo, const float* p, const float* dpbar, float* ds_scratch, void* dq,
+                           const void* dout, int64_t lddo, const float* p, const uint8_t* keep, float keep_scale,
+                           float* pd_scratch, const float* dpbar, float* ds_scratch, void* dq,
                            int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk,
                            float scale, void* stream_) {
   TDB_REQUIRE(q && k && v && dout && p && ds_scratch && dq && dk && dv, "tdb_mha_bwd: null pointer");
@@ -273,8 +296,9 @@ extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
   TDB_REQUIRE(smem <= 200 * 1024, "tdb_mha_bwd: Lk=%d too long", Lk);
   int rc = attn_init();
   if (rc) return rc;
-  AttnBwdParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)dout, ldq, ldk, ldv, lddo, p, dpbar,
-                  ds_scratch, (bf16*)dq, (bf16*)dk, (bf16*)dv, lddq, lddk, lddv, B, H, Lq, Lk, scale};
+  TDB_REQUIRE(!keep || pd_scratch, "tdb_mha_bwd: dropout needs pd_scratch");
+  AttnBwdParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)dout, ldq, ldk, ldv, lddo, p, keep, keep_scale,
+                  pd_scratch, dpbar, ds_scratch, (bf16*)dq, (bf16*)dk, (bf16*)dv, lddq, lddk, lddv, B, H, Lq, Lk, scale};
   dim3 g1(B * H, attn_grid_y(B * H, Lq));
   mha_bwd_row_kernel<<<g1, kAttnThreads, smem, (cudaStream_t)stream_>>>(a);
   dim3 g2(B * H, (Lk + kColKeys - 1) / kColKeys);

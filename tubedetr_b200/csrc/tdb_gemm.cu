@@ -988,7 +988,12 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
     // otherwise the pipelined register path (3)
     const bool tma_res_ok = d->residual && d->remap == TDB_REMAP_NONE && splits == 1 && d->N % 128 == 0 &&
                             (d->block_n == 0 || d->block_n == 128);
-    const bool tma_out_ok = tma_res_ok && d->out_dtype == TDB_OUT_BF16 && nz == 1;
+    static int out_all = -1;
+    if (out_all < 0) { const char* e = getenv("TDB_TMA_OUT_ALL"); out_all = e ? atoi(e) : 0; }
+    // TMA-store epilogue also without a residual (short reductions only: it trades pipeline depth for the output tile)
+    const bool plain_ok = out_all && !d->residual && d->remap == TDB_REMAP_NONE && splits == 1 && d->N % 128 == 0 &&
+                          (d->block_n == 0 || d->block_n == 128) && (long long)d->K * d->ntaps <= 512 && d->M >= 4096;
+    const bool tma_out_ok = (tma_res_ok || plain_ok) && d->out_dtype == TDB_OUT_BF16 && nz == 1;
     if (epi_mode == 5 && !tma_out_ok) epi_mode = 4;
     if (epi_mode == 4 && !tma_res_ok) epi_mode = 3;
   }
@@ -1031,7 +1036,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : bn);
   if (rc) return rc;
   CUtensorMap tmR = tmA, tmO = tmA;   // only dereferenced in epilogue modes 4 / 5
-  if (p.epi_mode == 4 || p.epi_mode == 5) {
+  if ((p.epi_mode == 4 || p.epi_mode == 5) && d->residual) {
     rc = tdb_make_tmap_bf16(&tmR, d->residual, d->M, d->N, d->ldr, BM);
     if (rc) return rc;
   }

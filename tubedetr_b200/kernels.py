@@ -64,16 +64,18 @@ def colsum_bf16(x, out, accumulate=False):
     return out
 
 
-def mha_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale):
-    """q,k,v: 2-D bf16 views [B*L, >=H*32] (row stride = .stride(0)); kpm uint8 [B,Lk] or None."""
+def mha_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=None, pdrop=None, keep_scale=1.0):
+    """q,k,v: 2-D bf16 views [B*L, >=H*32] (row stride = .stride(0)); kpm uint8 [B,Lk] or None.
+    keep (uint8 [B,H,Lq,Lk]) + pdrop enable attention-probability dropout."""
     check(lib().tdb_mha_fwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(kpm),
-                            ptr(o), _i64(o.stride(0)), ptr(p), ptr(pbar), B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_fwd")
+                            ptr(o), _i64(o.stride(0)), ptr(p), ptr(pbar), ptr(keep), ptr(pdrop), _f(keep_scale),
+                            B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_fwd")
 
 
-def mha_bwd(q, k, v, dout, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale):
+def mha_bwd(q, k, v, dout, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, keep=None, keep_scale=1.0, pd_scratch=None):
     check(lib().tdb_mha_bwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)),
-                            ptr(dout), _i64(dout.stride(0)), ptr(p), ptr(dpbar), ptr(ds),
-                            ptr(dq), _i64(dq.stride(0)), ptr(dk), _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)),
+                            ptr(dout), _i64(dout.stride(0)), ptr(p), ptr(keep), _f(keep_scale), ptr(pd_scratch), ptr(dpbar),
+                            ptr(ds), ptr(dq), _i64(dq.stride(0)), ptr(dk), _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)),
                             B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_bwd")
 
 

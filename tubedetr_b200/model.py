@@ -11,7 +11,8 @@ Internals are NOT the reference's: activations are batch-major pixel/token rows 
 and linear layers run on the tcgen05 GEMM, attention / LayerNorm on the kernels of libtdb.so, and the per-clip Python
 loops of the reference (tubedetr.py:167-179, transformer.py:275-308, 400-417) are single gathers.
 Only the reference default path is implemented (temporal stride > 0, fast_mode "", sine embeddings); other flag values
-are rejected loudly in build().  Dropout is not applied yet (eval-mode numerics; DESIGN.md "open items").
+are rejected loudly in build().  In train() mode every dropout of the reference is applied (attention probabilities inside the
+attention kernel, residual / FFN / resizer / sted-head dropouts as torch ops); eval() is deterministic.
 """
 import math
 import zlib
@@ -188,16 +189,21 @@ class _Resizer(nn.Module):
 
 
 class _MLP(nn.Module):
-    def __init__(self, din, dh, dout, n):
+    """reference models/tubedetr.py:23-42 (dropout, when set, follows EVERY layer including the last one)"""
+
+    def __init__(self, din, dh, dout, n, dropout=0.0):
         super().__init__()
         h = [dh] * (n - 1)
         self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip([din] + h, h + [dout]))
+        self.dropout = dropout
 
     def forward(self, x):
         for i, l in enumerate(self.layers):
             x = l(x)
             if i < len(self.layers) - 1:
                 x = F.relu(x)
+            if self.dropout and self.training:
+                x = F.dropout(x, self.dropout, True)
         return x
 
 
@@ -235,8 +241,10 @@ def _make_text_encoder(name="roberta-base"):
 class Transformer(nn.Module):
     """Parameter container + the video-text encoder / space-time decoder drivers."""
 
-    def __init__(self, num_encoder_layers=6, num_decoder_layers=6, video_max_len=200, stride=5, no_tsa=False, fast=True):
+    def __init__(self, num_encoder_layers=6, num_decoder_layers=6, video_max_len=200, stride=5, no_tsa=False, fast=True,
+                 dropout=0.1):
         super().__init__()
+        self.dropout = dropout          # reference models/transformer.py:608-676 (attention, residual and FFN dropouts)
         self.encoder = _Stack(_EncLayer, num_encoder_layers, final_norm=False)
         self.decoder = _Stack(_DecLayer, num_decoder_layers, final_norm=True)
         self.time_embed = _TimeSine(video_max_len, D_MODEL)
@@ -256,52 +264,70 @@ class Transformer(nn.Module):
             nn.init.zeros_(self.fast_residual.bias)
 
     # ---- one post-norm encoder layer on token rows (reference transformer.py:629-646)
-    def _enc_layer(self, l, x32, xb, xpb, pos, kpm, n, S, need_pos):
-        a = l.self_attn
-        qk, v = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((0, 512), (512, 768)), xpb, xb)
-        o, _ = ops.mha(qk, None, v, kpm, n, NHEAD, S, S, 32 ** -0.5, packed=True)
-        att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
-        x32, xb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias)
+    def _drop(self):
+        return self.dropout if self.training else 0.0
+
+    def _ffn(self, l, xb, dp):
+        """linear2(dropout(relu(linear1(x)))) -> fp32.  Without dropout the ReLU backward rides in linear2's dgrad epilogue."""
+        if dp > 0:
+            hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True)
+            hdn = F.dropout(hdn, dp, True)
+            return F.dropout(ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True), dp, True)
         hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True, masked_by_consumer=True)
-        f = ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True, mask_dx=True)
+        return ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True, mask_dx=True)
+
+    def _enc_layer(self, l, x32, xb, xpb, pos, kpm, n, S, need_pos):
+        a, dp = l.self_attn, self._drop()
+        qk, v = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((0, 512), (512, 768)), xpb, xb)
+        o, _ = ops.mha(qk, None, v, kpm, n, NHEAD, S, S, 32 ** -0.5, packed=True, drop_p=dp)
+        att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
+        if dp > 0:
+            att = F.dropout(att, dp, True)
+        x32, xb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias)
+        f = self._ffn(l, xb, dp)
         if need_pos:
             return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias, pos)
         return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias) + (None,)
 
     # ---- one decoder layer (reference transformer.py:684-751); rows are (b,t) batch-major
     def _dec_layer(self, l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S):
-        a = l.self_attn
+        a, dp = l.self_attn, self._drop()
         if self.no_tsa:  # each time query attends to itself only (transformer.py:701-711)
             (v,) = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((512, 768),), xb)
+            if dp > 0:   # softmax over one key = 1, then attention dropout on that single probability
+                v = v * ((torch.rand(B * T, NHEAD, 1, device=v.device) >= dp).to(v.dtype) / (1 - dp)).expand(B * T, NHEAD, 32).reshape(B * T, 256)
             att = ops.linear(v, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
             w = torch.ones(B * T, 1, 1, dtype=torch.float32, device=x32.device)
         else:
             qk, v = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((0, 512), (512, 768)), xqb, xb)
-            o, w = ops.mha(qk, None, v, kpm_q, B, NHEAD, T, T, 32 ** -0.5, packed=True)
+            o, w = ops.mha(qk, None, v, kpm_q, B, NHEAD, T, T, 32 ** -0.5, packed=True, drop_p=dp)
             att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
+        if dp > 0:
+            att = F.dropout(att, dp, True)
         x32, xb, xqb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, qp)
         c = l.cross_attn_image
-        if self.fused_xattn and S >= 43:    # K/V projection fused into the attention kernel (K, V never reach HBM)
+        if self.fused_xattn and S >= 43 and dp == 0:    # K/V projection fused into the attention kernel (K, V never reach HBM)
             (q,) = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256),), xqb)
             o, cw = ops.xattn_fused(q, mempb, memb, c.in_proj_weight, c.in_proj_bias, kpm_mem, B * T, S, 32 ** -0.5)
         else:
             q, k, v = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256), (256, 512), (512, 768)), xqb, mempb, memb)
-            o, cw = ops.mha(q, k, v, kpm_mem, B * T, NHEAD, 1, S, 32 ** -0.5)
+            o, cw = ops.mha(q, k, v, kpm_mem, B * T, NHEAD, 1, S, 32 ** -0.5, drop_p=dp)
         att = ops.linear(o, c.out_proj.weight, c.out_proj.bias, out_fp32=True)
+        if dp > 0:
+            att = F.dropout(att, dp, True)
         x32, xb = ops.add_layernorm(x32, att, l.norm3.weight, l.norm3.bias)
-        hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True, masked_by_consumer=True)
-        f = ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True, mask_dx=True)
+        f = self._ffn(l, xb, dp)
         x32, xb, xqb = ops.add_layernorm(x32, f, l.norm4.weight, l.norm4.bias, qp)
         return x32, xb, xqb, w, cw
 
 
 class TubeDETR(nn.Module):
     def __init__(self, num_queries=1, aux_loss=True, video_max_len=200, stride=5, guided_attn=True, fast=True,
-                 fast_mode="", sted=True, no_tsa=False, enc_layers=6, dec_layers=6, train_backbone=True):
+                 fast_mode="", sted=True, no_tsa=False, enc_layers=6, dec_layers=6, train_backbone=True, dropout=0.1):
         super().__init__()
         assert num_queries == 1 and fast_mode == "" and stride > 0, "only the reference default path is implemented"
         self.num_queries = num_queries
-        self.transformer = Transformer(enc_layers, dec_layers, video_max_len, stride, no_tsa, fast)
+        self.transformer = Transformer(enc_layers, dec_layers, video_max_len, stride, no_tsa, fast, dropout)
         self.bbox_embed = _MLP(D_MODEL, D_MODEL, 4, 3)
         self.query_embed = nn.Embedding(num_queries, D_MODEL)
         self.input_proj = _Conv(2048, D_MODEL, 1, bias=True)
@@ -310,8 +336,7 @@ class TubeDETR(nn.Module):
         self.aux_loss, self.video_max_len, self.stride = aux_loss, video_max_len, stride
         self.guided_attn, self.fast, self.fast_mode, self.sted = guided_attn, fast, fast_mode, sted
         if sted:
-            self.sted_embed = _MLP(D_MODEL, D_MODEL, 2, 2)
-            self.sted_embed.dropout = 0.5  # reference applies Dropout(0.5) here in train mode (not applied yet)
+            self.sted_embed = _MLP(D_MODEL, D_MODEL, 2, 2, dropout=0.5)   # reference models/tubedetr.py:91
         self._engine = ResNet101Engine()
         self.text_autocast = False  # True: RoBERTa (library call) runs its GEMMs under bf16 autocast (bench.py sets it)
 
@@ -413,6 +438,8 @@ class TubeDETR(nn.Module):
         L = hid.shape[1]
         r = ops.linear(hid.float().reshape(B * L, 768).to(torch.bfloat16), tr.resizer.fc.weight, tr.resizer.fc.bias, out_fp32=True)
         txt, _ = ops.add_layernorm(r, None, tr.resizer.layer_norm.weight, tr.resizer.layer_norm.bias, eps=1e-12)
+        if self.training:
+            txt = F.dropout(txt, 0.1, True)                     # FeatureResizer dropout (reference transformer.py:141,772)
         txt = txt.view(B, L, D_MODEL)
         txt_kpm = am.ne(1)
         txt_rep = txt.repeat_interleave(n_clips, 0)                                      # (n,L,d)
@@ -591,7 +618,7 @@ def build(args):
     model = TubeDETR(num_queries=args.num_queries, aux_loss=args.aux_loss, video_max_len=args.video_max_len_train,
                      stride=args.stride, guided_attn=args.guided_attn, fast=args.fast, fast_mode=args.fast_mode,
                      sted=args.sted, no_tsa=args.no_tsa, enc_layers=args.enc_layers, dec_layers=args.dec_layers,
-                     train_backbone=args.lr_backbone > 0)
+                     train_backbone=args.lr_backbone > 0, dropout=getattr(args, "dropout", 0.1))
     if getattr(args, "freeze_backbone", False):
         for p in model.backbone.parameters():
             p.requires_grad_(False)

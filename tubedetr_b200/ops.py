@@ -137,10 +137,11 @@ def in_proj(W, b, segs, *xs):
 
 class MHAFn(torch.autograd.Function):
     """Attention core on projected q/k/v (bf16 [B*L, 256]); returns (o bf16 [B*Lq,256], pbar fp32 [B,Lq,Lk]).
-    qk_packed: q and k are the two halves of one [R,512] tensor (self-attention)."""
+    packed: q and k are the two halves of one [R,512] tensor (self-attention).  drop_p > 0 applies torch's
+    attention-probability dropout (mask drawn with torch.rand, applied inside the kernel; pbar averages the dropped P)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, kpm, B, H, Lq, Lk, scale, packed):
+    def forward(ctx, q, k, v, kpm, B, H, Lq, Lk, scale, packed, drop_p):
         if packed:
             qv, kv = q[:, :256], q[:, 256:]
         else:
@@ -148,15 +149,19 @@ class MHAFn(torch.autograd.Function):
         o = torch.empty(B * Lq, H * 32, dtype=torch.bfloat16, device=q.device)
         p = torch.empty(B, H, Lq, Lk, dtype=torch.float32, device=q.device)
         pbar = torch.empty(B, Lq, Lk, dtype=torch.float32, device=q.device)
-        K.mha_fwd(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale)
-        ctx.cfg = (B, H, Lq, Lk, scale, packed)
-        ctx.save_for_backward(q, k if not packed else None, v, p)
+        keep = pdrop = None
+        if drop_p > 0:
+            keep = (torch.rand(B, H, Lq, Lk, device=q.device) >= drop_p).to(torch.uint8)
+            pdrop = torch.empty_like(p)
+        K.mha_fwd(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pdrop, keep_scale=1.0 / (1.0 - drop_p))
+        ctx.cfg = (B, H, Lq, Lk, scale, packed, drop_p)
+        ctx.save_for_backward(q, k if not packed else None, v, p, keep)
         return o, pbar
 
     @staticmethod
     def backward(ctx, do, dpbar):
-        q, k, v, p = ctx.saved_tensors
-        B, H, Lq, Lk, scale, packed = ctx.cfg
+        q, k, v, p, keep = ctx.saved_tensors
+        B, H, Lq, Lk, scale, packed, drop_p = ctx.cfg
         if do is None:
             do = torch.zeros(B * Lq, H * 32, dtype=torch.bfloat16, device=q.device)
         do = _as_bf16(do).contiguous()
@@ -164,17 +169,18 @@ class MHAFn(torch.autograd.Function):
             dpbar = dpbar.contiguous().float()
         ds = torch.empty_like(p)
         dv = torch.empty_like(v)
+        kw = dict(keep=keep, keep_scale=1.0 / (1.0 - drop_p), pd_scratch=torch.empty_like(p) if keep is not None else None)
         if packed:
             dqk = torch.empty_like(q)
-            K.mha_bwd(q[:, :256], q[:, 256:], v, do, p, dpbar, ds, dqk[:, :256], dqk[:, 256:], dv, B, H, Lq, Lk, scale)
-            return dqk, None, dv, None, None, None, None, None, None, None
+            K.mha_bwd(q[:, :256], q[:, 256:], v, do, p, dpbar, ds, dqk[:, :256], dqk[:, 256:], dv, B, H, Lq, Lk, scale, **kw)
+            return (dqk, None, dv) + (None,) * 8
         dq, dk = torch.empty_like(q), torch.empty_like(k)
-        K.mha_bwd(q, k, v, do, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale)
-        return dq, dk, dv, None, None, None, None, None, None, None
+        K.mha_bwd(q, k, v, do, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, **kw)
+        return (dq, dk, dv) + (None,) * 8
 
 
-def mha(q, k, v, kpm, B, H, Lq, Lk, scale, packed=False):
-    return MHAFn.apply(q, k, v, kpm, B, H, Lq, Lk, scale, packed)
+def mha(q, k, v, kpm, B, H, Lq, Lk, scale, packed=False, drop_p=0.0):
+    return MHAFn.apply(q, k, v, kpm, B, H, Lq, Lk, scale, packed, float(drop_p))
 
 
 class XAttnFusedFn(torch.autograd.Function):
