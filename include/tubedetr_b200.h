@@ -148,9 +148,11 @@ int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
  * S must be >= 43 (a 128-row tile may touch at most 4 frames).
  * ------------------------------------------------------------------------------------------------ */
 int64_t tdb_xattn_workspace_bytes(int F, int S);
+/* keep [F][8][S] (1 = kept) + keep_scale = 1/(1-p): attention dropout (train mode); p stays pre-dropout, pbar averages
+ * the dropped probabilities.  keep == NULL disables it. */
 int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, const void* wkv, const float* bv,
-                        const uint8_t* kpm, void* o, float* p, float* pbar, void* workspace, int64_t ws_bytes, int F, int S,
-                        float scale, void* stream);
+                        const uint8_t* kpm, const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar,
+                        void* workspace, int64_t ws_bytes, int F, int S, float scale, void* stream);
 
 #ifdef __cplusplus
 }

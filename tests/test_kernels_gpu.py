@@ -199,6 +199,15 @@ def test_xattn_fused_matches_unfused_math(F, S):
     _close(pbar, rp.mean(1), 2e-2)
     _close(o.view(F, 1, d), ro, 2e-2)
     assert torch.isfinite(o.float()).all()
+    # attention dropout inside the fused kernel: same probabilities, context and head-mean use the dropped ones
+    pdrop = 0.1
+    keep = (torch.rand(F, H, 1, S, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)) >= pdrop).to(torch.uint8)
+    K.xattn_fused_fwd(q, mempb, memb, W[d:], b[2 * d:], kpm, o, p, pbar, F, S, scale, keep=keep, keep_scale=1 / (1 - pdrop))
+    rpd = rp * keep.float() / (1 - pdrop)
+    vh = vv.view(F, S, H, 32).transpose(1, 2)
+    _close(p, rp, 2e-2)
+    _close(pbar, rpd.mean(1), 2e-2)
+    _close(o.view(F, 1, d), (rpd @ vh).transpose(1, 2).reshape(F, 1, d), 2e-2)
 
 
 def test_mha_attention_dropout_fwd_bwd():

@@ -989,7 +989,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
     const bool tma_res_ok = d->residual && d->remap == TDB_REMAP_NONE && splits == 1 && d->N % 128 == 0 &&
                             (d->block_n == 0 || d->block_n == 128);
     static int out_all = -1;
-    if (out_all < 0) { const char* e = getenv("TDB_TMA_OUT_ALL"); out_all = e ? atoi(e) : 0; }
+    if (out_all < 0) { const char* e = getenv("TDB_TMA_OUT_ALL"); out_all = e ? atoi(e) : 1; }
     // TMA-store epilogue also without a residual (short reductions only: it trades pipeline depth for the output tile)
     const bool plain_ok = out_all && !d->residual && d->remap == TDB_REMAP_NONE && splits == 1 && d->N % 128 == 0 &&
                           (d->block_n == 0 || d->block_n == 128) && (long long)d->K * d->ntaps <= 512 && d->M >= 4096;

@@ -45,6 +45,8 @@ constexpr int XSMEM_BYTES = XSTAGES * XSTAGE_BYTES + 1024 + (int)sizeof(XattnSme
 struct XattnParams {
   const bf16* q;        // [F][256] projected queries (bias included), unscaled
   const uint8_t* kpm;   // [F][S] nonzero = padded key
+  const uint8_t* keep;  // [F][8][S] attention-dropout keep mask (train mode) or null
+  float keep_scale;     // 1 / (1 - p_drop)
   float* p;             // [F][8][S]  out: exp(s - m_tile) (normalised later by the merge kernel)
   float* part_m;        // [tiles][XMAXF][8]
   float* part_l;        // [tiles][XMAXF][8]
@@ -211,6 +213,10 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     if (valid) {
 #pragma unroll
       for (int h = 0; h < XH; ++h) p.p[((long long)f * XH + h) * p.S + tok] = pt[h];
+      if (p.keep != nullptr) {      // dropout acts on the probabilities that weight V; the softmax sum keeps all of them
+#pragma unroll
+        for (int h = 0; h < XH; ++h) pt[h] = p.keep[((long long)f * XH + h) * p.S + tok] ? pt[h] * p.keep_scale : 0.f;
+      }
     }
     // ---- partial context from the V accumulator: o[ff][h*32+d] += sum_j pt[j,h] V[j,h,d]
     mbar_wait(&sh.vfull, 0, 14);
@@ -267,7 +273,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 __global__ void __launch_bounds__(256) xattn_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
                                                           const float* __restrict__ part_o, const float* __restrict__ bv,
                                                           float* __restrict__ p, float* __restrict__ pbar, bf16* __restrict__ o,
-                                                          int S, int F) {
+                                                          const uint8_t* __restrict__ keep, float keep_scale, int S, int F) {
   __shared__ float Ms[XH], Ls[XH];
   __shared__ float fac[4][XH];       // exp(m_t - M) per segment
   const int f = blockIdx.x;
@@ -297,18 +303,28 @@ __global__ void __launch_bounds__(256) xattn_merge_kernel(const float* __restric
     acc += part_o[((long long)t * XMAXF + ff) * XD + h * 32 + d] * fac[t - t0][h];
   }
   const float invL = 1.f / Ls[h];
-  o[(long long)f * XD + h * 32 + d] = __float2bfloat16(acc * invL + (bv ? bv[h * 32 + d] : 0.f));
+  float sd = 0.f;      // sum over tokens of the (dropped) probabilities of this head: 1 without dropout
   for (int tok = d; tok < S; tok += 32) {
     int t = (f * S + tok) / XBM;
     long long idx = ((long long)f * XH + h) * S + tok;
-    p[idx] = p[idx] * fac[t - t0][h] * invL;
+    float pn = p[idx] * fac[t - t0][h] * invL;
+    p[idx] = pn;
+    if (keep) sd += keep[idx] ? pn * keep_scale : 0.f;
   }
+  sd = keep ? warp_sum(sd) : 1.f;
+  // context: sum_j p_j (V_j + bv) = (sum_j p_j V_j) + bv * sum_j p_j
+  o[(long long)f * XD + h * 32 + d] = __float2bfloat16(acc * invL + (bv ? bv[h * 32 + d] * sd : 0.f));
   __syncthreads();
   if (pbar) {
     for (int tok = threadIdx.x; tok < S; tok += blockDim.x) {
       float sacc = 0.f;
 #pragma unroll
-      for (int hh = 0; hh < XH; ++hh) sacc += p[((long long)f * XH + hh) * S + tok];
+      for (int hh = 0; hh < XH; ++hh) {
+        const long long idx = ((long long)f * XH + hh) * S + tok;
+        float pv = p[idx];
+        if (keep) pv = keep[idx] ? pv * keep_scale : 0.f;      // the returned weights are the dropped probabilities
+        sacc += pv;
+      }
       pbar[(long long)f * S + tok] = sacc * (1.f / XH);
     }
   }
@@ -324,8 +340,8 @@ extern "C" int64_t tdb_xattn_workspace_bytes(int F, int S) {
 }
 
 extern "C" int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, const void* wkv, const float* bv,
-                                   const uint8_t* kpm, void* o, float* p, float* pbar, void* workspace, int64_t ws_bytes,
-                                   int F, int S, float scale, void* stream_) {
+                                   const uint8_t* kpm, const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar,
+                                   void* workspace, int64_t ws_bytes, int F, int S, float scale, void* stream_) {
   int rc = tdb_init_once();
   if (rc) return rc;
   TDB_REQUIRE(q && mempb && memb && wkv && o && p && workspace && F > 0, "tdb_xattn_fused_fwd: null argument");
@@ -345,6 +361,8 @@ extern "C" int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void*
   XattnParams prm;
   prm.q = (const bf16*)q;
   prm.kpm = kpm;
+  prm.keep = keep;
+  prm.keep_scale = keep_scale;
   prm.p = p;
   float* ws = (float*)workspace;
   prm.part_m = ws;
@@ -357,7 +375,7 @@ extern "C" int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void*
   cudaStream_t st = (cudaStream_t)stream_;
   xattn_fused_kernel<<<tiles, XTHREADS, XSMEM_BYTES, st>>>(tmK, tmV, tmW, prm);
   TDB_CHECK_CUDA(cudaGetLastError());
-  xattn_merge_kernel<<<F, 256, 0, st>>>(prm.part_m, prm.part_l, prm.part_o, bv, p, pbar, (bf16*)o, S, F);
+  xattn_merge_kernel<<<F, 256, 0, st>>>(prm.part_m, prm.part_l, prm.part_o, bv, p, pbar, (bf16*)o, keep, keep_scale, S, F);
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(2);
   return TDB_OK;

@@ -79,9 +79,9 @@ def mha_bwd(q, k, v, dout, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, keep=N
                             B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_bwd")
 
 
-def xattn_fused_fwd(q, mempb, memb, wkv, bv, kpm, o, p, pbar, F, S, scale):
+def xattn_fused_fwd(q, mempb, memb, wkv, bv, kpm, o, p, pbar, F, S, scale, keep=None, keep_scale=1.0):
     lib().tdb_xattn_workspace_bytes.restype = C.c_int64
     nbytes = int(lib().tdb_xattn_workspace_bytes(F, S))
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device)
-    check(lib().tdb_xattn_fused_fwd(ptr(q), ptr(mempb), ptr(memb), ptr(wkv), ptr(bv), ptr(kpm), ptr(o), ptr(p), ptr(pbar),
+    check(lib().tdb_xattn_fused_fwd(ptr(q), ptr(mempb), ptr(memb), ptr(wkv), ptr(bv), ptr(kpm), ptr(keep), _f(keep_scale), ptr(o), ptr(p), ptr(pbar),
                                     ptr(ws), _i64(nbytes), F, S, _f(scale), stream_ptr()), "xattn_fused_fwd")

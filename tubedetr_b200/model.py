@@ -306,9 +306,9 @@ class Transformer(nn.Module):
             att = F.dropout(att, dp, True)
         x32, xb, xqb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, qp)
         c = l.cross_attn_image
-        if self.fused_xattn and S >= 43 and dp == 0:    # K/V projection fused into the attention kernel (K, V never reach HBM)
+        if self.fused_xattn and S >= 43:                # K/V projection fused into the attention kernel (K, V never reach HBM)
             (q,) = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256),), xqb)
-            o, cw = ops.xattn_fused(q, mempb, memb, c.in_proj_weight, c.in_proj_bias, kpm_mem, B * T, S, 32 ** -0.5)
+            o, cw = ops.xattn_fused(q, mempb, memb, c.in_proj_weight, c.in_proj_bias, kpm_mem, B * T, S, 32 ** -0.5, drop_p=dp)
         else:
             q, k, v = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256), (256, 512), (512, 768)), xqb, mempb, memb)
             o, cw = ops.mha(q, k, v, kpm_mem, B * T, NHEAD, 1, S, 32 ** -0.5, drop_p=dp)

@@ -189,20 +189,22 @@ class XAttnFusedFn(torch.autograd.Function):
     Returns (o bf16 [F,256], pbar fp32 [F,1,S]).  Backward re-projects K/V with tdb_gemm (they were never stored)."""
 
     @staticmethod
-    def forward(ctx, q, mempb, memb, W, b, kpm, F, S, scale):
+    def forward(ctx, q, mempb, memb, W, b, kpm, F, S, scale, drop_p):
         Wb = bf16_weight(W)
         o = torch.empty(F, 256, dtype=torch.bfloat16, device=q.device)
         p = torch.empty(F, 8, 1, S, dtype=torch.float32, device=q.device)
         pbar = torch.empty(F, 1, S, dtype=torch.float32, device=q.device)
-        K.xattn_fused_fwd(q, mempb, memb, Wb[256:768], b[512:768], kpm, o, p, pbar, F, S, scale)
-        ctx.cfg = (F, S, scale)
-        ctx.save_for_backward(q, mempb, memb, W, b, p)
+        keep = (torch.rand(F, 8, 1, S, device=q.device) >= drop_p).to(torch.uint8) if drop_p > 0 else None
+        K.xattn_fused_fwd(q, mempb, memb, Wb[256:768], b[512:768], kpm, o, p, pbar, F, S, scale, keep=keep,
+                          keep_scale=1.0 / (1.0 - drop_p))
+        ctx.cfg = (F, S, scale, drop_p)
+        ctx.save_for_backward(q, mempb, memb, W, b, p, keep)
         return o, pbar
 
     @staticmethod
     def backward(ctx, do, dpbar):
-        q, mempb, memb, W, b, p = ctx.saved_tensors
-        F, S, scale = ctx.cfg
+        q, mempb, memb, W, b, p, keep = ctx.saved_tensors
+        F, S, scale, drop_p = ctx.cfg
         Wb = bf16_weight(W)
         R = F * S
         kp = torch.empty(R, 256, dtype=torch.bfloat16, device=q.device)
@@ -215,7 +217,8 @@ class XAttnFusedFn(torch.autograd.Function):
         dpbar = dpbar.contiguous().float() if dpbar is not None else None
         ds = torch.empty_like(p)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(kp), torch.empty_like(vp)
-        K.mha_bwd(q, kp, vp, do, p, dpbar, ds, dq, dk, dv, F, 8, 1, S, scale)
+        K.mha_bwd(q, kp, vp, do, p, dpbar, ds, dq, dk, dv, F, 8, 1, S, scale, keep=keep, keep_scale=1.0 / (1.0 - drop_p),
+                  pd_scratch=torch.empty_like(p) if keep is not None else None)
         dW = torch.zeros_like(W) if ctx.needs_input_grad[3] else None
         db = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device) if ctx.needs_input_grad[4] else None
         if dW is not None:
@@ -231,11 +234,11 @@ class XAttnFusedFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dmb = torch.empty_like(memb)
             gemm(dv, Wb[512:768], dmb, R, 256, 256, b_major=1)
-        return dq, dmp, dmb, dW, db, None, None, None, None
+        return dq, dmp, dmb, dW, db, None, None, None, None, None
 
 
-def xattn_fused(q, mempb, memb, W, b, kpm, F, S, scale):
-    return XAttnFusedFn.apply(q, mempb, memb, W, b, kpm, F, S, scale)
+def xattn_fused(q, mempb, memb, W, b, kpm, F, S, scale, drop_p=0.0):
+    return XAttnFusedFn.apply(q, mempb, memb, W, b, kpm, F, S, scale, float(drop_p))
 
 
 class AddLayerNormFn(torch.autograd.Function):
