@@ -134,6 +134,7 @@ def build_everything(device, seed=0):
     # RoBERTa stays the library call it is in the reference; let its fp32 GEMMs use TF32 tensor cores (bf16 autocast would
     # re-cast ~200 weight tensors every step: ~500 extra tiny kernels for a 20-token sequence)
     torch.backends.cuda.matmul.allow_tf32 = True
+    model.fast_l2_chunk = int(os.environ.get("TDB_L2_CHUNK", "0")) or None
     torch.backends.cudnn.allow_tf32 = True
     return model.to(device).train(), crit, wd     # a real training step: every dropout of the reference is active
 
@@ -273,9 +274,15 @@ def kernel_probe(device, pk):
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * N * h * w * C * 9 * C           # algorithmic (un-haloed) conv FLOPs per launch
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "tdb_gemm_kernel<256> (layer3 3x3 conv, implicit GEMM, 100 frames)", "achieved": ach,
-            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None,
-            "peak_source": pk["src"] + " cuBLAS bf16 burst", "ms_per_launch": ms, "flops_per_launch": flops}
+    traffic, tsrc = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_gemm2_traffic.json")   # dram read+write bytes of this launch from ncu --set full
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        traffic, tsrc = t["dram_bytes_per_launch"], t["source"]
+    return {"bound": "tensor", "kernel": "tdb_gemm2_kernel (layer3 3x3 conv as implicit GEMM, cta_group::2, 100 frames)",
+            "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
+            "traffic_source": tsrc, "peak_source": pk["src"] + " cuBLAS bf16 burst", "ms_per_launch": ms,
+            "flops_per_launch": flops, "algorithmic_bytes_per_launch": 2 * (Rp * C + C * 9 * C + N * h * w * C)}
 
 
 def run_ours(args):

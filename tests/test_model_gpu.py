@@ -169,3 +169,18 @@ def test_train_mode_applies_dropout_and_backpropagates():
         model.eval()
     _, _, _, _, _, o3 = _run(g["cfg"])
     assert torch.equal(o3["pred_boxes"], out_eval["pred_boxes"])
+
+
+def test_l2_chunked_fast_pass_is_equivalent():
+    """the L2-resident chunked schedule of stem+layer1+layer2 (no-grad pass) gives the same features as one big batch"""
+    g = load_gold("cfg1")
+    model, *_ = _model(g["cfg"])
+    b = batch_for(g["cfg"])
+    frames = b["frames_fast"].cuda()
+    with torch.no_grad():
+        W = model._engine.prepare(model._backbone_tensors())
+        f0, h, w, _ = model._engine.forward(frames, W, save=False, tag="eq0")
+        f0 = f0.clone()
+        f1, h1, w1, _ = model._engine.forward(frames, W, save=False, tag="eq1", l2_chunk=3)
+    assert (h, w) == (h1, w1) and f0.shape == f1.shape
+    assert (f0.float() - f1.float()).abs().max().item() <= 1e-2 * f0.float().abs().max().item()

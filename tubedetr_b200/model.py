@@ -338,6 +338,7 @@ class TubeDETR(nn.Module):
         if sted:
             self.sted_embed = _MLP(D_MODEL, D_MODEL, 2, 2, dropout=0.5)   # reference models/tubedetr.py:91
         self._engine = ResNet101Engine()
+        self.fast_l2_chunk = None   # frames per chunk for the L2-resident schedule of stem+layer1+layer2 in the no-grad pass
         self.text_autocast = False  # True: RoBERTa (library call) runs its GEMMs under bf16 autocast (bench.py sets it)
 
     # ------------------------------------------------------------------ helpers
@@ -411,7 +412,7 @@ class TubeDETR(nn.Module):
         if self.fast:
             ff, fm_ = samples_fast.decompose()
             with torch.no_grad():
-                feat_f, hf, wf, _ = self._engine.forward(ff.float(), W, save=False, tag="fast")
+                feat_f, hf, wf, _ = self._engine.forward(ff.float(), W, save=False, tag="fast", l2_chunk=self.fast_l2_chunk)
                 m_f = self._resize_mask(fm_, hf, wf)
             fsrc_all = ops.linear(feat_f, Win, bin_).view(-1, HW, D_MODEL)       # input_proj gets weight-grad here too
             ragged = any(d != T for d in durations)

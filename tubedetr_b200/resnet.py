@@ -85,10 +85,29 @@ class ResNet101Engine:
         return W
 
     # ------------------------------------------------------------------ forward
-    def forward(self, frames, W, save, tag):
-        """frames fp32 [N,3,H,W] cuda.  Returns (feat rows bf16 [N*h*w, 2048], h, w, ctx or None)."""
+    def forward(self, frames, W, save, tag, l2_chunk=None):
+        """frames fp32 [N,3,H,W] cuda.  Returns (feat rows bf16 [N*h*w, 2048], h, w, ctx or None).
+
+        l2_chunk (no-grad pass only): run stem + layer1 + layer2 -- the HBM-bound, high-resolution part -- over chunks of that
+        many frames with per-chunk buffers that are reused by every chunk, so the intermediate activations of a chunk
+        (~8 MB/frame at res 352) live in the 126 MB L2 instead of streaming through HBM; layer3/4 then run on the whole batch."""
         N, _, H, Wd = frames.shape
         frames = frames.contiguous()
+        if l2_chunk and not save and N > l2_chunk:
+            big, h2, w2 = None, 0, 0
+            for n0 in range(0, N, l2_chunk):
+                n = min(l2_chunk, N - n0)
+                x, h2, w2, _ = self._stages(self._stem(frames[n0:n0 + n], W, f"{tag}c{n}"), n, W, False, f"{tag}c{n}", 1, 2,
+                                            H, Wd, out_into=(big, n0, N))
+                big = x if big is None else big
+            x, h, w, ctx = self._stages((big, h2, w2), N, W, False, tag, 3, 4, H, Wd)
+        else:
+            x, h, w, ctx = self._stages(self._stem(frames, W, tag), N, W, save, tag, 1, 4, H, Wd)
+        self.last_hw = (h, w)
+        return x, h, w, ctx
+
+    def _stem(self, frames, W, tag):
+        N, _, H, Wd = frames.shape
         H1, W1 = conv_out(H, 7, 2, 3), conv_out(Wd, 7, 2, 3)
         H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
         wb, _, sc, sh = W["conv1"]
@@ -101,10 +120,17 @@ class ResNet101Engine:
             gemm(col, wb, stem[n0 * H1 * W1:(n0 + n) * H1 * W1], n * H1 * W1, 64, 192, scale=sc, bias=sh, relu=True)
         x = self.buf(tag + ":pool", (N * H2 * W2, 64))
         K.maxpool3x3s2(stem, x, N, H1, W1, 64)
+        return x, H2, W2
 
+    def _stages(self, xhw, N, W, save, tag, li_lo, li_hi, H, Wd, out_into=None):
+        """bottleneck stages li_lo..li_hi on pixel rows x [N*h*w, C].  out_into=(big, n0, Ntot): the last block writes its
+        rows into rows [n0*ho*wo, ...) of a full-batch buffer (allocated on first use) instead of a private one."""
+        x, h, w = xhw
         ctx = {"N": N, "blocks": [], "tag": tag} if save else None
-        h, w = H2, W2
+        big = None
         for li, (width, nb, stride0) in enumerate(STAGES, start=1):
+            if li < li_lo or li > li_hi:
+                continue
             for bi in range(nb):
                 name = f"layer{li}.{bi}."
                 stride = stride0 if bi == 0 else 1
@@ -147,14 +173,22 @@ class ResNet101Engine:
                     rec["xs"] = xs
                 else:
                     idt = x
-                # ping-pong the block output so the no-grad pass needs two buffers per stage
-                out = self.buf(f"{btag}out{0 if keep else bi % 2}", (Ro, cout))
+                last = out_into is not None and li == li_hi and bi == nb - 1
+                if last:
+                    big, n0, ntot = out_into
+                    if big is None:
+                        big = self.buf(f"{tag}:big{li}", (ntot * ho * wo, cout))
+                    out = big[n0 * ho * wo:(n0 + N) * ho * wo]
+                else:
+                    # ping-pong the block output so the no-grad pass needs two buffers per stage
+                    out = self.buf(f"{btag}out{0 if keep else bi % 2}", (Ro, cout))
                 gemm(y2, w3, out, Ro, cout, width, scale=s3, bias=b3, residual=idt, relu=True)
                 rec.update(y1=y1, y2=y2, out=out)
                 if keep:
                     ctx["blocks"].append(rec)
                 x, h, w = out, ho, wo
-        self.last_hw = (h, w)
+        if big is not None:
+            x = big
         return x, h, w, ctx
 
     # ------------------------------------------------------------------ backward
