@@ -68,7 +68,8 @@ typedef struct tdb_gemm_desc {
   int32_t remap, img_h, img_w;
   /* tuning: 0 = auto */
   int32_t block_n; int32_t max_ctas;
-  /* bring-up only: bit0 swaps LBO/SBO of MN-major operand descriptors */
+  /* bring-up only: bit0 swaps LBO/SBO of MN-major operand descriptors; bits1-3 epilogue variant + 1; bit4 no stores;
+     bit6 force the 2-CTA kernel; bit7 disable its halo mode; bit8 set a descriptor base offset in halo mode (wrong on purpose) */
   int32_t debug_flags;
 } tdb_gemm_desc;
 

@@ -184,3 +184,31 @@ def test_l2_chunked_fast_pass_is_equivalent():
         f1, h1, w1, _ = model._engine.forward(frames, W, save=False, tag="eq1", l2_chunk=3)
     assert (h, w) == (h1, w1) and f0.shape == f1.shape
     assert (f0.float() - f1.float()).abs().max().item() <= 1e-2 * f0.float().abs().max().item()
+
+
+def test_joint_backbone_batch_equals_two_passes():
+    """slow (with grad) + fast (no grad) frames as ONE backbone batch give the outputs and the backbone weight gradients of
+    the reference's two separate backbone calls (models/tubedetr.py:120-131): rows of a GEMM are independent."""
+    from tubedetr_b200 import NestedTensor
+    g = load_gold("cfg1")
+    cfg = g["cfg"]
+    model, crit, wd = _model(cfg)
+    b = batch_for(cfg)
+    samples = NestedTensor(b["frames_slow"].cuda(), b["mask_slow"].cuda())
+    fast = NestedTensor(b["frames_fast"].cuda(), b["mask_fast"].cuda())
+    caps = (b["input_ids"].cuda(), b["attention_mask"].cuda())
+    res = {}
+    for joint in (True, False):
+        model.joint_backbone = joint
+        model.zero_grad(set_to_none=True)
+        mc = model(samples, cfg["durations"], caps, encode_and_save=True, samples_fast=fast)
+        out = model(samples, cfg["durations"], caps, encode_and_save=False, memory_cache=mc)
+        (out["pred_boxes"].float().square().sum() + out["pred_sted"].float().square().sum()).backward()
+        gr = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None and "backbone" in n}
+        res[joint] = (out["pred_boxes"].detach().clone(), out["pred_sted"].detach().clone(), gr)
+    model.joint_backbone = True
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    assert res[True][2].keys() == res[False][2].keys() and len(res[True][2]) > 50
+    for n in res[True][2]:
+        a, c = res[True][2][n], res[False][2][n]
+        assert (a - c).abs().max().item() <= 1e-5 * (c.abs().max().item() + 1e-12), n

@@ -122,6 +122,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// The start-address field is the only part of a descriptor that changes inside a main loop: build the constant high part
+// once (umma_smem_desc(0, lbo, sbo)) and add (byte address >> 4) per MMA -- one integer add instead of ~10 ALU ops on the
+// single issuing thread, whose instruction rate, not the tensor pipe, bounds narrow tiles (profiles/r01_ncu_narrow_conv.txt).
+__device__ __forceinline__ uint64_t umma_desc_at(uint64_t desc_hi, uint32_t saddr) { return desc_hi | (uint64_t)((saddr >> 4) & 0x3FFF); }
+// one lane of a fully active warp (the same lane every time); lets the surrounding loop stay warp-uniform so that descriptors
+// and barrier addresses live in uniform registers instead of being broadcast from a divergent lane before every MMA
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B, fp32 D.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                         // D format f32

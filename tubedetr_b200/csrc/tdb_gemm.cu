@@ -49,6 +49,9 @@ struct GemmKParams {
   int remap, img_h, img_w;
   int debug_flags;
   int epi_mode;
+  // halo mode (see tdb_gemm2.cu): one row-haloed A tile per k-block serves all taps; B either streams through a ring of
+  // BN x 64 stages or, when every (tap, k-block) slice fits next to the A tiles, is loaded once and stays resident
+  int halo, a_min_off, a_box_rows, a_nbox, a_tile_bytes, na_stages, nb_stages, b_resident;
 };
 
 template <int BN, int EPI = 0>
@@ -61,7 +64,7 @@ struct GemmCfg {
   static constexpr int kOperandSlots = (EPI == 4) ? 2 : (EPI == 5 ? 3 : 0);
   static constexpr int kOperandBytes = kOperandSlots * BM * BN * 2;
   static constexpr int kStagingBytes = (EPI == 5) ? 1024 : 4 * 32 * 64 * 4;  // per epilogue warp 32 x 64 fp32 (mode 5: shared scale/bias)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOperandBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOperandBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kStagingBytes;
 };
 
 struct WorkItem {
@@ -106,7 +109,9 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
   uint64_t* ofull_bar = tempty_bar + 2;             // [3] residual tile landed (modes 4, 5)
   uint64_t* oempty_bar = ofull_bar + 3;             // [3] residual / output tile free again
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oempty_bar + 3);
+  uint64_t* afull_bar = oempty_bar + 3;             // [4] halo mode: row-haloed A tile landed
+  uint64_t* aempty_bar = afull_bar + 4;             // [4] ... and consumed by all taps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +133,10 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&ofull_bar[s], 1);
       mbar_init(&oempty_bar[s], EPI == 5 ? 1 : 4);
     }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&afull_bar[s], 1);
+      mbar_init(&aempty_bar[s], 1);
+    }
     if (EPI == 5) tma_prefetch_desc(&tmO);
     fence_barrier_init();
   }
@@ -147,6 +156,62 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int oslot = 0;
       uint32_t ophase = 0;
+      if (EPI == 3 && p.halo) {
+        uint8_t* bring = smem + p.na_stages * p.a_tile_bytes;
+        constexpr int kBStage = BN * 128;
+        int sa = 0;
+        uint32_t pa = 0;
+        bool first = true;
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+          const WorkItem wi = decode_work(p, w, BN);
+          if (p.b_resident && first) {       // all (k-block, tap) weight slices once; they stay for every tile of this CTA
+            first = false;
+            mbar_expect_tx(&full_bar[0], p.kb_per_tap * p.ntaps * kBStage);
+            for (int kk = 0; kk < p.kb_per_tap; ++kk)
+              for (int tap = 0; tap < p.ntaps; ++tap) {
+                uint8_t* sB = bring + (kk * p.ntaps + tap) * kBStage;
+                if (p.b_major == 0) {
+                  tma_load_2d(sB, &tmB, &full_bar[0], kk * BK + p.b_off0[tap], wi.n0 + p.b_off1[tap]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < BN / 64; ++j)
+                    tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[0], wi.n0 + j * 64 + p.b_off0[tap], kk * BK + p.b_off1[tap]);
+                }
+              }
+          }
+          for (int kk = 0; kk < p.kb_per_tap; ++kk) {
+            mbar_wait(&aempty_bar[sa], pa ^ 1, 9);
+            mbar_expect_tx(&afull_bar[sa], p.a_tile_bytes);
+            uint8_t* sA = smem + sa * p.a_tile_bytes;
+            for (int j = 0; j < p.a_nbox; ++j)
+              tma_load_2d(sA + j * p.a_box_rows * 128, &tmA, &afull_bar[sa], kk * BK + p.a_off0[0],
+                          wi.m0 + p.a_min_off + j * p.a_box_rows);
+            if (++sa == p.na_stages) {
+              sa = 0;
+              pa ^= 1;
+            }
+            if (!p.b_resident) {
+              for (int tap = 0; tap < p.ntaps; ++tap) {
+                mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                mbar_expect_tx(&full_bar[stage], kBStage);
+                uint8_t* sB = bring + stage * kBStage;
+                if (p.b_major == 0) {
+                  tma_load_2d(sB, &tmB, &full_bar[stage], kk * BK + p.b_off0[tap], wi.n0 + p.b_off1[tap]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < BN / 64; ++j)
+                    tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], wi.n0 + j * 64 + p.b_off0[tap],
+                                kk * BK + p.b_off1[tap]);
+                }
+                if (++stage == p.nb_stages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         const WorkItem wi = decode_work(p, w, BN);
         if constexpr (EPI == 5) {
@@ -213,16 +278,74 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) loop; one elected lane issues tcgen05.mma / tcgen05.commit.
+    {
       const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_major, p.b_major);
-      const uint32_t a_kstep = p.a_major ? 2048u : 32u;
-      const uint32_t b_kstep = p.b_major ? 2048u : 32u;
+      const uint32_t a_k16 = (p.a_major ? 2048u : 32u) >> 4;      // descriptor address units (16 B) per K step of 16
+      const uint32_t b_k16 = (p.b_major ? 2048u : 32u) >> 4;
       const uint32_t a_lbo = p.a_major ? (uint32_t)kChunkBytes : 16u;
       const uint32_t b_lbo = p.b_major ? (uint32_t)kChunkBytes : 16u;
+      const uint64_t a_hi = (p.a_major && (p.debug_flags & 1)) ? umma_smem_desc(0, 1024, a_lbo) : umma_smem_desc(0, a_lbo, 1024);
+      const uint64_t b_hi = (p.b_major && (p.debug_flags & 1)) ? umma_smem_desc(0, 1024, b_lbo) : umma_smem_desc(0, b_lbo, 1024);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (EPI == 3 && p.halo) {
+        const uint32_t bring = smem_base + p.na_stages * p.a_tile_bytes;
+        constexpr uint32_t kBStage = BN * 128;
+        int sa = 0;
+        uint32_t pa = 0;
+        bool first = true;
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          if (p.b_resident && first) {
+            first = false;
+            mbar_wait(&full_bar[0], 0, 3);
+          }
+          for (int kk = 0; kk < p.kb_per_tap; ++kk) {
+            mbar_wait(&afull_bar[sa], pa, 10);
+            const uint32_t a_tile = smem_base + sa * p.a_tile_bytes;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              uint32_t b_base;
+              if (p.b_resident) {
+                b_base = bring + (uint32_t)(kk * p.ntaps + tap) * kBStage;
+              } else {
+                mbar_wait(&full_bar[stage], phase, 3);
+                b_base = bring + stage * kBStage;
+              }
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t ad = umma_desc_at(a_hi, a_tile + (uint32_t)(p.a_off1[tap] - p.a_min_off) * 128u);
+                const uint64_t bd = umma_desc_at(b_hi, b_base);
+#pragma unroll
+                for (int s = 0; s < BK / 16; ++s)
+                  umma_bf16(d_tmem, ad + s * 2u, bd + s * b_k16, idesc, (kk > 0 || tap > 0 || s > 0) ? 1u : 0u);
+                if (!p.b_resident) umma_commit(&empty_bar[stage]);
+              }
+              __syncwarp();
+              if (!p.b_resident && ++stage == p.nb_stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            if (elect_one()) umma_commit(&aempty_bar[sa]);
+            __syncwarp();
+            if (++sa == p.na_stages) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+          if (elect_one()) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      } else
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         const WorkItem wi = decode_work(p, w, BN);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
@@ -231,23 +354,22 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int it = 0; it < wi.iters; ++it) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_base = a_base + BM * BK * 2;
+          if (elect_one()) {
+            const uint32_t a_base = smem_base + stage * Cfg::kStageBytes;
+            const uint64_t ad = umma_desc_at(a_hi, a_base);
+            const uint64_t bd = umma_desc_at(b_hi, a_base + BM * BK * 2);
 #pragma unroll
-          for (int s = 0; s < BK / 16; ++s) {
-            const uint64_t adesc = (p.a_major && (p.debug_flags & 1)) ? umma_smem_desc(a_base + s * a_kstep, 1024, a_lbo)
-                                                                      : umma_smem_desc(a_base + s * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = (p.b_major && (p.debug_flags & 1)) ? umma_smem_desc(b_base + s * b_kstep, 1024, b_lbo)
-                                                                      : umma_smem_desc(b_base + s * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (it > 0 || s > 0) ? 1u : 0u);
+            for (int s = 0; s < BK / 16; ++s) umma_bf16(d_tmem, ad + s * a_k16, bd + s * b_k16, idesc, (it > 0 || s > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -257,7 +379,7 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int wq = warp & 3;
-    float* stage = reinterpret_cast<float*>(after + 256) + (EPI == 5 ? 0 : wq * (32 * 64));
+    float* stage = reinterpret_cast<float*>(after + 512) + (EPI == 5 ? 0 : wq * (32 * 64));
     int oslot = 0;
     uint32_t ophase = 0;
     int tiles_done = 0;
@@ -1030,8 +1152,57 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
     if (r2 == 1) return TDB_OK;
   }
 
+  // halo mode of the implicit 3x3 convolution (K-major A, taps = row shifts): pipelined-register epilogue (3) only
+  int a_box = BM;
+  {
+    static int halo_ok = -1;
+    if (halo_ok < 0) { const char* e = getenv("TDB_GEMM_HALO"); halo_ok = e ? atoi(e) : 1; }
+    if (halo_ok && !((d->debug_flags >> 7) & 1) && p.epi_mode == 3 && p.a_major == 0 && d->ntaps > 1 && splits == 1 && nz == 1) {
+      int lo = d->a_off1[0], hi = d->a_off1[0];
+      bool same_cols = true;
+      for (int i = 1; i < d->ntaps; ++i) {
+        lo = d->a_off1[i] < lo ? d->a_off1[i] : lo;
+        hi = d->a_off1[i] > hi ? d->a_off1[i] : hi;
+        same_cols = same_cols && d->a_off0[i] == d->a_off0[0];
+      }
+      const int rows = BM + hi - lo;
+      const int nbox = (rows + 255) / 256;
+      const int box_rows = (((rows + nbox - 1) / nbox) + 7) & ~7;
+      const int tile_bytes = nbox * box_rows * 128;
+      const int ring = (bn == 256 ? 4 * 49152 : (bn == 128 ? 6 * 32768 : 8 * 24576));   // GemmCfg<bn,3>::kStages * kStageBytes
+      const int bstage = bn * 128;
+      const int max_stages = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
+      // the weights stay resident when every (k-block, tap) slice fits next to two A tiles; the A ring then takes the rest.
+      // Otherwise: as many A tiles in flight as leave >= 4 weight stages (A tiles are what hides the load latency: the next
+      // tile's rows can only be requested once a buffer is free)
+      static int na_env = -1;
+      if (na_env < 0) { const char* e = getenv("TDB_HALO_A_STAGES"); na_env = e ? atoi(e) : 0; }
+      const int slices = kb * d->ntaps;
+      const bool resident = p.n_tiles == 1 && slices * bstage + 2 * tile_bytes <= ring && slices * bstage < (1 << 20);
+      int na, nb;
+      if (resident) {
+        nb = slices;
+        na = (ring - slices * bstage) / tile_bytes;
+      } else {
+        na = (ring - 4 * bstage) / tile_bytes;
+        if (na > 3) na = 3;
+        if (na < 2) na = 2;
+        nb = (ring - na * tile_bytes) / bstage;
+      }
+      if (na > 4) na = 4;
+      if (na_env >= 2 && na_env <= na) na = na_env;
+      if (!resident) nb = (ring - na * tile_bytes) / bstage;
+      if (same_cols && nb >= 3 && na >= 2) {
+        p.halo = 1; p.a_min_off = lo; p.a_box_rows = box_rows; p.a_nbox = nbox; p.a_tile_bytes = tile_bytes;
+        p.na_stages = na;
+        p.nb_stages = nb > max_stages ? max_stages : nb;
+        p.b_resident = resident ? 1 : 0;
+        a_box = box_rows;
+      }
+    }
+  }
   CUtensorMap tmA, tmB;
-  rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, p.a_major ? 64 : BM);
+  rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, p.a_major ? 64 : a_box);
   if (rc) return rc;
   rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : bn);
   if (rc) return rc;
@@ -1089,7 +1260,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   const int g = (d->max_ctas > 0 && d->max_ctas < g_num_sms) ? d->max_ctas : g_num_sms;
   static int tail_split = -1;
   if (tail_split < 0) { const char* e = getenv("TDB_TAIL_SPLIT"); tail_split = e ? atoi(e) : 0; }  // measured: no gain (r01), off
-  if (tail_split && splits == 1 && nz == 1 && bn > 64 && p.total_work > g && d->block_n == 0) {
+  if (tail_split && !p.halo && splits == 1 && nz == 1 && bn > 64 && p.total_work > g && d->block_n == 0) {
     const int full = (p.total_work / g) * g;
     const int rem = p.total_work - full;
     const int m_main = full / p.n_tiles;                 // whole M tiles covered by the full waves

@@ -22,6 +22,15 @@ constexpr int G2_STAGE_BYTES = 128 * 64 * 2 * 2;   // A 16 KB + half of B 16 KB
 constexpr int G2_STAGES = 6;
 constexpr int G2_THREADS = 256;
 constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 1024 + 256 + 4 * 2048;
+// halo mode (implicit 3x3 convolution with a K-major A operand): the 9 taps of one k-block are row-shifted views of the SAME
+// pixel rows, so A is loaded ONCE per k-block as rows [m0 + min_off, m0 + 127 + max_off] (128-byte swizzled, 128 B per row) and
+// each tap's MMA descriptor starts `a_off1[tap] - min_off` rows into that tile.  The 128-byte swizzle is a function of the
+// absolute shared-memory address (measured: a start address that is not 1024-byte aligned needs NO descriptor base offset --
+// setting one gives wrong products; tools/halo_diag.py), so a row-shifted start address reads exactly the shifted rows.  Per k-block a CTA then pulls ~1.4 x 16 KB of A instead of 9 x 16 KB through the L2 -> SM crossbar,
+// which is what bounds this kernel (profiles/r01_ncu_gemm_final.txt).  A ring: 2 tiles; B ring: up to 8 x 16 KB.
+constexpr int G2_HALO_A_STAGES = 2;
+constexpr int G2_HALO_B_MAX = 8;
+constexpr int G2_RING_BYTES = G2_STAGES * G2_STAGE_BYTES;
 
 struct Gemm2Params {
   int M, N;
@@ -42,6 +51,8 @@ struct Gemm2Params {
   int out_f32;
   long long ldo;
   int remap, img_h, img_w;
+  // halo mode
+  int halo, a_min_off, a_box_rows, a_nbox, a_tile_bytes, nb_stages, use_base_offset;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -122,11 +133,13 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* after = smem + G2_STAGES * G2_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);
-  uint64_t* empty_bar = full_bar + G2_STAGES;
-  uint64_t* tfull_bar = empty_bar + G2_STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);          // [8] (halo mode: B ring)
+  uint64_t* empty_bar = full_bar + G2_HALO_B_MAX;
+  uint64_t* tfull_bar = empty_bar + G2_HALO_B_MAX;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* afull_bar = tempty_bar + 2;                              // [2] halo mode: A tile ring
+  uint64_t* aempty_bar = afull_bar + G2_HALO_A_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + G2_HALO_A_STAGES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -136,9 +149,13 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < G2_STAGES; ++s) {
+    for (int s = 0; s < G2_HALO_B_MAX; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < G2_HALO_A_STAGES; ++s) {
+      mbar_init(&afull_bar[s], 1);
+      mbar_init(&aempty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -160,6 +177,44 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.halo) {
+        uint8_t* bring = smem + G2_HALO_A_STAGES * p.a_tile_bytes;
+        int sa = 0;
+        uint32_t pa = 0;
+        for (int w = pair; w < p.total_work; w += npairs) {
+          const Work2 wi = decode2(p, w);
+          const int m0 = wi.mt * 256 + (int)rank * 128;
+          const int nb = wi.nt * G2_BN + (int)rank * 128;
+          for (int kk = 0; kk < p.kb_per_tap; ++kk) {
+            mbar_wait(&aempty_bar[sa], pa ^ 1, 25);
+            if (rank == 0) mbar_expect_tx(&afull_bar[sa], 2 * p.a_tile_bytes);
+            uint8_t* sA = smem + sa * p.a_tile_bytes;
+            for (int j = 0; j < p.a_nbox; ++j)
+              tma_load_2d_2sm(sA + j * p.a_box_rows * 128, &tmA, &afull_bar[sa], kk * 64 + p.a_off0[0],
+                              m0 + p.a_min_off + j * p.a_box_rows);
+            if (++sa == G2_HALO_A_STAGES) {
+              sa = 0;
+              pa ^= 1;
+            }
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              mbar_wait(&empty_bar[stage], phase ^ 1, 21);
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * 128 * 64 * 2);
+              uint8_t* sB = bring + stage * (128 * 64 * 2);
+              if (p.b_major == 0) {
+                tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kk * 64 + p.b_off0[tap], nb + p.b_off1[tap]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[stage], nb + j * 64 + p.b_off0[tap], kk * 64 + p.b_off1[tap]);
+              }
+              if (++stage == p.nb_stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      } else
       for (int w = pair; w < p.total_work; w += npairs) {
         const Work2 wi = decode2(p, w);
         const int m0 = wi.mt * 256 + (int)rank * 128;
@@ -200,16 +255,62 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    // leader CTA only; the whole warp runs the warp-uniform loop, one elected lane issues tcgen05.mma / tcgen05.commit
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(256, G2_BN, p.a_major, p.b_major);
-      const uint32_t a_kstep = p.a_major ? 2048u : 32u;
-      const uint32_t a_lbo = p.a_major ? 8192u : 16u;
-      const uint32_t b_kstep = p.b_major ? 2048u : 32u;
-      const uint32_t b_lbo = p.b_major ? 8192u : 16u;
+      const uint32_t a_k16 = (p.a_major ? 2048u : 32u) >> 4;
+      const uint32_t b_k16 = (p.b_major ? 2048u : 32u) >> 4;
+      const uint64_t a_hi = umma_smem_desc(0, p.a_major ? 8192u : 16u, 1024);
+      const uint64_t b_hi = umma_smem_desc(0, p.b_major ? 8192u : 16u, 1024);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.halo) {
+        const uint32_t bring = smem_base + G2_HALO_A_STAGES * p.a_tile_bytes;
+        int sa = 0;
+        uint32_t pa = 0;
+        for (int w = pair; w < p.total_work; w += npairs) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
+          const uint32_t d_tmem = tmem_base + acc * G2_BN;
+          for (int kk = 0; kk < p.kb_per_tap; ++kk) {
+            mbar_wait(&afull_bar[sa], pa, 26);
+            const uint32_t a_tile = smem_base + sa * p.a_tile_bytes;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              mbar_wait(&full_bar[stage], phase, 23);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a_base = a_tile + (uint32_t)(p.a_off1[tap] - p.a_min_off) * 128u;
+                const uint64_t boff = p.use_base_offset ? ((uint64_t)((a_base >> 7) & 7u) << 49) : 0ull;   // bring-up probe only
+                const uint64_t ad = umma_desc_at(a_hi, a_base) | boff;
+                const uint64_t bd = umma_desc_at(b_hi, bring + stage * (128 * 64 * 2));
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                  umma2_bf16(d_tmem, ad + s * 2u, bd + s * b_k16, idesc, (kk > 0 || tap > 0 || s > 0) ? 1u : 0u);
+                umma2_commit_mc(&empty_bar[stage]);
+              }
+              __syncwarp();
+              if (++stage == p.nb_stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            if (elect_one()) umma2_commit_mc(&aempty_bar[sa]);
+            __syncwarp();
+            if (++sa == G2_HALO_A_STAGES) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+          if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
+          __syncwarp();
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      } else
       for (int w = pair; w < p.total_work; w += npairs) {
         const int iters = decode2(p, w).iters;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 22);
@@ -218,19 +319,22 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full_bar[stage], phase, 23);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * G2_STAGE_BYTES);
-          const uint32_t b_base = a_base + 128 * 64 * 2;
+          if (elect_one()) {
+            const uint32_t a_base = smem_base + stage * G2_STAGE_BYTES;
+            const uint64_t ad = umma_desc_at(a_hi, a_base);
+            const uint64_t bd = umma_desc_at(b_hi, a_base + 128 * 64 * 2);
 #pragma unroll
-          for (int s = 0; s < 4; ++s)
-            umma2_bf16(d_tmem, umma_smem_desc(a_base + s * a_kstep, a_lbo, 1024), umma_smem_desc(b_base + s * b_kstep, b_lbo, 1024),
-                       idesc, (it > 0 || s > 0) ? 1u : 0u);
-          umma2_commit_mc(&empty_bar[stage]);
+            for (int s = 0; s < 4; ++s) umma2_bf16(d_tmem, ad + s * a_k16, bd + s * b_k16, idesc, (it > 0 || s > 0) ? 1u : 0u);
+            umma2_commit_mc(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == G2_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma2_commit_mc(&tfull_bar[acc]);
+        if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -439,8 +543,32 @@ int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
   p.mask = (const bf16*)d->mask; p.ldmask = d->ldmask;
   p.relu = d->relu; p.out = d->out; p.out_f32 = d->out_dtype == TDB_OUT_F32; p.ldo = d->ldo;
   p.remap = d->remap; p.img_h = d->img_h; p.img_w = d->img_w;
+  // halo mode: K-major A whose taps differ only by a row shift (implicit 3x3 convolution over the zero-haloed pixel grid)
+  static int halo_ok = -1;
+  if (halo_ok < 0) { const char* e = getenv("TDB_GEMM2_HALO"); halo_ok = e ? atoi(e) : 1; }
+  int a_box = 128;
+  if (halo_ok && !((d->debug_flags >> 7) & 1) && p.a_major == 0 && d->ntaps > 1 && splits == 1 && nz == 1) {
+    int lo = d->a_off1[0], hi = d->a_off1[0];
+    bool same_cols = true;
+    for (int i = 1; i < d->ntaps; ++i) {
+      lo = d->a_off1[i] < lo ? d->a_off1[i] : lo;
+      hi = d->a_off1[i] > hi ? d->a_off1[i] : hi;
+      same_cols = same_cols && d->a_off0[i] == d->a_off0[0];
+    }
+    const int rows = 128 + hi - lo;
+    const int nbox = (rows + 255) / 256;
+    const int box_rows = (((rows + nbox - 1) / nbox) + 7) & ~7;
+    const int tile_bytes = nbox * box_rows * 128;
+    const int nb = (G2_RING_BYTES - G2_HALO_A_STAGES * tile_bytes) / (128 * 64 * 2);
+    if (same_cols && nb >= 4) {
+      p.halo = 1; p.a_min_off = lo; p.a_box_rows = box_rows; p.a_nbox = nbox; p.a_tile_bytes = tile_bytes;
+      p.nb_stages = nb > G2_HALO_B_MAX ? G2_HALO_B_MAX : nb;
+      p.use_base_offset = (d->debug_flags >> 8) & 1;
+      a_box = box_rows;
+    }
+  }
   CUtensorMap tmA, tmB;
-  int rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, p.a_major ? 64 : 128);
+  int rc = tdb_make_tmap_bf16(&tmA, d->A, d->a_rows, d->a_cols, d->lda, p.a_major ? 64 : a_box);
   if (rc) return rc;
   rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : 128);
   if (rc) return rc;

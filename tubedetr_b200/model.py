@@ -338,6 +338,7 @@ class TubeDETR(nn.Module):
         if sted:
             self.sted_embed = _MLP(D_MODEL, D_MODEL, 2, 2, dropout=0.5)   # reference models/tubedetr.py:91
         self._engine = ResNet101Engine()
+        self.joint_backbone = True  # slow + fast frames share one backbone batch when their spatial sizes agree
         self.fast_l2_chunk = None   # frames per chunk for the L2-resident schedule of stem+layer1+layer2 in the no-grad pass
         self.text_autocast = False  # True: RoBERTa (library call) runs its GEMMs under bf16 autocast (bench.py sets it)
 
@@ -393,7 +394,19 @@ class TubeDETR(nn.Module):
         sd = self._backbone_tensors()
         W = self._engine.prepare(sd)
         names = [n for n, p in sd.items() if isinstance(p, nn.Parameter) and p.requires_grad]
-        if names and torch.is_grad_enabled():
+        feat_f = None
+        joint = (self.fast and self.joint_backbone and samples_fast is not None
+                 and samples_fast.tensors.shape[2:] == frames.shape[2:])
+        if joint:      # slow + fast frames as one backbone batch (same launches, better SM fill); fast rows carry no grad
+            ffr = samples_fast.tensors.float()
+            if names and torch.is_grad_enabled():
+                feat, feat_f = ops.BackboneJointFn.apply(frames.float(), ffr, self._engine, W, names, "joint",
+                                                         *[sd[n] for n in names])
+                h, w = self._engine.last_hw
+            else:
+                fa, h, w, _ = self._engine.forward([frames.float(), ffr], W, save=False, tag="joint")
+                feat, feat_f = fa[:frames.shape[0] * h * w], fa[frames.shape[0] * h * w:]
+        elif names and torch.is_grad_enabled():
             feat = ops.BackboneFn.apply(frames.float(), self._engine, W, names, "slow", *[sd[n] for n in names])
             h, w = self._engine.last_hw
         else:
@@ -412,7 +425,11 @@ class TubeDETR(nn.Module):
         if self.fast:
             ff, fm_ = samples_fast.decompose()
             with torch.no_grad():
-                feat_f, hf, wf, _ = self._engine.forward(ff.float(), W, save=False, tag="fast", l2_chunk=self.fast_l2_chunk)
+                if feat_f is None:
+                    feat_f, hf, wf, _ = self._engine.forward(ff.float(), W, save=False, tag="fast",
+                                                             l2_chunk=self.fast_l2_chunk)
+                else:
+                    hf, wf = h, w
                 m_f = self._resize_mask(fm_, hf, wf)
             fsrc_all = ops.linear(feat_f, Win, bin_).view(-1, HW, D_MODEL)       # input_proj gets weight-grad here too
             ragged = any(d != T for d in durations)

@@ -290,6 +290,30 @@ def add_layernorm(x, r, gamma, beta, pos=None, eps=1e-5):
     return AddLayerNormFn.apply(x, r, gamma, beta, pos, eps)
 
 
+class BackboneJointFn(torch.autograd.Function):
+    """Slow (with grad) and fast (no grad) frames through the backbone as ONE batch (reference models/tubedetr.py:120-131
+    runs them as two calls; the fast call is under no_grad).  Returns (feat_slow, feat_fast); only feat_slow is
+    differentiable, and backward runs on the slow frames' row prefix of the saved activations."""
+
+    @staticmethod
+    def forward(ctx, frames, frames_fast, engine, W, names, tag, *params):
+        ns = frames.shape[0]
+        feat, h, w, bctx = engine.forward([frames, frames_fast], W, save=True, tag=tag, n_keep=ns)
+        fs, ff = feat[:ns * h * w], feat[ns * h * w:]
+        ctx.engine, ctx.W, ctx.names, ctx.bctx = engine, W, names, bctx
+        ctx.save_for_backward(fs, *params)
+        ctx.mark_non_differentiable(ff)
+        return fs, ff
+
+    @staticmethod
+    def backward(ctx, g, _g_fast):
+        feat, *params = ctx.saved_tensors
+        g = (_as_bf16(g) * (feat > 0)).contiguous()
+        grads = {n: torch.empty_like(p, dtype=torch.float32) for n, p in zip(ctx.names, params)}
+        ctx.engine.backward(ctx.bctx, ctx.W, g, grads)
+        return (None, None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
 class BackboneFn(torch.autograd.Function):
     """ResNet-101 layer4 features WITH grad for layer2-4 conv weights (reference models/backbone.py:82-89)."""
 

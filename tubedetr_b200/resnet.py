@@ -85,48 +85,63 @@ class ResNet101Engine:
         return W
 
     # ------------------------------------------------------------------ forward
-    def forward(self, frames, W, save, tag, l2_chunk=None):
-        """frames fp32 [N,3,H,W] cuda.  Returns (feat rows bf16 [N*h*w, 2048], h, w, ctx or None).
+    def forward(self, frames, W, save, tag, l2_chunk=None, n_keep=None):
+        """frames fp32 [N,3,H,W] cuda, or a LIST of such tensors that is processed as ONE batch (concatenated along N without
+        a copy: the stem gathers each source into one row buffer).  Returns (feat rows bf16 [N*h*w, 2048], h, w, ctx or None).
+
+        n_keep (with save): only the first n_keep frames are differentiated -- ctx records row-prefix views of the saved
+        activations, so backward() runs on n_keep frames.  This is how the slow (with grad) and fast (no grad) passes of
+        reference models/tubedetr.py:120-131 share one launch sequence: 125 frames per GEMM instead of 25 + 100 fills the
+        148 SMs better (wave quantisation) and halves the launch count; per-frame results are bit-identical.
 
         l2_chunk (no-grad pass only): run stem + layer1 + layer2 -- the HBM-bound, high-resolution part -- over chunks of that
         many frames with per-chunk buffers that are reused by every chunk, so the intermediate activations of a chunk
         (~8 MB/frame at res 352) live in the 126 MB L2 instead of streaming through HBM; layer3/4 then run on the whole batch."""
-        N, _, H, Wd = frames.shape
-        frames = frames.contiguous()
-        if l2_chunk and not save and N > l2_chunk:
+        srcs = [f.contiguous() for f in (frames if isinstance(frames, (list, tuple)) else [frames])]
+        _, _, H, Wd = srcs[0].shape
+        N = sum(f.shape[0] for f in srcs)
+        if l2_chunk and not save and N > l2_chunk and len(srcs) == 1:
+            frames = srcs[0]
             big, h2, w2 = None, 0, 0
             for n0 in range(0, N, l2_chunk):
                 n = min(l2_chunk, N - n0)
-                x, h2, w2, _ = self._stages(self._stem(frames[n0:n0 + n], W, f"{tag}c{n}"), n, W, False, f"{tag}c{n}", 1, 2,
+                x, h2, w2, _ = self._stages(self._stem([frames[n0:n0 + n]], W, f"{tag}c{n}"), n, W, False, f"{tag}c{n}", 1, 2,
                                             H, Wd, out_into=(big, n0, N))
                 big = x if big is None else big
             x, h, w, ctx = self._stages((big, h2, w2), N, W, False, tag, 3, 4, H, Wd)
         else:
-            x, h, w, ctx = self._stages(self._stem(frames, W, tag), N, W, save, tag, 1, 4, H, Wd)
+            x, h, w, ctx = self._stages(self._stem(srcs, W, tag), N, W, save, tag, 1, 4, H, Wd, n_keep=n_keep)
         self.last_hw = (h, w)
         return x, h, w, ctx
 
-    def _stem(self, frames, W, tag):
-        N, _, H, Wd = frames.shape
+    def _stem(self, srcs, W, tag):
+        _, _, H, Wd = srcs[0].shape
+        N = sum(f.shape[0] for f in srcs)
         H1, W1 = conv_out(H, 7, 2, 3), conv_out(Wd, 7, 2, 3)
         H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
         wb, _, sc, sh = W["conv1"]
         stem = self.buf(tag + ":stem", (N * H1 * W1, 64))
         chunk = max(1, min(N, (1 << 28) // (H1 * W1 * 192 * 2)))
         col = self.buf(tag + ":stemcol", (chunk * H1 * W1, 192))
-        for n0 in range(0, N, chunk):
-            n = min(chunk, N - n0)
-            K.stem_im2col(frames[n0:n0 + n], col, n, H, Wd)
-            gemm(col, wb, stem[n0 * H1 * W1:(n0 + n) * H1 * W1], n * H1 * W1, 64, 192, scale=sc, bias=sh, relu=True)
+        base = 0
+        for frames in srcs:
+            assert frames.shape[2:] == (H, Wd), "frames of one backbone batch must share their spatial size"
+            for n0 in range(0, frames.shape[0], chunk):
+                n = min(chunk, frames.shape[0] - n0)
+                K.stem_im2col(frames[n0:n0 + n], col, n, H, Wd)
+                gemm(col, wb, stem[(base + n0) * H1 * W1:(base + n0 + n) * H1 * W1], n * H1 * W1, 64, 192, scale=sc, bias=sh,
+                     relu=True)
+            base += frames.shape[0]
         x = self.buf(tag + ":pool", (N * H2 * W2, 64))
         K.maxpool3x3s2(stem, x, N, H1, W1, 64)
         return x, H2, W2
 
-    def _stages(self, xhw, N, W, save, tag, li_lo, li_hi, H, Wd, out_into=None):
+    def _stages(self, xhw, N, W, save, tag, li_lo, li_hi, H, Wd, out_into=None, n_keep=None):
         """bottleneck stages li_lo..li_hi on pixel rows x [N*h*w, C].  out_into=(big, n0, Ntot): the last block writes its
         rows into rows [n0*ho*wo, ...) of a full-batch buffer (allocated on first use) instead of a private one."""
         x, h, w = xhw
-        ctx = {"N": N, "blocks": [], "tag": tag} if save else None
+        nk = N if n_keep is None else n_keep
+        ctx = {"N": nk, "blocks": [], "tag": tag} if save else None
         big = None
         for li, (width, nb, stride0) in enumerate(STAGES, start=1):
             if li < li_lo or li > li_hi:
@@ -185,6 +200,12 @@ class ResNet101Engine:
                 gemm(y2, w3, out, Ro, cout, width, scale=s3, bias=b3, residual=idt, relu=True)
                 rec.update(y1=y1, y2=y2, out=out)
                 if keep:
+                    if nk != N:      # differentiate the first nk frames only: row-prefix views of every saved activation
+                        pre = {"x": nk * h * w, "y1": nk * (h + 2) * (w + 2) if stride == 1 else nk * h * w, "y2": nk * ho * wo,
+                               "out": nk * ho * wo, "col": nk * ho * wo, "xs": nk * ho * wo}
+                        for key, rows in pre.items():
+                            if key in rec:
+                                rec[key] = rec[key][:rows]
                     ctx["blocks"].append(rec)
                 x, h, w = out, ho, wo
         if big is not None:
