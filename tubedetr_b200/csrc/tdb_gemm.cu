@@ -1,8 +1,8 @@
 // tubedetr_b200 -- the tcgen05 / TMEM / TMA GEMM behind every convolution and linear layer (sm_100a).
 //
 // Persistent, warp-specialised, cta_group::1, tile 128 x BN x 64 (BN in {64,128,256}):
-//   warp 0   : TMA producer (one elected lane)   global -> 128B-swizzled smem ring, mbarrier complete_tx
-//   warp 1   : MMA issuer   (one elected lane)   tcgen05.mma kind::f16 bf16 x bf16 -> fp32 in TMEM, tcgen05.commit
+//   warp 0   : TMA producer (warp-uniform loop, one elected lane issues)   global -> 128B-swizzled smem ring, mbarrier complete_tx
+//   warp 1   : MMA issuer   (same scheme)         tcgen05.mma kind::f16 bf16 x bf16 -> fp32 in TMEM, tcgen05.commit
 //   warp 2   : TMEM allocator / deallocator      2 x BN columns = double-buffered accumulator
 //   warps 4-7: epilogue                          tcgen05.ld -> scale/bias/residual/ReLU/mask -> row-remapped global stores
 // The accumulator double buffer lets the epilogue of tile i overlap the main loop of tile i+1.
@@ -100,7 +100,9 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ GemmKParams p) {
   using Cfg = GemmCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET on the __shared__ pointer: an integer round trip would turn every access below into a
+  // generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* opnd = smem + Cfg::kStages * Cfg::kStageBytes;     // [2][BN/64][128 rows][128 B] residual tiles (mode 4), 1024-aligned
   uint8_t* after = opnd + Cfg::kOperandBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);
@@ -151,7 +153,9 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the warp-uniform loop (coordinates and barrier addresses stay in uniform registers); one elected
+    // lane arms the mbarrier and issues the bulk-tensor copies.  No per-stage division: taps and k-blocks are nested loops.
+    {
       int stage = 0;
       uint32_t phase = 0;
       int oslot = 0;
@@ -166,26 +170,32 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const WorkItem wi = decode_work(p, w, BN);
           if (p.b_resident && first) {       // all (k-block, tap) weight slices once; they stay for every tile of this CTA
             first = false;
-            mbar_expect_tx(&full_bar[0], p.kb_per_tap * p.ntaps * kBStage);
-            for (int kk = 0; kk < p.kb_per_tap; ++kk)
-              for (int tap = 0; tap < p.ntaps; ++tap) {
-                uint8_t* sB = bring + (kk * p.ntaps + tap) * kBStage;
-                if (p.b_major == 0) {
-                  tma_load_2d(sB, &tmB, &full_bar[0], kk * BK + p.b_off0[tap], wi.n0 + p.b_off1[tap]);
-                } else {
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[0], p.kb_per_tap * p.ntaps * kBStage);
+              for (int kk = 0; kk < p.kb_per_tap; ++kk)
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                  uint8_t* sB = bring + (kk * p.ntaps + tap) * kBStage;
+                  if (p.b_major == 0) {
+                    tma_load_2d(sB, &tmB, &full_bar[0], kk * BK + p.b_off0[tap], wi.n0 + p.b_off1[tap]);
+                  } else {
 #pragma unroll
-                  for (int j = 0; j < BN / 64; ++j)
-                    tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[0], wi.n0 + j * 64 + p.b_off0[tap], kk * BK + p.b_off1[tap]);
+                    for (int j = 0; j < BN / 64; ++j)
+                      tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[0], wi.n0 + j * 64 + p.b_off0[tap], kk * BK + p.b_off1[tap]);
+                  }
                 }
-              }
+            }
+            __syncwarp();
           }
           for (int kk = 0; kk < p.kb_per_tap; ++kk) {
             mbar_wait(&aempty_bar[sa], pa ^ 1, 9);
-            mbar_expect_tx(&afull_bar[sa], p.a_tile_bytes);
-            uint8_t* sA = smem + sa * p.a_tile_bytes;
-            for (int j = 0; j < p.a_nbox; ++j)
-              tma_load_2d(sA + j * p.a_box_rows * 128, &tmA, &afull_bar[sa], kk * BK + p.a_off0[0],
-                          wi.m0 + p.a_min_off + j * p.a_box_rows);
+            if (elect_one()) {
+              mbar_expect_tx(&afull_bar[sa], p.a_tile_bytes);
+              uint8_t* sA = smem + sa * p.a_tile_bytes;
+              for (int j = 0; j < p.a_nbox; ++j)
+                tma_load_2d(sA + j * p.a_box_rows * 128, &tmA, &afull_bar[sa], kk * BK + p.a_off0[0],
+                            wi.m0 + p.a_min_off + j * p.a_box_rows);
+            }
+            __syncwarp();
             if (++sa == p.na_stages) {
               sa = 0;
               pa ^= 1;
@@ -193,16 +203,19 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (!p.b_resident) {
               for (int tap = 0; tap < p.ntaps; ++tap) {
                 mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                mbar_expect_tx(&full_bar[stage], kBStage);
-                uint8_t* sB = bring + stage * kBStage;
-                if (p.b_major == 0) {
-                  tma_load_2d(sB, &tmB, &full_bar[stage], kk * BK + p.b_off0[tap], wi.n0 + p.b_off1[tap]);
-                } else {
+                if (elect_one()) {
+                  mbar_expect_tx(&full_bar[stage], kBStage);
+                  uint8_t* sB = bring + stage * kBStage;
+                  if (p.b_major == 0) {
+                    tma_load_2d(sB, &tmB, &full_bar[stage], kk * BK + p.b_off0[tap], wi.n0 + p.b_off1[tap]);
+                  } else {
 #pragma unroll
-                  for (int j = 0; j < BN / 64; ++j)
-                    tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], wi.n0 + j * 64 + p.b_off0[tap],
-                                kk * BK + p.b_off1[tap]);
+                    for (int j = 0; j < BN / 64; ++j)
+                      tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], wi.n0 + j * 64 + p.b_off0[tap],
+                                  kk * BK + p.b_off1[tap]);
+                  }
                 }
+                __syncwarp();
                 if (++stage == p.nb_stages) {
                   stage = 0;
                   phase ^= 1;
@@ -217,10 +230,13 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if constexpr (EPI == 5) {
           if (p.residual != nullptr) {      // residual tile, two tiles ahead of the epilogue (3 slots)
             mbar_wait(&oempty_bar[oslot], ophase ^ 1, 7);
-            mbar_expect_tx(&ofull_bar[oslot], BM * BN * 2);
+            if (elect_one()) {
+              mbar_expect_tx(&ofull_bar[oslot], BM * BN * 2);
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(opnd + (oslot * (BN / 64) + j) * (BM * 128), &tmR, &ofull_bar[oslot], wi.n0 + j * 64, wi.m0);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(opnd + (oslot * (BN / 64) + j) * (BM * 128), &tmR, &ofull_bar[oslot], wi.n0 + j * 64, wi.m0);
+            }
+            __syncwarp();
           }
           if (++oslot == 3) {
             oslot = 0;
@@ -231,47 +247,49 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // whole residual tile of this work item (128 rows x BN columns) by TMA, one tile ahead of the epilogue: its HBM
           // latency overlaps the previous tile's epilogue and this tile's main loop, with 2 x 32 KB in flight per SM
           mbar_wait(&oempty_bar[oslot], ophase ^ 1, 5);
-          mbar_expect_tx(&ofull_bar[oslot], BM * BN * 2);
+          if (elect_one()) {
+            mbar_expect_tx(&ofull_bar[oslot], BM * BN * 2);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(opnd + (oslot * (BN / 64) + j) * (BM * 128), &tmR, &ofull_bar[oslot], wi.n0 + j * 64, wi.m0);
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(opnd + (oslot * (BN / 64) + j) * (BM * 128), &tmR, &ofull_bar[oslot], wi.n0 + j * 64, wi.m0);
+          }
+          __syncwarp();
           if (++oslot == 2) {
             oslot = 0;
             ophase ^= 1;
           }
         }
-        for (int it = 0; it < wi.iters; ++it) {
-          int tap, kk;
-          if (p.splits == 1) {
-            tap = it / p.kb_per_tap;
-            kk = it - tap * p.kb_per_tap;
-          } else {
-            tap = 0;
-            kk = wi.kb_begin + it;
-          }
-          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          uint8_t* sA = smem + stage * Cfg::kStageBytes;
-          uint8_t* sB = sA + BM * BK * 2;
-          if (p.a_major == 0) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], kk * BK + p.a_off0[tap], wi.m0 + p.a_off1[tap]);
-          } else {
+        const int ntap = p.splits == 1 ? p.ntaps : 1;
+        const int kb0 = p.splits == 1 ? 0 : wi.kb_begin;
+        const int nkb = p.splits == 1 ? p.kb_per_tap : wi.iters;
+        const int zb = p.z_b_off1[wi.z];
+        for (int tap = 0; tap < ntap; ++tap) {
+          const int a0 = p.a_off0[tap], a1 = p.a_off1[tap], b0 = p.b_off0[tap], b1 = p.b_off1[tap];
+          for (int kk = kb0; kk < kb0 + nkb; ++kk) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              uint8_t* sA = smem + stage * Cfg::kStageBytes;
+              uint8_t* sB = sA + BM * BK * 2;
+              if (p.a_major == 0) {
+                tma_load_2d(sA, &tmA, &full_bar[stage], kk * BK + a0, wi.m0 + a1);
+              } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sA + j * kChunkBytes, &tmA, &full_bar[stage], wi.m0 + j * 64 + p.a_off0[tap],
-                          kk * BK + p.a_off1[tap]);
-          }
-          if (p.b_major == 0) {
-            tma_load_2d(sB, &tmB, &full_bar[stage], kk * BK + p.b_off0[tap], wi.n0 + p.b_off1[tap]);
-          } else {
+                for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * kChunkBytes, &tmA, &full_bar[stage], wi.m0 + j * 64 + a0, kk * BK + a1);
+              }
+              if (p.b_major == 0) {
+                tma_load_2d(sB, &tmB, &full_bar[stage], kk * BK + b0, wi.n0 + b1);
+              } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], wi.n0 + j * 64 + p.b_off0[tap],
-                          kk * BK + p.b_off1[tap] + p.z_b_off1[wi.z]);
-          }
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], wi.n0 + j * 64 + b0, kk * BK + b1 + zb);
+              }
+            }
+            __syncwarp();
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -1192,7 +1210,11 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
       if (na > 4) na = 4;
       if (na_env >= 2 && na_env <= na) na = na_env;
       if (!resident) nb = (ring - na * tile_bytes) / bstage;
-      if (same_cols && nb >= 3 && na >= 2) {
+      // measured (tools/halo_diag.py): with streamed weights the 1-CTA kernel gains nothing from the halo tile (the weight
+      // stream, 9 x BN x 128 B per k-block, is the feed either way); with resident weights it does
+      static int halo_ring = -1;
+      if (halo_ring < 0) { const char* e = getenv("TDB_HALO_RING"); halo_ring = e ? atoi(e) : 0; }
+      if (same_cols && nb >= 3 && na >= 2 && (resident || halo_ring)) {
         p.halo = 1; p.a_min_off = lo; p.a_box_rows = box_rows; p.a_nbox = nbox; p.a_tile_bytes = tile_bytes;
         p.na_stages = na;
         p.nb_stages = nb > max_stages ? max_stages : nb;

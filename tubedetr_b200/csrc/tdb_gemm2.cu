@@ -131,7 +131,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET on the __shared__ pointer: an integer round trip would turn every access below into a
+  // generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* after = smem + G2_STAGES * G2_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);          // [8] (halo mode: B ring)
   uint64_t* empty_bar = full_bar + G2_HALO_B_MAX;
@@ -174,7 +176,8 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // both CTAs: the whole warp runs the warp-uniform loop, one elected lane arms the barrier and issues the copies
+    {
       int stage = 0;
       uint32_t phase = 0;
       if (p.halo) {
@@ -187,26 +190,32 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int nb = wi.nt * G2_BN + (int)rank * 128;
           for (int kk = 0; kk < p.kb_per_tap; ++kk) {
             mbar_wait(&aempty_bar[sa], pa ^ 1, 25);
-            if (rank == 0) mbar_expect_tx(&afull_bar[sa], 2 * p.a_tile_bytes);
-            uint8_t* sA = smem + sa * p.a_tile_bytes;
-            for (int j = 0; j < p.a_nbox; ++j)
-              tma_load_2d_2sm(sA + j * p.a_box_rows * 128, &tmA, &afull_bar[sa], kk * 64 + p.a_off0[0],
-                              m0 + p.a_min_off + j * p.a_box_rows);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(&afull_bar[sa], 2 * p.a_tile_bytes);
+              uint8_t* sA = smem + sa * p.a_tile_bytes;
+              for (int j = 0; j < p.a_nbox; ++j)
+                tma_load_2d_2sm(sA + j * p.a_box_rows * 128, &tmA, &afull_bar[sa], kk * 64 + p.a_off0[0],
+                                m0 + p.a_min_off + j * p.a_box_rows);
+            }
+            __syncwarp();
             if (++sa == G2_HALO_A_STAGES) {
               sa = 0;
               pa ^= 1;
             }
             for (int tap = 0; tap < p.ntaps; ++tap) {
               mbar_wait(&empty_bar[stage], phase ^ 1, 21);
-              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * 128 * 64 * 2);
-              uint8_t* sB = bring + stage * (128 * 64 * 2);
-              if (p.b_major == 0) {
-                tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kk * 64 + p.b_off0[tap], nb + p.b_off1[tap]);
-              } else {
+              if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * 128 * 64 * 2);
+                uint8_t* sB = bring + stage * (128 * 64 * 2);
+                if (p.b_major == 0) {
+                  tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kk * 64 + p.b_off0[tap], nb + p.b_off1[tap]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[stage], nb + j * 64 + p.b_off0[tap], kk * 64 + p.b_off1[tap]);
+                  for (int j = 0; j < 2; ++j)
+                    tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[stage], nb + j * 64 + p.b_off0[tap], kk * 64 + p.b_off1[tap]);
+                }
               }
+              __syncwarp();
               if (++stage == p.nb_stages) {
                 stage = 0;
                 phase ^= 1;
@@ -219,37 +228,36 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const Work2 wi = decode2(p, w);
         const int m0 = wi.mt * 256 + (int)rank * 128;
         const int nb = wi.nt * G2_BN + (int)rank * 128;     // this CTA's half of the B tile
-        for (int it = 0; it < wi.iters; ++it) {
-          int tap, kk;
-          if (p.splits == 1) {
-            tap = it / p.kb_per_tap;
-            kk = it - tap * p.kb_per_tap;
-          } else {
-            tap = 0;
-            kk = wi.kb_begin + it;
-          }
-          mbar_wait(&empty_bar[stage], phase ^ 1, 21);
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
-          uint8_t* sA = smem + stage * G2_STAGE_BYTES;
-          uint8_t* sB = sA + 128 * 64 * 2;
-          if (p.a_major == 0) {
-            tma_load_2d_2sm(sA, &tmA, &full_bar[stage], kk * 64 + p.a_off0[tap], m0 + p.a_off1[tap]);
-          } else {
+        const int ntap = p.splits == 1 ? p.ntaps : 1;
+        const int kb0 = p.splits == 1 ? 0 : wi.kb_begin;
+        const int nkb = p.splits == 1 ? p.kb_per_tap : wi.iters;
+        const int zb = p.z_b_off1[wi.z];
+        for (int tap = 0; tap < ntap; ++tap) {
+          const int a0 = p.a_off0[tap], a1 = p.a_off1[tap], b0 = p.b_off0[tap], b1 = p.b_off1[tap];
+          for (int kk = kb0; kk < kb0 + nkb; ++kk) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 21);
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+              uint8_t* sA = smem + stage * G2_STAGE_BYTES;
+              uint8_t* sB = sA + 128 * 64 * 2;
+              if (p.a_major == 0) {
+                tma_load_2d_2sm(sA, &tmA, &full_bar[stage], kk * 64 + a0, m0 + a1);
+              } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tma_load_2d_2sm(sA + j * 8192, &tmA, &full_bar[stage], m0 + j * 64 + p.a_off0[tap], kk * 64 + p.a_off1[tap]);
-          }
-          if (p.b_major == 0) {
-            tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kk * 64 + p.b_off0[tap], nb + p.b_off1[tap]);
-          } else {
+                for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sA + j * 8192, &tmA, &full_bar[stage], m0 + j * 64 + a0, kk * 64 + a1);
+              }
+              if (p.b_major == 0) {
+                tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kk * 64 + b0, nb + b1);
+              } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[stage], nb + j * 64 + p.b_off0[tap],
-                              kk * 64 + p.b_off1[tap] + p.z_b_off1[wi.z]);
-          }
-          if (++stage == G2_STAGES) {
-            stage = 0;
-            phase ^= 1;
+                for (int j = 0; j < 2; ++j) tma_load_2d_2sm(sB + j * 8192, &tmB, &full_bar[stage], nb + j * 64 + b0, kk * 64 + b1 + zb);
+              }
+            }
+            __syncwarp();
+            if (++stage == G2_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
