@@ -33,6 +33,8 @@ struct AttnParams {
 };
 
 __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams a) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int Lkp = a.Lk | 1;                 // odd pitch: conflict-free transposed K
   float* kt = sm;                           // [32][Lkp]
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams 
 
 // Pbar[b][i][j] = mean_h P[b][h][i][j]
 __global__ void head_mean_kernel(const float* __restrict__ p, float* __restrict__ pbar, int B, int H, long long LL) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * LL) return;
   long long b = idx / LL, r = idx - b * LL;
@@ -125,6 +129,8 @@ struct AttnBwdParams {
 
 // row pass: one warp per query row: dP = dO V^T (+ dPbar/H), dS, dQ = scale * dS K
 __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwdParams a) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   const int Lkp = a.Lk | 1;
   float* vt = sm;                    // [32][Lkp]   V transposed
@@ -189,6 +195,8 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
 constexpr int kColKeys = 64;
 constexpr int kColRows = 32;
 __global__ void __launch_bounds__(kAttnThreads) mha_bwd_col_kernel(const AttnBwdParams a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float ps[kColRows][kColKeys];
   __shared__ float dss[kColRows][kColKeys];
   __shared__ float dos[kColRows][HD];
@@ -274,12 +282,12 @@ extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   if (rc) return rc;
   AttnParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, kpm, (bf16*)o, ldo, p, pdrop, keep, keep_scale, B, H, Lq, Lk, scale};
   dim3 grid(B * H, attn_grid_y(B * H, Lq));
-  mha_fwd_kernel<<<grid, kAttnThreads, smem, (cudaStream_t)stream_>>>(a);
+  TDB_CHECK_CUDA(tdb_launch(mha_fwd_kernel, dim3(grid), dim3(kAttnThreads), smem, (cudaStream_t)stream_, a));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   if (pbar) {
     long long LL = (long long)Lq * Lk;
-    head_mean_kernel<<<(unsigned)(((long long)B * LL + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(keep ? pdrop : p, pbar, B, H, LL);
+    TDB_CHECK_CUDA(tdb_launch(head_mean_kernel, dim3((unsigned)(((long long)B * LL + 255) / 256)), dim3(256), 0, (cudaStream_t)stream_, keep ? pdrop : p, pbar, B, H, LL));
     TDB_CHECK_CUDA(cudaGetLastError());
     tdb_count_launch(1);
   }
@@ -300,9 +308,9 @@ extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
   AttnBwdParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)dout, ldq, ldk, ldv, lddo, p, keep, keep_scale,
                   pd_scratch, dpbar, ds_scratch, (bf16*)dq, (bf16*)dk, (bf16*)dv, lddq, lddk, lddv, B, H, Lq, Lk, scale};
   dim3 g1(B * H, attn_grid_y(B * H, Lq));
-  mha_bwd_row_kernel<<<g1, kAttnThreads, smem, (cudaStream_t)stream_>>>(a);
+  TDB_CHECK_CUDA(tdb_launch(mha_bwd_row_kernel, dim3(g1), dim3(kAttnThreads), smem, (cudaStream_t)stream_, a));
   dim3 g2(B * H, (Lk + kColKeys - 1) / kColKeys);
-  mha_bwd_col_kernel<<<g2, kAttnThreads, 0, (cudaStream_t)stream_>>>(a);
+  TDB_CHECK_CUDA(tdb_launch(mha_bwd_col_kernel, dim3(g2), dim3(kAttnThreads), 0, (cudaStream_t)stream_, a));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(2);
   return TDB_OK;

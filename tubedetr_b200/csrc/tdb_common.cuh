@@ -133,6 +133,13 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+// Programmatic dependent launch: every kernel of this library is launched with programmatic stream serialisation (tdb_launch
+// below), so its CTAs may become resident -- and run their prologue (barrier init, TMEM allocation, descriptor prefetch,
+// shared-memory staging of constants) -- while the previous kernel in the stream is still draining.  pdl_wait() blocks until
+// that previous grid has completed and its memory is visible; nothing before it may touch global memory that another kernel
+// writes.  pdl_trigger() lets the NEXT kernel in the stream start its own pre-wait part.  Both are no-ops without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Instruction descriptor for kind::f16 with bf16 A/B, fp32 D.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                         // D format f32
@@ -188,3 +195,21 @@ void tdb_set_error(const char* fmt, ...);
       return TDB_ERR_ARG;           \
     }                               \
   } while (0)
+
+// ------------------------------------------------------------------ host: launch with programmatic stream serialisation
+int tdb_pdl_enabled();   // env TDB_PDL (default 1), defined in tdb_gemm.cu
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tdb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = tdb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

@@ -16,6 +16,8 @@ static inline unsigned nblocks(long long n, int threads) { return (unsigned)((n 
 // loads (zero padded by 3 on both sides), then every output pixel's 192-column row is written as 24 x 16-byte stores.
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ col, int N, int H, int W,
                                                           int Ho, int Wo) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float srow[];           // [3][7][W + 6]
   const int Wp = W + 6;
   const int n = blockIdx.x / Ho, ho = blockIdx.x % Ho;
@@ -29,32 +31,32 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   }
   __syncthreads();
   bf16* out = col + ((long long)n * Ho + ho) * Wo * 192;
-  for (int e = threadIdx.x; e < Wo * 24; e += blockDim.x) {
-    int wo = e / 24, g = e % 24;
-    uint32_t packed[4];
+  // thread -> fixed 16-byte group g of the 192-column row (its 8 shared-memory offsets are loop invariants), strided over the
+  // output pixels: per 16-byte store 8 LDS + 4 packs, no index arithmetic; 24 consecutive threads write one 384-byte row
+  if (threadIdx.x >= 240) return;
+  const int g = threadIdx.x % 24, wo0 = threadIdx.x / 24;
+  int off[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float v[2];
+  for (int i = 0; i < 8; ++i) {
+    int cidx = g * 8 + i;
+    int c = cidx / 49;
+    int r = cidx - c * 49;
+    int kh = r / 7, kw = r - kh * 7;
+    off[i] = cidx < 147 ? (c * 7 + kh) * Wp + kw : -1;
+  }
+  for (int wo = wo0; wo < Wo; wo += 10) {
+    float v[8];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        int cidx = g * 8 + i * 2 + j;
-        float val = 0.f;
-        if (cidx < 147) {
-          int c = cidx / 49;
-          int r = cidx - c * 49;
-          int kh = r / 7, kw = r - kh * 7;
-          val = srow[(c * 7 + kh) * Wp + wo * 2 + kw];
-        }
-        v[j] = val;
-      }
-      packed[i] = pack_bf16x2(v[0], v[1]);
-    }
-    *reinterpret_cast<uint4*>(out + (long long)wo * 192 + g * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    for (int i = 0; i < 8; ++i) v[i] = off[i] >= 0 ? srow[off[i] + wo * 2] : 0.f;
+    *reinterpret_cast<uint4*>(out + (long long)wo * 192 + g * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
 
 // ------------------------------------------------------------------ 3x3 / stride 2 / pad 1 max pool, NHWC bf16, 8 channels per thread
 __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int cg = C / 8;
   long long total = (long long)N * Ho * Wo * cg;
@@ -86,6 +88,8 @@ __global__ void maxpool3x3s2_kernel(const bf16* __restrict__ x, bf16* __restrict
 
 // ------------------------------------------------------------------ 3x3 / stride 2 / pad 1 im2col, NHWC bf16 -> [N*Ho*Wo][9*C] (tap major)
 __global__ void im2col3x3s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int cg = C / 8;
   long long total = (long long)N * Ho * Wo * 9 * cg;
@@ -109,6 +113,8 @@ __global__ void im2col3x3s2_kernel(const bf16* __restrict__ x, bf16* __restrict_
 // transpose of the above as a gather (deterministic): dx[n,h,w,:] = sum over (ho,wo,tap) hitting (h,w); then ReLU mask by y>0
 __global__ void col2im3x3s2_mask_kernel(const bf16* __restrict__ dcol, const bf16* __restrict__ ymask, bf16* __restrict__ dx,
                                         int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int cg = C / 8;
   long long total = (long long)N * H * W * cg;
@@ -151,6 +157,8 @@ __global__ void col2im3x3s2_mask_kernel(const bf16* __restrict__ dcol, const bf1
 
 // ------------------------------------------------------------------ stride-2 pixel subsample (1x1 stride-2 downsample conv input) and its transpose
 __global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int cg = C / 8;
   long long total = (long long)N * Ho * Wo * cg;
@@ -165,6 +173,8 @@ __global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__
       __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + c8 * 8));
 }
 __global__ void upsample2_zero_kernel(const bf16* __restrict__ y, bf16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int cg = C / 8;
   long long total = (long long)N * H * W * cg;
@@ -186,6 +196,8 @@ __global__ void upsample2_zero_kernel(const bf16* __restrict__ y, bf16* __restri
 // taps==49 (stem) keeps torch order c*49+tap.  Columns >= taps*Cin are zero.
 __global__ void prep_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, bf16* __restrict__ out_scaled,
                                    const float* __restrict__ rowscale, int Cout, int Cin, int taps, int Kpad) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)Cout * Kpad;
   if (idx >= total) return;
@@ -206,6 +218,8 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, bf16* __restrict
 
 // ------------------------------------------------------------------ fp32 -> bf16 cast with optional add (x + pos), 4 elements per thread
 __global__ void cast_add_bf16_kernel(const float* __restrict__ x, const float* __restrict__ add, bf16* __restrict__ y, long long n4) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n4) return;
   float4 v = __ldg(reinterpret_cast<const float4*>(x) + idx);
@@ -223,6 +237,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ beta, const float* __restrict__ pos, float* __restrict__ y,
                                      bf16* __restrict__ y_bf, bf16* __restrict__ ypos_bf, float* __restrict__ mean_out,
                                      float* __restrict__ rstd_out, int rows, float eps) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int PER = D / 32;
   int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   int lane = threadIdx.x & 31;
@@ -265,6 +281,8 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
                                      const float* __restrict__ x, const float* __restrict__ r,
                                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                                      float* __restrict__ dz, bf16* __restrict__ dz_bf, float* __restrict__ partial, int rows) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int PER = D / 32;
   __shared__ float sg[8][D];
   __shared__ float sb[8][D];
@@ -321,6 +339,8 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
 // block = 32 columns x 8 part-groups: part-group y sums parts y, y+8, ... then the 8 groups are combined through shared memory.
 __global__ void colsum_partials_kernel(const float* __restrict__ partial, int nparts, long long part_stride, int D,
                                        float* __restrict__ out, int accumulate) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
@@ -338,6 +358,8 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, int np
 
 // column sums of a bf16 [rows][N] matrix (bias gradients): stage 1 -> partial [nb][N] fp32.  Thread = 2 adjacent columns.
 __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, int rows, int N, float* __restrict__ partial, int rows_per_block) {
+  pdl_wait();
+  pdl_trigger();
   int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (c >= N) return;
   int r0 = blockIdx.y * rows_per_block;
@@ -368,42 +390,42 @@ extern "C" int tdb_stem_im2col(const float* x, void* col, int N, int H, int W, v
   int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   size_t smem = (size_t)21 * (W + 6) * sizeof(float);
   TDB_REQUIRE(smem <= 48 * 1024, "tdb_stem_im2col: frame width %d too large", W);
-  stem_im2col_kernel<<<(unsigned)(N * Ho), 256, smem, STREAM>>>(x, (bf16*)col, N, H, W, Ho, Wo);
+  TDB_CHECK_CUDA(tdb_launch(stem_im2col_kernel, dim3((unsigned)(N * Ho)), dim3(256), smem, STREAM, x, (bf16*)col, N, H, W, Ho, Wo));
   LAUNCH_OK();
 }
 extern "C" int tdb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
   TDB_REQUIRE(x && y && C % 8 == 0, "tdb_maxpool3x3s2: bad args");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * Ho * Wo * (C / 8);
-  maxpool3x3s2_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)x, (bf16*)y, N, H, W, C, Ho, Wo);
+  TDB_CHECK_CUDA(tdb_launch(maxpool3x3s2_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, (const bf16*)x, (bf16*)y, N, H, W, C, Ho, Wo));
   LAUNCH_OK();
 }
 extern "C" int tdb_im2col3x3s2(const void* x, void* col, int N, int H, int W, int C, void* stream_) {
   TDB_REQUIRE(x && col && C % 8 == 0, "tdb_im2col3x3s2: bad args");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * Ho * Wo * 9 * (C / 8);
-  im2col3x3s2_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)x, (bf16*)col, N, H, W, C, Ho, Wo);
+  TDB_CHECK_CUDA(tdb_launch(im2col3x3s2_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, (const bf16*)x, (bf16*)col, N, H, W, C, Ho, Wo));
   LAUNCH_OK();
 }
 extern "C" int tdb_col2im3x3s2_mask(const void* dcol, const void* ymask, void* dx, int N, int H, int W, int C, void* stream_) {
   TDB_REQUIRE(dcol && dx && C % 8 == 0, "tdb_col2im3x3s2_mask: bad args");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   long long total = (long long)N * H * W * (C / 8);
-  col2im3x3s2_mask_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)dcol, (const bf16*)ymask, (bf16*)dx, N, H, W, C, Ho, Wo);
+  TDB_CHECK_CUDA(tdb_launch(col2im3x3s2_mask_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, (const bf16*)dcol, (const bf16*)ymask, (bf16*)dx, N, H, W, C, Ho, Wo));
   LAUNCH_OK();
 }
 extern "C" int tdb_subsample2(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
   TDB_REQUIRE(x && y && C % 8 == 0, "tdb_subsample2: bad args");
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   long long total = (long long)N * Ho * Wo * (C / 8);
-  subsample2_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)x, (bf16*)y, N, H, W, C, Ho, Wo);
+  TDB_CHECK_CUDA(tdb_launch(subsample2_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, (const bf16*)x, (bf16*)y, N, H, W, C, Ho, Wo));
   LAUNCH_OK();
 }
 extern "C" int tdb_upsample2_zero(const void* y, void* x, int N, int H, int W, int C, void* stream_) {
   TDB_REQUIRE(x && y && C % 8 == 0, "tdb_upsample2_zero: bad args");
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   long long total = (long long)N * H * W * (C / 8);
-  upsample2_zero_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>((const bf16*)y, (bf16*)x, N, H, W, C, Ho, Wo);
+  TDB_CHECK_CUDA(tdb_launch(upsample2_zero_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, (const bf16*)y, (bf16*)x, N, H, W, C, Ho, Wo));
   LAUNCH_OK();
 }
 extern "C" int tdb_prep_weight(const float* w, void* out, void* out_scaled, const float* rowscale, int Cout, int Cin,
@@ -411,12 +433,12 @@ extern "C" int tdb_prep_weight(const float* w, void* out, void* out_scaled, cons
   TDB_REQUIRE(w && out && Cout > 0 && Cin > 0 && (taps == 1 || taps == 9 || taps == 49) && Kpad >= taps * Cin, "tdb_prep_weight: bad args");
   TDB_REQUIRE(!out_scaled || rowscale, "tdb_prep_weight: scaled copy needs rowscale");
   long long total = (long long)Cout * Kpad;
-  prep_weight_kernel<<<nblocks(total, 256), 256, 0, STREAM>>>(w, (bf16*)out, (bf16*)out_scaled, rowscale, Cout, Cin, taps, Kpad);
+  TDB_CHECK_CUDA(tdb_launch(prep_weight_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, w, (bf16*)out, (bf16*)out_scaled, rowscale, Cout, Cin, taps, Kpad));
   LAUNCH_OK();
 }
 extern "C" int tdb_cast_add_bf16(const float* x, const float* add, void* y, int64_t n, void* stream_) {
   TDB_REQUIRE(x && y && n % 4 == 0, "tdb_cast_add_bf16: n must be a multiple of 4");
-  cast_add_bf16_kernel<<<nblocks(n / 4, 256), 256, 0, STREAM>>>(x, add, (bf16*)y, n / 4);
+  TDB_CHECK_CUDA(tdb_launch(cast_add_bf16_kernel, dim3(nblocks(n / 4, 256)), dim3(256), 0, STREAM, x, add, (bf16*)y, n / 4));
   LAUNCH_OK();
 }
 extern "C" int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta, const float* pos,
@@ -424,8 +446,8 @@ extern "C" int tdb_layernorm_fwd(const float* x, const float* r, const float* ga
                                  void* stream_) {
   TDB_REQUIRE(x && gamma && beta && y && rows > 0 && D == 256, "tdb_layernorm_fwd: only D=256 (got %d)", D);
   TDB_REQUIRE(!ypos_bf || pos, "tdb_layernorm_fwd: ypos needs pos");
-  layernorm_fwd_kernel<256><<<nblocks((long long)rows * 32, 256), 256, 0, STREAM>>>(x, r, gamma, beta, pos, y, (bf16*)y_bf,
-                                                                                    (bf16*)ypos_bf, mean, rstd, rows, eps);
+  TDB_CHECK_CUDA(tdb_launch(layernorm_fwd_kernel<256>, dim3(nblocks((long long)rows * 32, 256)), dim3(256), 0, STREAM, x, r, gamma, beta, pos, y, (bf16*)y_bf,
+                                                                                    (bf16*)ypos_bf, mean, rstd, rows, eps));
   LAUNCH_OK();
 }
 extern "C" int tdb_layernorm_bwd_blocks(int rows) {
@@ -437,10 +459,10 @@ extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void
                                  float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate, void* stream_) {
   TDB_REQUIRE((dy || dy2_bf || dy3_bf) && x && gamma && mean && rstd && dz && partial && rows > 0 && D == 256, "tdb_layernorm_bwd: bad args");
   int blocks = tdb_layernorm_bwd_blocks(rows);
-  layernorm_bwd_kernel<256><<<blocks, 256, 0, STREAM>>>(dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows);
+  TDB_CHECK_CUDA(tdb_launch(layernorm_bwd_kernel<256>, dim3(blocks), dim3(256), 0, STREAM, dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows));
   TDB_CHECK_CUDA(cudaGetLastError());
-  if (dgamma) colsum_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, STREAM>>>(partial, blocks, 2 * D, D, dgamma, accumulate);
-  if (dbeta) colsum_partials_kernel<<<(D + 31) / 32, dim3(32, 8), 0, STREAM>>>(partial + D, blocks, 2 * D, D, dbeta, accumulate);
+  if (dgamma) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial, blocks, 2 * D, D, dgamma, accumulate));
+  if (dbeta) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial + D, blocks, 2 * D, D, dbeta, accumulate));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(3);
   return TDB_OK;
@@ -451,8 +473,8 @@ extern "C" int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float
   TDB_REQUIRE(N % 2 == 0 && ld % 2 == 0, "tdb_colsum_bf16: N and ld must be even");
   int rpb = (rows + nparts - 1) / nparts;
   dim3 grid((N / 2 + 127) / 128, nparts);
-  colsum_bf16_kernel<<<grid, 128, 0, STREAM>>>((const bf16*)x, ld, rows, N, partial, rpb);
-  colsum_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, STREAM>>>(partial, nparts, N, N, out, accumulate);
+  TDB_CHECK_CUDA(tdb_launch(colsum_bf16_kernel, dim3(grid), dim3(128), 0, STREAM, (const bf16*)x, ld, rows, N, partial, rpb));
+  TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((N + 31) / 32), dim3(32, 8), 0, STREAM, partial, nparts, N, N, out, accumulate));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(2);
   return TDB_OK;

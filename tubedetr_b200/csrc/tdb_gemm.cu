@@ -150,6 +150,8 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; from here on we read what it wrote
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -976,6 +978,8 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
                                      const float* __restrict__ rowscale, float* __restrict__ out, int taps,
                                      int accumulate) {
+  pdl_wait();
+  pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)M * N;
   if (idx >= total) return;
@@ -1007,6 +1011,11 @@ void tdb_set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void tdb_count_launch(int n) { g_launches += n; }
 
+int tdb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TDB_PDL"); v = e ? atoi(e) : 1; }
+  return v;
+}
 extern "C" const char* tdb_last_error_string(void) { return g_err; }
 extern "C" int tdb_version(void) { return TDB_ABI_VERSION; }
 extern "C" int64_t tdb_launch_count(void) { return g_launches.load(); }
@@ -1244,7 +1253,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   auto launch = [&](int bn_, const CUtensorMap& tmB_, const GemmKParams& q) -> int {
     int grid = q.total_work < g_num_sms ? q.total_work : g_num_sms;
     if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
-#define TDB_LAUNCH(BN_, EPI_) tdb_gemm_kernel<BN_, EPI_><<<grid, kGemmThreads, GemmCfg<BN_, EPI_>::kSmemBytes, stream>>>(tmA, tmB_, tmR, tmO, q)
+#define TDB_LAUNCH(BN_, EPI_) TDB_CHECK_CUDA(tdb_launch(tdb_gemm_kernel<BN_, EPI_>, dim3(grid), dim3(kGemmThreads), GemmCfg<BN_, EPI_>::kSmemBytes, stream, tmA, tmB_, tmR, tmO, q))
     if (q.epi_mode == 0) {
       switch (bn_) {
         case 64: TDB_LAUNCH(64, 0); break;
@@ -1339,7 +1348,7 @@ extern "C" int tdb_splitk_reduce(const float* part, int splits, int M, int N, co
   long long total = (long long)M * N;
   int threads = 256;
   long long blocks = (total + threads - 1) / threads;
-  tdb::splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream_>>>(part, splits, M, N, rowscale, out, taps, accumulate);
+  TDB_CHECK_CUDA(tdb_launch(tdb::splitk_reduce_kernel, dim3((unsigned)blocks), dim3(threads), 0, (cudaStream_t)stream_, part, splits, M, N, rowscale, out, taps, accumulate));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   return TDB_OK;

@@ -174,6 +174,8 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; from here on we read what it wrote
+  pdl_trigger();
 
   if (warp == 0) {
     // both CTAs: the whole warp runs the warp-uniform loop, one elected lane arms the barrier and issues the copies
@@ -581,7 +583,7 @@ int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
   rc = tdb_make_tmap_bf16(&tmB, d->B, d->b_rows, d->b_cols, d->ldb, p.b_major ? 64 : 128);
   if (rc) return rc;
   int np = total < pairs ? (int)total : pairs;
-  tdb_gemm2_kernel<<<np * 2, G2_THREADS, G2_SMEM, (cudaStream_t)stream_>>>(tmA, tmB, p);
+  TDB_CHECK_CUDA(tdb_launch(tdb_gemm2_kernel, dim3(np * 2), dim3(G2_THREADS), G2_SMEM, (cudaStream_t)stream_, tmA, tmB, p));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   return 1;

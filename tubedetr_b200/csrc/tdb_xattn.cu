@@ -93,6 +93,8 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh.tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -276,6 +278,8 @@ __global__ void __launch_bounds__(256) xattn_merge_kernel(const float* __restric
                                                           const float* __restrict__ part_o, const float* __restrict__ bv,
                                                           float* __restrict__ p, float* __restrict__ pbar, bf16* __restrict__ o,
                                                           const uint8_t* __restrict__ keep, float keep_scale, int S, int F) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float Ms[XH], Ls[XH];
   __shared__ float fac[4][XH];       // exp(m_t - M) per segment
   const int f = blockIdx.x;
@@ -375,9 +379,9 @@ extern "C" int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void*
   prm.F = F;
   prm.scale = scale;
   cudaStream_t st = (cudaStream_t)stream_;
-  xattn_fused_kernel<<<tiles, XTHREADS, XSMEM_BYTES, st>>>(tmK, tmV, tmW, prm);
+  TDB_CHECK_CUDA(tdb_launch(xattn_fused_kernel, dim3(tiles), dim3(XTHREADS), XSMEM_BYTES, st, tmK, tmV, tmW, prm));
   TDB_CHECK_CUDA(cudaGetLastError());
-  xattn_merge_kernel<<<F, 256, 0, st>>>(prm.part_m, prm.part_l, prm.part_o, bv, p, pbar, (bf16*)o, keep, keep_scale, S, F);
+  TDB_CHECK_CUDA(tdb_launch(xattn_merge_kernel, dim3(F), dim3(256), 0, st, prm.part_m, prm.part_l, prm.part_o, bv, p, pbar, (bf16*)o, keep, keep_scale, S, F));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(2);
   return TDB_OK;
