@@ -248,11 +248,12 @@ class Step:
 
 
 def kernel_probe(device, pk):
-    """Dominant kernel alone: layer3 3x3 conv (22 of them per frame) as the implicit tcgen05 GEMM on the 100-frame batch."""
+    """Dominant kernel alone: layer3 3x3 conv (22 of them per frame) as the implicit tcgen05 GEMM on the batch the step
+    launches it on: the 25 slow + 100 fast frames of one clip (joint backbone batch)."""
     from tubedetr_b200.gemm import REMAP_P2C, gemm
-    N, h, w, C = 100, 22, 22, 256
+    N, h, w, C = T_FRAMES + (T_FRAMES + STRIDE - 1) // STRIDE, 22, 22, 256
     Rp = N * (h + 2) * (w + 2)
-    nb = 6                                       # rotate buffers: 6 x (29.5 + 24.8) MB > 126 MB L2
+    nb = 6                                       # rotate buffers: 6 x (36.9 + 31.0) MB > 126 MB L2
     xs = [torch.randn(Rp, C, device=device).to(torch.bfloat16) for _ in range(nb)]
     ys = [torch.empty(N * h * w, C, dtype=torch.bfloat16, device=device) for _ in range(nb)]
     wk = (torch.randn(C, 9 * C, device=device) * 0.02).to(torch.bfloat16)
@@ -279,7 +280,7 @@ def kernel_probe(device, pk):
     if os.path.exists(tp):
         t = json.load(open(tp))
         traffic, tsrc = t["dram_bytes_per_launch"], t["source"]
-    return {"bound": "tensor", "kernel": "tdb_gemm2_kernel (layer3 3x3 conv as implicit GEMM, cta_group::2, 100 frames)",
+    return {"bound": "tensor", "kernel": f"tdb_gemm2_kernel (layer3 3x3 conv as implicit GEMM, cta_group::2 + halo tile, {N} frames)",
             "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
             "traffic_source": tsrc, "peak_source": pk["src"] + " cuBLAS bf16 burst", "ms_per_launch": ms,
             "flops_per_launch": flops, "algorithmic_bytes_per_launch": 2 * (Rp * C + C * 9 * C + N * h * w * C)}

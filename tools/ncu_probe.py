@@ -1,6 +1,6 @@
-"""Tiny driver for `ncu --set full`: the two dominant GEMM flavours of the TubeDETR step on the 100-frame batch.
-  A: layer3 3x3 conv as implicit GEMM (M=57600 haloed rows, N=256, K=9x256), FrozenBN+ReLU epilogue, halo rows dropped
-  B: layer3 conv3 1x1 (M=48400, N=1024, K=256) with FrozenBN + residual + ReLU epilogue
+"""Tiny driver for `ncu --set full`: the two dominant GEMM flavours of the TubeDETR step on the 125-frame (25 slow + 100 fast) batch.
+  A: layer3 3x3 conv as implicit GEMM (M=72000 haloed rows, N=256, K=9x256), FrozenBN+ReLU epilogue, halo rows dropped
+  B: layer3 conv3 1x1 (M=60500, N=1024, K=256) with FrozenBN + residual + ReLU epilogue
 Usage: ncu --set full --clock-control none --import-source on -k regex:tdb_gemm -o gpurun_out/prof_gemm python tools/ncu_probe.py"""
 import os
 import sys
@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tubedetr_b200.gemm import REMAP_P2C, gemm  # noqa: E402
 
 mode = int(os.environ.get("TDB_EPI_MODE", "0"))
-N_, h, w, C = 100, 22, 22, 256
+N_, h, w, C = 125, 22, 22, 256
 Rp = N_ * (h + 2) * (w + 2)
 x = torch.randn(Rp, C, device="cuda").to(torch.bfloat16)
 wk = (torch.randn(C, 9 * C, device="cuda") * 0.02).to(torch.bfloat16)
@@ -21,7 +21,7 @@ taps = [(kh - 1) * (w + 2) + (kw - 1) for kh in range(3) for kw in range(3)]
 for _ in range(2):
     gemm(x, wk, y, Rp, C, C, ntaps=9, a_off1=taps, b_off0=[t * C for t in range(9)], scale=sc, bias=sh, relu=True,
          remap=REMAP_P2C, img_hw=(h, w))
-M, N, K = 48400, 1024, 256
+M, N, K = 60500, 1024, 256
 A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
 B = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
 R = torch.randn(M, N, device="cuda").to(torch.bfloat16)

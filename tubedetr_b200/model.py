@@ -321,6 +321,9 @@ class Transformer(nn.Module):
         return x32, xb, xqb, w, cw
 
 
+_TEXT_STREAMS = {}   # device -> side stream of the text encoder (module level: streams do not deepcopy with the model)
+
+
 class TubeDETR(nn.Module):
     def __init__(self, num_queries=1, aux_loss=True, video_max_len=200, stride=5, guided_attn=True, fast=True,
                  fast_mode="", sted=True, no_tsa=False, enc_layers=6, dec_layers=6, train_backbone=True, dropout=0.1):
@@ -338,6 +341,7 @@ class TubeDETR(nn.Module):
         if sted:
             self.sted_embed = _MLP(D_MODEL, D_MODEL, 2, 2, dropout=0.5)   # reference models/tubedetr.py:91
         self._engine = ResNet101Engine()
+        self.text_side_stream = True   # RoBERTa on its own CUDA stream, concurrent with the backbone (forward and backward)
         self.joint_backbone = True  # slow + fast frames share one backbone batch when their spatial sizes agree
         self.fast_l2_chunk = None   # frames per chunk for the L2-resident schedule of stem+layer1+layer2 in the no-grad pass
         self.text_autocast = False  # True: RoBERTa (library call) runs its GEMMs under bf16 autocast (bench.py sets it)
@@ -391,6 +395,21 @@ class TubeDETR(nn.Module):
         dev = frames.device
         B, T, k = len(durations), max(durations), self.stride
         n_clips = math.ceil(T / k)
+        # Text encoder (library call, reference transformer.py:250-263) on a side stream: its ~10^3 tiny kernels (L = 20 tokens)
+        # are independent of the backbone in forward AND backward (autograd replays a node on the stream it ran on), so they
+        # fill the launch gaps of the convolution GEMMs instead of extending the critical path.  Joined right before first use.
+        ids, am = self._tokenize(captions, dev)
+        side = self.text_side_stream
+        if side:
+            tstream = _TEXT_STREAMS.get(dev)
+            if tstream is None:
+                tstream = _TEXT_STREAMS[dev] = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            tstream.wait_stream(main)
+        with torch.cuda.stream(tstream if side else torch.cuda.current_stream(dev)):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.text_autocast):
+                hid = tr.text_encoder(input_ids=ids, attention_mask=am).last_hidden_state    # (B,L,768)
+
         sd = self._backbone_tensors()
         W = self._engine.prepare(sd)
         names = [n for n, p in sd.items() if isinstance(p, nn.Parameter) and p.requires_grad]
@@ -449,10 +468,10 @@ class TubeDETR(nn.Module):
         q_kpm = ~valid
         q_kpm[:, 0] = False
 
-        # text (library call, reference transformer.py:250-263) + resizer on our kernels
-        ids, am = self._tokenize(captions, dev)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.text_autocast):
-            hid = tr.text_encoder(input_ids=ids, attention_mask=am).last_hidden_state    # (B,L,768)
+        # text features -> resizer on our kernels
+        if side:
+            main.wait_stream(tstream)
+            hid.record_stream(main)
         L = hid.shape[1]
         r = ops.linear(hid.float().reshape(B * L, 768).to(torch.bfloat16), tr.resizer.fc.weight, tr.resizer.fc.bias, out_fp32=True)
         txt, _ = ops.add_layernorm(r, None, tr.resizer.layer_norm.weight, tr.resizer.layer_norm.bias, eps=1e-12)
