@@ -403,7 +403,7 @@ class TubeDETR(nn.Module):
         if side:
             tstream = _TEXT_STREAMS.get(dev)
             if tstream is None:
-                tstream = _TEXT_STREAMS[dev] = torch.cuda.Stream(device=dev)
+                tstream = _TEXT_STREAMS[dev] = torch.cuda.Stream(device=dev, priority=-1)   # high: its tiny kernels slip in at GEMM boundaries
             main = torch.cuda.current_stream(dev)
             tstream.wait_stream(main)
         with torch.cuda.stream(tstream if side else torch.cuda.current_stream(dev)):
