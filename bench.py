@@ -6,7 +6,8 @@ Contract (driver):  python bench.py --gpus N --steps K --warmup W   [--impl refe
 Workload = BASELINE.json configs[1]/[2]: per GPU B=1 clip, T=100 frames, stride k=4 (25 slow + 100 fast frames),
 res 352, 20-token caption, random-init seeded weights, bf16 tensor-core compute with fp32 master weights.
 A step = H2D-resident inputs -> TubeDETR.forward (encode) -> TubeDETR.forward (decode) -> SetCriterion -> backward
-(all parameter gradients incl. RoBERTa) -> (N>1) one NCCL all-reduce of the flat gradient buffer.
+(all parameter gradients incl. RoBERTa) -> (N>1) NCCL all-reduce of the flat gradient buffer (text-encoder slice overlapped
+with the backbone backward, the rest after it; captured in the same CUDA graph).
 `value`  : device-timed, inputs already in HBM.      `e2e`: same step fed from pinned host memory every step
 (H2D of both frame tensors, D2H of the loss), through the public module API.
 --impl reference times the CPU oracle (the reference algorithm restated in oracle/, pinned to the reference's own
@@ -162,9 +163,13 @@ class Step:
         self.inter_idx, self.time_mask = b["inter_idx"], b["time_mask"].to(device)
         self.crit.static = self.crit.prepare(self.targets, self.inter_idx, self.time_mask)
         # flat gradient buffer: every .grad is a view into it => ONE all-reduce, static addresses for graph replay
-        from tubedetr_b200.parallel import FlatGradBuffer
-        self.fgb = FlatGradBuffer(model.parameters(), device)
+        # (grouped text | transformer | backbone so the text slice can be reduced while the backbone backward still runs)
+        from tubedetr_b200.parallel import FlatGradBuffer, default_group_of
+        self.fgb = FlatGradBuffer(model.named_parameters(), device, groups=default_group_of)
         self.flat = self.fgb.flat
+        # N>1: all-reduce issued inside the step (and captured with it), overlapped with the backbone backward;
+        # TDB_OVERLAP=0 -> one serialised all-reduce after the replay
+        self.overlap = world > 1 and os.environ.get("TDB_OVERLAP", "1") != "0"
         self.loss = torch.zeros((), device=device)
         self.host_loss = torch.zeros((), pin_memory=True)
         self.copy_stream = torch.cuda.Stream()
@@ -183,12 +188,35 @@ class Step:
                    aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][self.keep]) for a in out["aux_outputs"]])
         losses = self.crit(out, self.targets, self.inter_idx, self.time_mask)
         total = sum(losses[k] * self.wd[k] for k in losses if k in self.wd)
-        total.backward()
-        if self.world > 1:
-            self.fgb.pack()
+        if self.overlap:
+            from tubedetr_b200.parallel import backward_overlapped
+            hid, feat = self.model.trunk_outputs()
+            backward_overlapped(total, self.fgb, hid, feat, side_stream=self.model.text_stream(self.flat.device))
+        else:
+            total.backward()
+            if self.world > 1:
+                self.fgb.pack()
         self.loss.copy_(total.detach())
 
     def capture(self):
+        if not self.overlap:
+            return self._capture()
+        err = None
+        try:
+            self._capture()
+        except Exception as e:
+            err = e
+        # every rank must take the same path: agree on the outcome before going on
+        ok = torch.tensor([0 if err is not None else 1], device=self.flat.device)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            sys.stderr.write(f"[bench] overlapped all-reduce step failed on some rank ({type(err).__name__ if err else 'peer'}: {err}); "
+                             "falling back to one serialised all-reduce after the step\n")
+            self.overlap, self.graph = False, None
+            torch.cuda.synchronize()
+            self._capture()
+
+    def _capture(self):
         from tubedetr_b200 import _lib
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -205,6 +233,8 @@ class Step:
                     self.body()
                 self.graph = g
             except Exception as e:  # keep going eagerly, say so
+                if self.overlap:
+                    raise              # retry without NCCL inside the capture first (capture())
                 sys.stderr.write(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
                 self.graph = None
                 torch.cuda.synchronize()
@@ -220,7 +250,7 @@ class Step:
             self.graph.replay()
         else:
             self.body()
-        if self.world > 1:
+        if self.world > 1 and not self.overlap:
             self.fgb.all_reduce()                        # the single gradient collective of the step
 
     def run_e2e(self, prefetched):
@@ -347,7 +377,7 @@ def run_ours(args):
     per_step_e2e = ms_e2e / args.steps
     h2d = st.host_fast.numel() * 4 + st.host_slow.numel() * 4
     cpu = None
-    if not args.skip_cpu:
+    if not args.skip_cpu and world == 1:      # the CPU baseline is reported on rank 0 at N=1 only
         cores = min(os.cpu_count() or 1, 32)   # eager CPU PyTorch stops scaling (and regresses) beyond ~32 threads
         nfr = 12
         sec = oracle_step_seconds(nfr, cores, steps=1)
@@ -359,7 +389,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world, "parallelism": f"dp{world}",
                        "l2": "inputs + activations of a step (>2 GB) exceed the 126 MB L2; no explicit flush",
-                       "cuda_graph": st.graph is not None, "numerics": "train mode (all reference dropouts active)",
+                       "cuda_graph": st.graph is not None, "allreduce": ("overlapped, in-graph" if st.overlap else "serialised after the step") if world > 1 else None,
+                       "numerics": "train mode (all reference dropouts active)",
                        "loss": loss_val},
             "e2e": {"value": world / (per_step_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": per_step_e2e},

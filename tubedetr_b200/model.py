@@ -373,6 +373,15 @@ class TubeDETR(nn.Module):
             c[key] = tuple(t.to(dev) for t in (dur, tt, valid, clip_of_t))
         return c[key]
 
+    def trunk_outputs(self):
+        """(RoBERTa last_hidden_state, backbone features of the slow frames) of the latest encode call: the tensors
+        `parallel.backward_overlapped` splits the backward at so the text-encoder gradients can be all-reduced while the
+        backbone backward runs."""
+        return self.__dict__.get("_trunk", (None, None))
+
+    def text_stream(self, device):
+        return _TEXT_STREAMS.get(device) if self.text_side_stream else None
+
     def _tokenize(self, captions, device):
         if isinstance(captions, (tuple, list)) and len(captions) == 2 and torch.is_tensor(captions[0]):
             return captions[0].to(device), captions[1].to(device)  # pre-tokenised (input_ids, attention_mask)
@@ -430,6 +439,8 @@ class TubeDETR(nn.Module):
             h, w = self._engine.last_hw
         else:
             feat, h, w, _ = self._engine.forward(frames.float(), W, save=False, tag="slow")
+        # the two trunk outputs a data-parallel step may cut the backward at (parallel.backward_overlapped)
+        self.__dict__["_trunk"] = (hid, feat) if torch.is_grad_enabled() else (None, None)
         n, HW = frames.shape[0], h * w
         assert n == B * n_clips, "with temporal stride every video of the batch needs the same number of clips"
         with torch.no_grad():
