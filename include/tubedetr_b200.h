@@ -155,6 +155,29 @@ int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, cons
                         const uint8_t* kpm, const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar,
                         void* workspace, int64_t ws_bytes, int F, int S, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer-side step on FLAT fp32 buffers (parameters, gradients, Adam moments, EMA copy share one element order).
+ * Replaces reference engine.py:147-161: torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step (main.py:410-414, three
+ * LR groups) + util/optim.py:8-25 update_ema.  SURVEY.md section 8(f).2.
+ *   tdb_grad_sqnorm      norm_out[0] = || grad ||_2 (device scalar, deterministic two-pass reduction, double accumulation)
+ *   tdb_adamw_ema_step   g *= min(max_norm / (norm + 1e-6), 1)  (grad_norm == NULL: no clipping);
+ *                        AdamW with decoupled weight decay and bias correction for step `step` (1-based);
+ *                        ema = ema * ema_decay + (1 - ema_decay) * p_new   (ema == NULL: skipped);
+ *                        param_bf16[i] = bf16(p_new)                      (NULL: skipped; GEMM operand copy of the new weights)
+ *   groups: element ranges [begin, end) of the flat buffers with their own lr / weight_decay (elements outside every
+ *           range keep their value: lr = wd = 0, moments still updated).
+ * ------------------------------------------------------------------------------------------------ */
+#define TDB_OPTIM_MAX_GROUPS 8
+typedef struct tdb_optim_group {
+  int64_t begin, end;
+  float lr, weight_decay;
+} tdb_optim_group;
+int64_t tdb_optim_workspace_bytes(void);
+int tdb_grad_sqnorm(const float* grad, int64_t n, void* workspace, int64_t ws_bytes, float* norm_out, void* stream);
+int tdb_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_bf16,
+                       int64_t n, const tdb_optim_group* groups, int ngroups, float beta1, float beta2, float eps,
+                       int64_t step, const float* grad_norm, float max_norm, float ema_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,7 +51,7 @@ def test_flat_gradient_allreduce_and_num_boxes_gloo():
     g = torch.Generator().manual_seed(5)
     x, y = torch.randn(12, 8, generator=g), torch.randn(12, 4, generator=g)
     ((net(x) - y) ** 2).mean().backward()
-    ref = torch.cat([p.grad.flatten() for p in net.parameters()])
+    ref = torch.cat([torch.cat([p.grad.flatten(), torch.zeros(-p.numel() % 8)]) for p in net.parameters()])
     for rank, flat, nb in res:
         torch.testing.assert_close(flat, ref, atol=1e-6, rtol=1e-5)
         assert nb == 4.0
@@ -84,7 +84,8 @@ def _worker_overlap(rank, world, port, q):
     fb = FlatGradBuffer(net.named_parameters(), groups=default_group_of)
     # group-major layout: text | rest | backbone, each one contiguous slice
     assert fb.group_ids == sorted(fb.group_ids)
-    assert fb.segment(GROUP_TEXT).numel() == sum(p.numel() for p in net.text_encoder.parameters())
+    assert fb.segment(GROUP_TEXT).numel() == sum((p.numel() + 7) // 8 * 8 for p in net.text_encoder.parameters())
+    assert all(o % 8 == 0 for o in fb.offsets)
     assert fb.segment(GROUP_REST, GROUP_BACKBONE).data_ptr() == fb.segment(GROUP_REST).data_ptr()
     g = torch.Generator().manual_seed(7)
     xt, xb, y = torch.randn(8, 6, generator=g), torch.randn(8, 5, generator=g), torch.randn(8, 3, generator=g)
@@ -123,9 +124,11 @@ def test_overlapped_backward_equals_plain_backward_gloo():
     xt, xb, y = torch.randn(8, 6, generator=g), torch.randn(8, 5, generator=g), torch.randn(8, 3, generator=g)
     ((net(xt, xb) - y) ** 2).mean().backward()
     named = sorted(enumerate(net.named_parameters()), key=lambda t: (default_group_of(t[1][0]), t[0]))
-    ref = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten() for _, (n, p) in named])
-    ref2 = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten() for _, (n, p) in named
-                      if "text_encoder" not in n])
+    def padded(p):
+        g = (p.grad if p.grad is not None else torch.zeros_like(p)).flatten()
+        return torch.cat([g, torch.zeros(-g.numel() % 8)])
+    ref = torch.cat([padded(p) for _, (n, p) in named])
+    ref2 = torch.cat([padded(p) for _, (n, p) in named if "text_encoder" not in n])
     for rank, flat, flat2, _ in res:
         torch.testing.assert_close(flat, ref, atol=1e-6, rtol=1e-5)
         torch.testing.assert_close(flat2, ref2, atol=1e-6, rtol=1e-5)

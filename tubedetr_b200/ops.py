@@ -22,6 +22,12 @@ def bf16_weight(w):
     return ent[1]
 
 
+def adopt_bf16_weight(w, wb):
+    """register an up-to-date bf16 copy of `w` produced elsewhere (optim.FusedAdamWEMA writes it in the optimizer kernel),
+    so the next forward does not launch a cast kernel for it"""
+    _WCACHE[(w.data_ptr(), tuple(w.shape))] = ((w._version,), wb)
+
+
 def _as_bf16(t):
     """bf16 view of a gradient.  Kernels that produce an fp32 gradient (LayerNorm backward) also write its bf16 copy and
     attach it as `_tdb_bf16`, so the consumer's GEMM operand needs no separate cast kernel."""

@@ -29,8 +29,10 @@ def default_group_of(name):
 class FlatGradBuffer:
     """Every trainable parameter owns a slice of ONE flat fp32 buffer, ordered group by group."""
 
-    def __init__(self, params, device=None, groups=None):
-        """params: iterable of tensors (one group) or, with groups=callable(name)->int, an iterable of (name, tensor)."""
+    def __init__(self, params, device=None, groups=None, align=8):
+        """params: iterable of tensors (one group) or, with groups=callable(name)->int, an iterable of (name, tensor).
+        Every parameter's slice starts at a multiple of `align` elements (zero padding in between: 32 B for fp32, 16 B for a
+        bf16 mirror of the same layout -> vector loads and TMA tensor maps can address each slice directly)."""
         if groups is None:
             items = [(0, p) for p in params if p.requires_grad]
         else:
@@ -39,25 +41,27 @@ class FlatGradBuffer:
         self.params = [items[i][1] for i in order]
         self.group_ids = [items[i][0] for i in order]
         device = device or self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=device)
-        self.bounds = {}                      # group -> (lo, hi) element range
-        o = 0
-        for g, p in zip(self.group_ids, self.params):
-            lo, hi = self.bounds.get(g, (o, o))
-            self.bounds[g] = (lo, o + p.numel())
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
-            o += p.numel()
+        pad = lambda n: (n + align - 1) // align * align
+        self.offsets, o = [], 0
+        for p in self.params:
+            self.offsets.append(o)
+            o += pad(p.numel())
+        self.flat = torch.zeros(o, dtype=torch.float32, device=device)
+        self.bounds = {}                      # group -> (lo, hi) element range (hi includes the last slice's padding)
+        for g, p, off in zip(self.group_ids, self.params, self.offsets):
+            lo, hi = self.bounds.get(g, (off, off))
+            self.bounds[g] = (lo, off + pad(p.numel()))
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
         self._views = None
 
     def zero(self):
         self.flat.zero_()
 
-    def views(self):
-        out, o = [], 0
-        for p in self.params:
-            out.append(self.flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
-        return out
+    def views(self, flat=None):
+        """per-parameter views into `flat` (default: the gradient buffer; any tensor of the same length works: parameters,
+        Adam moments, an EMA copy, a bf16 mirror)"""
+        flat = self.flat if flat is None else flat
+        return [flat[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
 
     def group_params(self, *gs):
         return [p for g, p in zip(self.group_ids, self.params) if g in gs]
