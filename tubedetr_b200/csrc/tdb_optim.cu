@@ -173,18 +173,22 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_ema_kernel(const __grid_con
 
 using namespace tdb;
 
-static int optim_blocks() { return tdb_num_sms() * 8; }
+constexpr int OPT_MAX_BLOCKS = 4096;          // workspace size must not depend on a device query (callable before any launch)
+static int optim_blocks() {
+  int nb = tdb_num_sms() * 8;
+  return nb < 1 ? 1 : (nb > OPT_MAX_BLOCKS ? OPT_MAX_BLOCKS : nb);
+}
 
-extern "C" int64_t tdb_optim_workspace_bytes(void) { return (int64_t)optim_blocks() * (int64_t)sizeof(double); }
+extern "C" int64_t tdb_optim_workspace_bytes(void) { return (int64_t)OPT_MAX_BLOCKS * (int64_t)sizeof(double); }
 
 extern "C" int tdb_grad_sqnorm(const float* grad, int64_t n, void* workspace, int64_t ws_bytes, float* norm_out, void* stream_) {
   int rc = tdb_init_once();
   if (rc) return rc;
   TDB_REQUIRE(grad && workspace && norm_out && n > 0, "tdb_grad_sqnorm: null argument");
   TDB_REQUIRE(((uintptr_t)grad & 15) == 0, "tdb_grad_sqnorm: grad must be 16-byte aligned");
-  TDB_REQUIRE(ws_bytes >= tdb_optim_workspace_bytes(), "tdb_grad_sqnorm: workspace too small");
   cudaStream_t st = (cudaStream_t)stream_;
   const int nb = optim_blocks();
+  TDB_REQUIRE(ws_bytes >= (int64_t)nb * (int64_t)sizeof(double), "tdb_grad_sqnorm: workspace too small");
   TDB_CHECK_CUDA(tdb_launch(sqnorm_partials_kernel, dim3(nb), dim3(OPT_THREADS), 0, st, grad, (long long)n, (double*)workspace));
   TDB_CHECK_CUDA(tdb_launch(sqnorm_final_kernel, dim3(1), dim3(OPT_THREADS), 0, st, (const double*)workspace, nb, norm_out));
   TDB_CHECK_CUDA(cudaGetLastError());
