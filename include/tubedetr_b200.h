@@ -155,6 +155,13 @@ int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, cons
                         const uint8_t* kpm, const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar,
                         void* workspace, int64_t ws_bytes, int F, int S, float scale, void* stream);
 
+/* Backward of the one-query-per-frame attention core (the cross-attention above; K/V are re-projected by tdb_gemm first):
+ *   q, dout [F][256] bf16;  k, v [F*S][256] bf16 projected keys / values;  p [F][8][S] fp32 probabilities (before dropout);
+ *   keep/keep_scale as in forward;  dpbar [F][S] fp32 gradient of the head-mean (post-dropout) probabilities or NULL.
+ *   Outputs dq [F][256], dk, dv [F*S][256] bf16.  One streaming pass over V and one over K per frame; deterministic. */
+int tdb_xattn_bwd(const void* q, const void* k, const void* v, const void* dout, const float* p, const uint8_t* keep,
+                  float keep_scale, const float* dpbar, void* dq, void* dk, void* dv, int F, int S, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimizer-side step on FLAT fp32 buffers (parameters, gradients, Adam moments, EMA copy share one element order).
  * Replaces reference engine.py:147-161: torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step (main.py:410-414, three

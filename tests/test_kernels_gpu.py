@@ -246,3 +246,55 @@ def test_mha_attention_dropout_fwd_bwd():
         _close(got, ref, 2e-2)
         a = (got.float() * ref).sum() / (ref * ref).sum()
         assert abs(a.item() - 1) < 5e-3, a.item()
+
+
+@pytest.mark.parametrize("F,S,drop", [(100, 141, 0.0), (7, 59, 0.1), (3, 200, 0.1), (400, 141, 0.0)])
+def test_xattn_bwd_streaming_kernel(F, S, drop):
+    """one-query-per-frame attention backward (tdb_xattn_bwd) vs autograd through fp32 torch on the same bf16 operands,
+    with key padding, the head-mean-probability gradient and (optionally) attention dropout"""
+    from tubedetr_b200 import kernels as K
+    H, d = 8, 256
+    scale = 1 / math.sqrt(32)
+    q, k, v = _r((F, 1, d), 60), _r((F, S, d), 61), _r((F, S, d), 62)
+    kpm = torch.zeros(F, S, dtype=torch.uint8, device="cuda")
+    kpm[:, S - S // 5:] = 1
+    kpm[0] = 0
+    keep = None
+    if drop > 0:
+        keep = (torch.rand(F, H, 1, S, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6)) >= drop).to(torch.uint8)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    qh = (qf * scale).view(F, 1, H, 32).transpose(1, 2)
+    kh, vh = kf.view(F, S, H, 32).transpose(1, 2), vf.view(F, S, H, 32).transpose(1, 2)
+    rp = (qh @ kh.transpose(-1, -2)).masked_fill(kpm[:, None, None, :].bool(), float("-inf")).softmax(-1)
+    rpd = rp * keep.float() / (1 - drop) if keep is not None else rp
+    ro = (rpd @ vh).transpose(1, 2).reshape(F, 1, d)
+    do = _r((F, 1, d), 63)
+    dpbar = _r((F, 1, S), 64, torch.float32)
+    (ro * do.float()).sum().add((rpd.mean(1) * dpbar).sum()).backward()
+    p = rp.detach().contiguous()
+    dq = torch.empty(F, d, dtype=torch.bfloat16, device="cuda")
+    dk, dv = torch.empty(F * S, d, dtype=torch.bfloat16, device="cuda"), torch.empty(F * S, d, dtype=torch.bfloat16, device="cuda")
+    K.xattn_bwd(q.view(F, d), k.view(-1, d), v.view(-1, d), do.view(F, d), p, dpbar, dq, dk, dv, F, S, scale, keep=keep,
+                keep_scale=1 / (1 - drop) if drop > 0 else 1.0)
+    for got, ref in ((dq.view_as(q), qf.grad), (dk.view_as(k), kf.grad), (dv.view_as(v), vf.grad)):
+        _close(got, ref, 2e-2)
+        a = (got.float() * ref).sum() / (ref * ref).sum()
+        assert abs(a.item() - 1) < 5e-3, a.item()
+    # padded keys receive exactly zero key / value gradient; no dpbar, second run bit-identical (deterministic reductions)
+    assert (dk.view(F, S, d)[1:, S - S // 5:] == 0).all() and (dv.view(F, S, d)[1:, S - S // 5:] == 0).all()
+    dq2, dk2, dv2 = torch.empty_like(dq), torch.empty_like(dk), torch.empty_like(dv)
+    K.xattn_bwd(q.view(F, d), k.view(-1, d), v.view(-1, d), do.view(F, d), p, dpbar, dq2, dk2, dv2, F, S, scale, keep=keep,
+                keep_scale=1 / (1 - drop) if drop > 0 else 1.0)
+    assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)
+
+
+@pytest.mark.parametrize("rows,N", [(3525, 2048), (14100, 256), (1000, 768), (20, 256), (37, 64)])
+def test_colsum_vector_path(rows, N):
+    from tubedetr_b200 import kernels as K
+    x = _r((rows, N), 70)
+    out = torch.zeros(N, device="cuda")
+    K.colsum_bf16(x, out)
+    _close(out, x.float().sum(0), 1e-4)
+    out2 = torch.zeros(N, device="cuda")
+    K.colsum_bf16(x, out2)
+    assert torch.equal(out, out2)

@@ -32,69 +32,134 @@ struct AttnParams {
   float scale;
 };
 
+// Shared-memory layout of the row kernels (fp32): [32][Lkp] transposed operand (odd pitch: conflict-free column reads),
+// [Lk4][32] row-major operand (rows >= Lk zero), [warps][Lk4] per-warp probability row, [warps][32] per-warp query row.
+constexpr int kMaxChunks = 8;            // Lk <= 256 keys in registers (32 lanes x 8 chunks)
+
+// stage head h of two bf16 [L][ld] matrices: T -> transposed [32][Lkp], R -> row-major [Lk4][32]; 16-byte global loads
+// (thread = one 8-channel group of one row: a row of a head is 64 B = 4 groups)
+__device__ __forceinline__ void stage_head(const bf16* __restrict__ tsrc, long long ldt, const bf16* __restrict__ rsrc, long long ldr,
+                                           int Lk, int Lkp, int Lk4, float* __restrict__ tdst, float* __restrict__ rdst) {
+  for (int i = threadIdx.x; i < Lk4 * 4; i += blockDim.x) {
+    const int j = i >> 2, g = i & 3;
+    float tv[8], rv[8];
+    if (j < Lk) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(tsrc + (long long)j * ldt) + g);
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(rsrc + (long long)j * ldr) + g);
+      float2 x;
+      x = unpack_bf16x2(a.x); tv[0] = x.x; tv[1] = x.y;
+      x = unpack_bf16x2(a.y); tv[2] = x.x; tv[3] = x.y;
+      x = unpack_bf16x2(a.z); tv[4] = x.x; tv[5] = x.y;
+      x = unpack_bf16x2(a.w); tv[6] = x.x; tv[7] = x.y;
+      x = unpack_bf16x2(b.x); rv[0] = x.x; rv[1] = x.y;
+      x = unpack_bf16x2(b.y); rv[2] = x.x; rv[3] = x.y;
+      x = unpack_bf16x2(b.z); rv[4] = x.x; rv[5] = x.y;
+      x = unpack_bf16x2(b.w); rv[6] = x.x; rv[7] = x.y;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) tdst[(g * 8 + t) * Lkp + j] = tv[t];
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) rv[t] = 0.f;
+    }
+    float4* r4 = reinterpret_cast<float4*>(rdst + j * HD + g * 8);
+    r4[0] = make_float4(rv[0], rv[1], rv[2], rv[3]);
+    r4[1] = make_float4(rv[4], rv[5], rv[6], rv[7]);
+  }
+}
+
+// s[c] = sum_d qrow[d] * T[d][c*32 + lane]  for the chunks c < nc (register blocked: one broadcast read of q per d)
+__device__ __forceinline__ void row_scores(const float* __restrict__ qrow, const float* __restrict__ tmat, int Lkp, int lane, int nc,
+                                           float (&s)[kMaxChunks]) {
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) s[c] = 0.f;
+#pragma unroll 8
+  for (int d = 0; d < HD; ++d) {
+    const float qv = qrow[d];
+    const float* tr = tmat + d * Lkp + lane;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c)
+      if (c < nc) s[c] = fmaf(qv, tr[c * 32], s[c]);
+  }
+}
+
+// acc(lane = d) = sum_j w[j] * R[j][d], four independent accumulators, w read as broadcast float4
+__device__ __forceinline__ float row_combine(const float* __restrict__ w, const float* __restrict__ rmat, int Lk4, int lane) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int j = 0; j < Lk4; j += 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(w + j);
+    const float* r = rmat + j * HD + lane;
+    a0 = fmaf(w4.x, r[0], a0);
+    a1 = fmaf(w4.y, r[HD], a1);
+    a2 = fmaf(w4.z, r[2 * HD], a2);
+    a3 = fmaf(w4.w, r[3 * HD], a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
 __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams a) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm[];
   const int Lkp = a.Lk | 1;                 // odd pitch: conflict-free transposed K
+  const int Lk4 = (a.Lk + 3) & ~3;
+  const int nwarps = blockDim.x >> 5;
   float* kt = sm;                           // [32][Lkp]
-  float* vs = kt + HD * Lkp;                // [Lk][32]
-  float* prow = vs + a.Lk * HD;             // [warps][Lk]
+  float* vs = kt + HD * Lkp + (4 - ((HD * Lkp) & 3)) % 4;   // [Lk4][32], 16-byte aligned
+  float* prow = vs + Lk4 * HD;              // [warps][Lk4]
+  float* qsm = prow + nwarps * Lk4;         // [warps][32]
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const bf16* kb = a.k + (long long)b * a.Lk * a.ldk + h * HD;
-  const bf16* vb = a.v + (long long)b * a.Lk * a.ldv + h * HD;
-  for (int i = threadIdx.x; i < a.Lk * HD; i += blockDim.x) {
-    int j = i >> 5, d = i & 31;
-    kt[d * Lkp + j] = __bfloat162float(kb[(long long)j * a.ldk + d]);
-    vs[j * HD + d] = __bfloat162float(vb[(long long)j * a.ldv + d]);
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_head(a.k + (long long)b * a.Lk * a.ldk + h * HD, a.ldk, a.v + (long long)b * a.Lk * a.ldv + h * HD, a.ldv, a.Lk, Lkp, Lk4, kt, vs);
   __syncthreads();
   const uint8_t* mk = a.kpm ? a.kpm + (long long)b * a.Lk : nullptr;
-  float* pw = prow + warp * a.Lk;
+  float* pw = prow + warp * Lk4;
+  float* qw = qsm + warp * HD;
+  const int nc = (a.Lk + 31) >> 5;
+  if (lane < Lk4 - a.Lk) pw[a.Lk + lane] = 0.f;          // zero tail of the probability row (read by row_combine)
   for (int i = blockIdx.y * nwarps + warp; i < a.Lq; i += gridDim.y * nwarps) {
     const bf16* qr = a.q + ((long long)b * a.Lq + i) * a.ldq + h * HD;
-    float qd = __bfloat162float(qr[lane]) * a.scale;
+    qw[lane] = __bfloat162float(qr[lane]) * a.scale;
+    __syncwarp();
+    float s[kMaxChunks];
+    row_scores(qw, kt, Lkp, lane, nc, s);
     float mx = -INFINITY;
-    for (int j0 = 0; j0 < a.Lk; j0 += 32) {
-      int j = j0 + lane;
-      float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) {
-        float qv = __shfl_sync(0xffffffffu, qd, d);
-        if (j < a.Lk) s += qv * kt[d * Lkp + j];
-      }
-      if (j < a.Lk) {
-        if (mk && mk[j]) s = -INFINITY;
-        pw[j] = s;
-        mx = fmaxf(mx, s);
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int j = c * 32 + lane;
+      if (c < nc) {
+        if (j >= a.Lk || (mk && mk[j])) s[c] = -INFINITY;
+        mx = fmaxf(mx, s[c]);
       }
     }
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int j = lane; j < a.Lk; j += 32) {
-      float e = (mx == -INFINITY) ? 0.f : __expf(pw[j] - mx);
-      pw[j] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    float inv = 1.f / sum;  // all keys masked -> NaN, exactly like the reference softmax
-    __syncwarp();
-    const long long prow = (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
-    float* pg = a.p + prow;
-    for (int j = lane; j < a.Lk; j += 32) pg[j] = pw[j] * inv;
-    if (a.keep != nullptr) {           // P <- P * keep / (1 - p); the context uses the dropped probabilities
-      const uint8_t* kp = a.keep + prow;
-      float* pd = a.pdrop + prow;
-      for (int j = lane; j < a.Lk; j += 32) {
-        float e = kp[j] ? pw[j] * a.keep_scale : 0.f;
-        pw[j] = e;
-        pd[j] = e * inv;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c)
+      if (c < nc) {
+        s[c] = (mx == -INFINITY || s[c] == -INFINITY) ? 0.f : __expf(s[c] - mx);
+        sum += s[c];
       }
-      __syncwarp();
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;  // all keys masked -> NaN, exactly like the reference softmax
+    const long long prow_off = (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    float* pg = a.p + prow_off;
+    const uint8_t* kp = a.keep ? a.keep + prow_off : nullptr;
+    float* pd = a.keep ? a.pdrop + prow_off : nullptr;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int j = c * 32 + lane;
+      if (c < nc && j < a.Lk) {
+        float e = s[c];
+        pg[j] = e * inv;
+        if (kp) {                   // P <- P * keep / (1 - p); the context uses the dropped probabilities
+          e = kp[j] ? e * a.keep_scale : 0.f;
+          pd[j] = e * inv;
+        }
+        pw[j] = e;
+      }
     }
-    float acc = 0.f;
-    for (int j = 0; j < a.Lk; ++j) acc += pw[j] * vs[j * HD + lane];
+    __syncwarp();
+    const float acc = row_combine(pw, vs, Lk4, lane);
     a.o[((long long)b * a.Lq + i) * a.ldo + h * HD + lane] = __float2bfloat16(acc * inv);
     __syncwarp();
   }
@@ -133,56 +198,59 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
   pdl_trigger();
   extern __shared__ float sm[];
   const int Lkp = a.Lk | 1;
+  const int Lk4 = (a.Lk + 3) & ~3;
+  const int nwarps = blockDim.x >> 5;
   float* vt = sm;                    // [32][Lkp]   V transposed
-  float* ks = vt + HD * Lkp;         // [Lk][32]
-  float* drow = ks + a.Lk * HD;      // [warps][Lk]
+  float* ks = vt + HD * Lkp + (4 - ((HD * Lkp) & 3)) % 4;   // [Lk4][32]
+  float* drow = ks + Lk4 * HD;       // [warps][Lk4]
+  float* dosm = drow + nwarps * Lk4; // [warps][32]
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const bf16* kb = a.k + (long long)b * a.Lk * a.ldk + h * HD;
-  const bf16* vb = a.v + (long long)b * a.Lk * a.ldv + h * HD;
-  for (int i = threadIdx.x; i < a.Lk * HD; i += blockDim.x) {
-    int j = i >> 5, d = i & 31;
-    vt[d * Lkp + j] = __bfloat162float(vb[(long long)j * a.ldv + d]);
-    ks[j * HD + d] = __bfloat162float(kb[(long long)j * a.ldk + d]);
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_head(a.v + (long long)b * a.Lk * a.ldv + h * HD, a.ldv, a.k + (long long)b * a.Lk * a.ldk + h * HD, a.ldk, a.Lk, Lkp, Lk4, vt, ks);
   __syncthreads();
-  float* dw = drow + warp * a.Lk;
+  float* dw = drow + warp * Lk4;
+  float* dov = dosm + warp * HD;
+  const int nc = (a.Lk + 31) >> 5;
   const float invH = 1.f / a.H;
+  if (lane < Lk4 - a.Lk) dw[a.Lk + lane] = 0.f;
   for (int i = blockIdx.y * nwarps + warp; i < a.Lq; i += gridDim.y * nwarps) {
-    float dod = __bfloat162float(a.dout[((long long)b * a.Lq + i) * a.lddo + h * HD + lane]);
-    const float* pr = a.p + (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    dov[lane] = __bfloat162float(a.dout[((long long)b * a.Lq + i) * a.lddo + h * HD + lane]);
+    __syncwarp();
+    const long long roff = (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+    const float* pr = a.p + roff;
     const float* dpb = a.dpbar ? a.dpbar + ((long long)b * a.Lq + i) * a.Lk : nullptr;
-    const uint8_t* kr = a.keep ? a.keep + (((long long)b * a.H + h) * a.Lq + i) * a.Lk : nullptr;
+    const uint8_t* kr = a.keep ? a.keep + roff : nullptr;
+    float dp[kMaxChunks], pj[kMaxChunks];
+    row_scores(dov, vt, Lkp, lane, nc, dp);
     float rs = 0.f;
-    for (int j0 = 0; j0 < a.Lk; j0 += 32) {
-      int j = j0 + lane;
-      float dp = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) {
-        float dv = __shfl_sync(0xffffffffu, dod, d);
-        if (j < a.Lk) dp += dv * vt[d * Lkp + j];
-      }
-      if (j < a.Lk) {
-        if (dpb) dp += dpb[j] * invH;
-        if (kr) dp = kr[j] ? dp * a.keep_scale : 0.f;      // d(pre-dropout P) = d(post) * keep / (1 - p)
-        float pj = pr[j];
-        dw[j] = dp;
-        rs += pj * dp;
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int j = c * 32 + lane;
+      pj[c] = 0.f;
+      if (c < nc && j < a.Lk) {
+        float d = dp[c];
+        if (dpb) d += dpb[j] * invH;
+        if (kr) d = kr[j] ? d * a.keep_scale : 0.f;      // d(pre-dropout P) = d(post) * keep / (1 - p)
+        pj[c] = pr[j];
+        dp[c] = d;
+        rs += pj[c] * d;
       }
     }
     rs = warp_sum(rs);
-    float* dsg = a.ds + (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
-    float* pdg = kr ? a.pd_scratch + (((long long)b * a.H + h) * a.Lq + i) * a.Lk : nullptr;
-    for (int j = lane; j < a.Lk; j += 32) {
-      float pj = pr[j];
-      float d = pj > 0.f ? pj * (dw[j] - rs) : 0.f;  // masked keys have P = 0 exactly
-      dw[j] = d;
-      dsg[j] = d;
-      if (pdg) pdg[j] = kr[j] ? pj * a.keep_scale : 0.f;
+    float* dsg = a.ds + roff;
+    float* pdg = kr ? a.pd_scratch + roff : nullptr;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int j = c * 32 + lane;
+      if (c < nc && j < a.Lk) {
+        const float d = pj[c] > 0.f ? pj[c] * (dp[c] - rs) : 0.f;  // masked keys have P = 0 exactly
+        dw[j] = d;
+        dsg[j] = d;
+        if (pdg) pdg[j] = kr[j] ? pj[c] * a.keep_scale : 0.f;
+      }
     }
     __syncwarp();
-    float acc = 0.f;
-    for (int j = 0; j < a.Lk; ++j) acc += dw[j] * ks[j * HD + lane];
+    const float acc = row_combine(dw, ks, Lk4, lane);
     a.dq[((long long)b * a.Lq + i) * a.lddq + h * HD + lane] = __float2bfloat16(acc * a.scale);
     __syncwarp();
   }
@@ -251,12 +319,12 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_col_kernel(const AttnBwd
 using namespace tdb;
 
 static size_t attn_smem_bytes(int Lk, int threads) {
-  int Lkp = Lk | 1;
-  return sizeof(float) * ((size_t)HD * Lkp + (size_t)Lk * HD + (size_t)(threads / 32) * Lk);
+  int Lkp = Lk | 1, Lk4 = (Lk + 3) & ~3;
+  return sizeof(float) * ((size_t)HD * Lkp + 4 + (size_t)Lk4 * HD + (size_t)(threads / 32) * (Lk4 + HD));
 }
 static int attn_grid_y(int BH, int Lq) {
   int per = (Lq + (kAttnThreads / 32) - 1) / (kAttnThreads / 32);
-  int want = (2 * 148 + BH - 1) / BH;
+  int want = (4 * 148 + BH - 1) / BH;      // ~4 CTAs per SM (42 KB of shared memory each at Lk = 141): latency hiding across CTAs
   if (want < 1) want = 1;
   return want < per ? want : per;
 }
@@ -277,7 +345,8 @@ extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   TDB_REQUIRE(!keep || pdrop, "tdb_mha_fwd: dropout needs the pdrop output");
   TDB_REQUIRE(q && k && v && o && p && B > 0 && H > 0 && Lq > 0 && Lk > 0, "tdb_mha_fwd: bad args");
   size_t smem = attn_smem_bytes(Lk, kAttnThreads);
-  TDB_REQUIRE(smem <= 200 * 1024, "tdb_mha_fwd: Lk=%d too long for the single-CTA kernel", Lk);
+  TDB_REQUIRE(Lk <= 32 * tdb::kMaxChunks, "tdb_mha_fwd: Lk=%d > %d keys", Lk, 32 * tdb::kMaxChunks);
+  TDB_REQUIRE((((uintptr_t)k | (uintptr_t)v) & 15) == 0 && ldk % 8 == 0 && ldv % 8 == 0, "tdb_mha_fwd: k/v need 16-byte aligned head slices");
   int rc = attn_init();
   if (rc) return rc;
   AttnParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, kpm, (bf16*)o, ldo, p, pdrop, keep, keep_scale, B, H, Lq, Lk, scale};
@@ -301,7 +370,8 @@ extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
                            float scale, void* stream_) {
   TDB_REQUIRE(q && k && v && dout && p && ds_scratch && dq && dk && dv, "tdb_mha_bwd: null pointer");
   size_t smem = attn_smem_bytes(Lk, kAttnThreads);
-  TDB_REQUIRE(smem <= 200 * 1024, "tdb_mha_bwd: Lk=%d too long", Lk);
+  TDB_REQUIRE(Lk <= 32 * tdb::kMaxChunks, "tdb_mha_bwd: Lk=%d > %d keys", Lk, 32 * tdb::kMaxChunks);
+  TDB_REQUIRE((((uintptr_t)k | (uintptr_t)v) & 15) == 0 && ldk % 8 == 0 && ldv % 8 == 0, "tdb_mha_bwd: k/v need 16-byte aligned head slices");
   int rc = attn_init();
   if (rc) return rc;
   TDB_REQUIRE(!keep || pd_scratch, "tdb_mha_bwd: dropout needs pd_scratch");

@@ -374,6 +374,67 @@ __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, int
   partial[(long long)blockIdx.y * N + c + 1] = s1;
 }
 
+// 16-byte form of stage 1 (N % 8 == 0, ld % 8 == 0, 16-byte aligned base): block = 32 column-lanes (8 columns each = one
+// 256-column slab) x 8 row-lanes; every thread keeps 4 independent 16-byte loads in flight, the 8 row-lanes are combined in
+// shared memory in fixed order.  (The 4-byte form above ran at 0.3 TB/s, latency bound: profiles/r01_kernel_table.txt.)
+__global__ void __launch_bounds__(256) colsum_bf16_v8_kernel(const bf16* __restrict__ x, long long ld, int rows, int N,
+                                                             float* __restrict__ partial, int rows_per_block) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[8][32][9];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  if (c < N) {
+    const bf16* base = x + c;
+    int r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (long long)(r + 8 * u) * ld));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 a = unpack_bf16x2(v[u].x), b = unpack_bf16x2(v[u].y), cc = unpack_bf16x2(v[u].z), d = unpack_bf16x2(v[u].w);
+        acc[0] += a.x;
+        acc[1] += a.y;
+        acc[2] += b.x;
+        acc[3] += b.y;
+        acc[4] += cc.x;
+        acc[5] += cc.y;
+        acc[6] += d.x;
+        acc[7] += d.y;
+      }
+    }
+    for (; r < r1; r += 8) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (long long)r * ld));
+      float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), cc = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+      acc[0] += a.x;
+      acc[1] += a.y;
+      acc[2] += b.x;
+      acc[3] += b.y;
+      acc[4] += cc.x;
+      acc[5] += cc.y;
+      acc[6] += d.x;
+      acc[7] += d.y;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) red[threadIdx.y][threadIdx.x][t] = acc[t];
+  __syncthreads();
+  // 256 threads -> 256 columns of the slab
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int col = blockIdx.x * 256 + tid;
+  if (col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][tid >> 3][tid & 7];
+    partial[(long long)blockIdx.y * N + col] = t;
+  }
+}
+
 }  // namespace tdb
 
 using namespace tdb;
@@ -461,6 +522,12 @@ extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void
   int blocks = tdb_layernorm_bwd_blocks(rows);
   TDB_CHECK_CUDA(tdb_launch(layernorm_bwd_kernel<256>, dim3(blocks), dim3(256), 0, STREAM, dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows));
   TDB_CHECK_CUDA(cudaGetLastError());
+  if (dgamma && dbeta == dgamma + D) {   // [dgamma | dbeta] contiguous: the partial rows [2D] reduce in ONE launch
+    TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((2 * D + 31) / 32), dim3(32, 8), 0, STREAM, partial, blocks, 2 * D, 2 * D, dgamma, accumulate));
+    TDB_CHECK_CUDA(cudaGetLastError());
+    tdb_count_launch(2);
+    return TDB_OK;
+  }
   if (dgamma) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial, blocks, 2 * D, D, dgamma, accumulate));
   if (dbeta) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial + D, blocks, 2 * D, D, dbeta, accumulate));
   TDB_CHECK_CUDA(cudaGetLastError());
@@ -472,6 +539,21 @@ extern "C" int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float
   TDB_REQUIRE(x && partial && out && rows > 0 && N > 0 && nparts > 0, "tdb_colsum_bf16: bad args");
   TDB_REQUIRE(N % 2 == 0 && ld % 2 == 0, "tdb_colsum_bf16: N and ld must be even");
   int rpb = (rows + nparts - 1) / nparts;
+  if (N % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0) {
+    // fewer, fatter parts (>= 64 rows each, enough CTAs for two waves): a shorter second stage; nparts only bounds the workspace
+    const int slabs = (N + 255) / 256;
+    int want = (2 * 148 + slabs - 1) / slabs;
+    int np = want < nparts ? want : nparts;
+    const int by_rows = (rows + 63) / 64;
+    if (np > by_rows) np = by_rows;
+    rpb = ((rows + np - 1) / np + 7) / 8 * 8;
+    np = (rows + rpb - 1) / rpb;
+    TDB_CHECK_CUDA(tdb_launch(colsum_bf16_v8_kernel, dim3(slabs, np), dim3(32, 8), 0, STREAM, (const bf16*)x, ld, rows, N, partial, rpb));
+    TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((N + 31) / 32), dim3(32, 8), 0, STREAM, partial, np, N, N, out, accumulate));
+    TDB_CHECK_CUDA(cudaGetLastError());
+    tdb_count_launch(2);
+    return TDB_OK;
+  }
   dim3 grid((N / 2 + 127) / 128, nparts);
   TDB_CHECK_CUDA(tdb_launch(colsum_bf16_kernel, dim3(grid), dim3(128), 0, STREAM, (const bf16*)x, ld, rows, N, partial, rpb));
   TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((N + 31) / 32), dim3(32, 8), 0, STREAM, partial, nparts, N, N, out, accumulate));

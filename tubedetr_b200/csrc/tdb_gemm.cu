@@ -975,6 +975,7 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------ split-K reduction (fixed order => deterministic)
+// generic scalar form (any N / taps)
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
                                      const float* __restrict__ rowscale, float* __restrict__ out, int taps,
                                      int accumulate) {
@@ -996,6 +997,69 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
     o = ((long long)m * cin + c) * taps + tap;
   }
   out[o] = accumulate ? out[o] + s : s;
+}
+
+// float4 form (N % 4 == 0 and (N / taps) % 4 == 0): the partials were just written by the wgrad GEMM and mostly sit in L2, so
+// this kernel is bound by load latency, not bandwidth -- every thread keeps 4 independent 16-byte loads in flight (the scalar
+// form above serialises one 4-byte load per split: measured 10.9 us per launch at 1.2 TB/s, profiles/r01_kernel_table.txt).
+// The additions keep the split order 0,1,2,... so results are bit-identical to the scalar form.
+__device__ __forceinline__ void add4(float4& s, const float4 v) {
+  s.x += v.x;
+  s.y += v.y;
+  s.z += v.z;
+  s.w += v.w;
+}
+__global__ void __launch_bounds__(256) splitk_reduce4_kernel(const float4* __restrict__ part, int splits, long long total4, int N,
+                                                             const float* __restrict__ rowscale, float* __restrict__ out, int taps,
+                                                             int accumulate) {
+  pdl_wait();
+  pdl_trigger();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const long long e = idx << 2;
+  const int m = (int)(e / N);
+  const int n = (int)(e - (long long)m * N);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* p = part + idx;
+  int i = 0;
+  for (; i + 4 <= splits; i += 4) {
+    const float4 a = __ldcs(p + (long long)i * total4);
+    const float4 b = __ldcs(p + (long long)(i + 1) * total4);
+    const float4 c = __ldcs(p + (long long)(i + 2) * total4);
+    const float4 d = __ldcs(p + (long long)(i + 3) * total4);
+    add4(s, a);
+    add4(s, b);
+    add4(s, c);
+    add4(s, d);
+  }
+  for (; i < splits; ++i) add4(s, __ldcs(p + (long long)i * total4));
+  if (rowscale) {
+    const float r = rowscale[m];
+    s.x *= r;
+    s.y *= r;
+    s.z *= r;
+    s.w *= r;
+  }
+  if (taps > 1) {  // [Cout][tap][Cin] -> torch [Cout][Cin][kh][kw]: 4 consecutive cin of one tap -> stride `taps`
+    const int cin = N / taps;
+    const int tap = n / cin;
+    const int c = n - tap * cin;
+    float* o = out + ((long long)m * cin + c) * taps + tap;
+    if (accumulate) {
+      s.x += o[0];
+      s.y += o[taps];
+      s.z += o[2 * taps];
+      s.w += o[3 * taps];
+    }
+    o[0] = s.x;
+    o[taps] = s.y;
+    o[2 * taps] = s.z;
+    o[3 * taps] = s.w;
+  } else {
+    float4* o = reinterpret_cast<float4*>(out + e);
+    if (accumulate) add4(s, *o);
+    *o = s;
+  }
 }
 
 }  // namespace tdb
@@ -1347,8 +1411,15 @@ extern "C" int tdb_splitk_reduce(const float* part, int splits, int M, int N, co
   TDB_REQUIRE(part && out && splits >= 1 && M > 0 && N > 0 && taps >= 1 && N % taps == 0, "tdb_splitk_reduce: bad args");
   long long total = (long long)M * N;
   int threads = 256;
-  long long blocks = (total + threads - 1) / threads;
-  TDB_CHECK_CUDA(tdb_launch(tdb::splitk_reduce_kernel, dim3((unsigned)blocks), dim3(threads), 0, (cudaStream_t)stream_, part, splits, M, N, rowscale, out, taps, accumulate));
+  const bool vec = N % 4 == 0 && (N / taps) % 4 == 0 && (((uintptr_t)part | (uintptr_t)out) & 15) == 0;
+  if (vec) {
+    long long total4 = total >> 2;
+    long long blocks = (total4 + threads - 1) / threads;
+    TDB_CHECK_CUDA(tdb_launch(tdb::splitk_reduce4_kernel, dim3((unsigned)blocks), dim3(threads), 0, (cudaStream_t)stream_, (const float4*)part, splits, total4, N, rowscale, out, taps, accumulate));
+  } else {
+    long long blocks = (total + threads - 1) / threads;
+    TDB_CHECK_CUDA(tdb_launch(tdb::splitk_reduce_kernel, dim3((unsigned)blocks), dim3(threads), 0, (cudaStream_t)stream_, part, splits, M, N, rowscale, out, taps, accumulate));
+  }
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   return TDB_OK;

@@ -336,9 +336,174 @@ __global__ void __launch_bounds__(256) xattn_merge_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of the attention core for ONE query per frame (Lq = 1): a streaming kernel, one CTA per frame.
+//   pass 1 (V rows):  dPd[j,h] = dO_h . V[j,h,:] + dPbar[j]/8,  dP = dropout'(dPd),  rs[h] = sum_j P dP,  dV[j] = Pd[j,h] dO_h
+//   pass 2 (K rows):  dS[j,h] = P (dP - rs[h]),  dK[j] = scale dS q_h,  dQ_h = scale sum_j dS[j,h] K[j,h,:]
+// Warp = one memory row at a time (512 B, lane = 8 channels, head = lane / 4); every K / V row is read once and every dK / dV
+// row written once with 16-byte coalesced accesses -- the generic (Lq x Lk) kernels spent a CTA per (frame, head) staging
+// K and V in shared memory for a single query row (profiles/r01_kernel_table.txt: mha_bwd_row/col 58 + 43 us per launch).
+// Reductions across warps go through shared memory in fixed order (deterministic).
+struct XattnBwdParams {
+  const bf16 *q, *k, *v, *dout;   // q, dout [F][256]; k, v [F*S][256]
+  const float* p;                 // [F][8][S] normalised probabilities (before dropout)
+  const uint8_t* keep;            // [F][8][S] or null
+  float keep_scale;
+  const float* dpbar;             // [F][S] or null
+  bf16 *dq, *dk, *dv;
+  int F, S;
+  float scale;
+};
+
+__device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
+  float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+__global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float xs[];
+  const int S = a.S;
+  float* sp = xs;                 // [8][S]  P
+  float* spd = sp + 8 * S;        // [8][S]  post-dropout P
+  float* sdp = spd + 8 * S;       // [8][S]  dP, then dS
+  float* srs = sdp + 8 * S;       // [8 warps][8 heads]
+  float* sdq = srs + 64;          // [8 warps][256]
+  const int f = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = lane >> 2;
+  const float* pg = a.p + (long long)f * 8 * S;
+  const uint8_t* kg = a.keep ? a.keep + (long long)f * 8 * S : nullptr;
+  for (int e = threadIdx.x; e < 8 * S; e += 256) {
+    const float pv = pg[e];
+    sp[e] = pv;
+    spd[e] = kg ? (kg[e] ? pv * a.keep_scale : 0.f) : pv;
+  }
+  float dO[8], qv[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.dout + (long long)f * XD) + lane), dO);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.q + (long long)f * XD) + lane), qv);
+  __syncthreads();
+  const uint4* vrow = reinterpret_cast<const uint4*>(a.v + (long long)f * S * XD) + lane;
+  const uint4* krow = reinterpret_cast<const uint4*>(a.k + (long long)f * S * XD) + lane;
+  uint4* dvrow = reinterpret_cast<uint4*>(a.dv + (long long)f * S * XD) + lane;
+  uint4* dkrow = reinterpret_cast<uint4*>(a.dk + (long long)f * S * XD) + lane;
+  const float* dpb = a.dpbar ? a.dpbar + (long long)f * S : nullptr;
+  // ---- pass 1
+  float rs = 0.f;
+  for (int j0 = warp; j0 < S; j0 += 32) {            // 4 rows of this warp per iteration: 4 independent 16-byte loads in flight
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      raw[u] = j < S ? __ldg(vrow + (long long)j * (XD / 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      if (j < S) {                                   // warp-uniform
+        float vv[8];
+        unpack8(raw[u], vv);
+        float d = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) d += dO[t] * vv[t];
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        if (dpb) d += dpb[j] * 0.125f;
+        if (kg) d = kg[h * S + j] ? d * a.keep_scale : 0.f;
+        const float pj = sp[h * S + j];
+        if ((lane & 3) == 0) {
+          sdp[h * S + j] = d;
+          rs += pj * d;
+        }
+        const float pdj = spd[h * S + j];
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = pdj * dO[t];
+        dvrow[(long long)j * (XD / 8)] = pack8(o);
+      }
+    }
+  }
+  if ((lane & 3) == 0) srs[warp * 8 + h] = rs;
+  __syncthreads();
+  float rsum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) rsum += srs[w * 8 + h];
+  // ---- pass 2
+  float dqa[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) dqa[t] = 0.f;
+  for (int j0 = warp; j0 < S; j0 += 32) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      raw[u] = j < S ? __ldg(krow + (long long)j * (XD / 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      if (j < S) {
+        float kk[8];
+        unpack8(raw[u], kk);
+        const float pj = sp[h * S + j];
+        const float ds = pj > 0.f ? pj * (sdp[h * S + j] - rsum) : 0.f;   // masked keys have P = 0 exactly
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          dqa[t] += ds * kk[t];
+          o[t] = a.scale * ds * qv[t];
+        }
+        dkrow[(long long)j * (XD / 8)] = pack8(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) sdq[warp * XD + lane * 8 + t] = dqa[t];
+  __syncthreads();
+  {
+    const int c = threadIdx.x;            // 256 threads = 256 channels
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sdq[w * XD + c];
+    a.dq[(long long)f * XD + c] = __float2bfloat16(t * a.scale);
+  }
+}
+
 }  // namespace tdb
 
 using namespace tdb;
+
+extern "C" int tdb_xattn_bwd(const void* q, const void* k, const void* v, const void* dout, const float* p, const uint8_t* keep,
+                             float keep_scale, const float* dpbar, void* dq, void* dk, void* dv, int F, int S, float scale,
+                             void* stream_) {
+  int rc = tdb_init_once();
+  if (rc) return rc;
+  TDB_REQUIRE(q && k && v && dout && p && dq && dk && dv && F > 0 && S > 0, "tdb_xattn_bwd: null argument");
+  TDB_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
+              "tdb_xattn_bwd: bf16 buffers must be 16-byte aligned");
+  const size_t smem = sizeof(float) * ((size_t)24 * S + 64 + 8 * XD);
+  TDB_REQUIRE(smem <= 200 * 1024, "tdb_xattn_bwd: S=%d too long", S);
+  static bool attr = false;
+  if (!attr) {
+    TDB_CHECK_CUDA(cudaFuncSetAttribute(xattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  XattnBwdParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)dout, p, keep, keep_scale, dpbar,
+                   (bf16*)dq, (bf16*)dk, (bf16*)dv, F, S, scale};
+  TDB_CHECK_CUDA(tdb_launch(xattn_bwd_kernel, dim3(F), dim3(256), smem, (cudaStream_t)stream_, a));
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(1);
+  return TDB_OK;
+}
 
 extern "C" int64_t tdb_xattn_workspace_bytes(int F, int S) {
   int64_t tiles = ((int64_t)F * S + XBM - 1) / XBM;

@@ -85,3 +85,9 @@ def xattn_fused_fwd(q, mempb, memb, wkv, bv, kpm, o, p, pbar, F, S, scale, keep=
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device)
     check(lib().tdb_xattn_fused_fwd(ptr(q), ptr(mempb), ptr(memb), ptr(wkv), ptr(bv), ptr(kpm), ptr(keep), _f(keep_scale), ptr(o), ptr(p), ptr(pbar),
                                     ptr(ws), _i64(nbytes), F, S, _f(scale), stream_ptr()), "xattn_fused_fwd")
+
+
+def xattn_bwd(q, kp, vp, dout, p, dpbar, dq, dk, dv, F, S, scale, keep=None, keep_scale=1.0):
+    """one-query-per-frame attention backward: q, dout [F,256]; kp, vp [F*S,256] (contiguous bf16); p [F,8,1,S] fp32"""
+    check(lib().tdb_xattn_bwd(ptr(q), ptr(kp), ptr(vp), ptr(dout), ptr(p), ptr(keep), _f(keep_scale), ptr(dpbar), ptr(dq), ptr(dk),
+                              ptr(dv), F, S, _f(scale), stream_ptr()), "xattn_bwd")

@@ -221,10 +221,8 @@ class XAttnFusedFn(torch.autograd.Function):
             do = torch.zeros(F, 256, dtype=torch.bfloat16, device=q.device)
         do = _as_bf16(do).contiguous()
         dpbar = dpbar.contiguous().float() if dpbar is not None else None
-        ds = torch.empty_like(p)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(kp), torch.empty_like(vp)
-        K.mha_bwd(q, kp, vp, do, p, dpbar, ds, dq, dk, dv, F, 8, 1, S, scale, keep=keep, keep_scale=1.0 / (1.0 - drop_p),
-                  pd_scratch=torch.empty_like(p) if keep is not None else None)
+        K.xattn_bwd(q.contiguous(), kp, vp, do, p, dpbar, dq, dk, dv, F, S, scale, keep=keep, keep_scale=1.0 / (1.0 - drop_p))
         dW = torch.zeros_like(W) if ctx.needs_input_grad[3] else None
         db = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device) if ctx.needs_input_grad[4] else None
         if dW is not None:
@@ -281,8 +279,8 @@ class AddLayerNormFn(torch.autograd.Function):
         dypb = dypb.contiguous() if dypb is not None else None
         dz = torch.empty_like(x)
         dzb = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device) if ctx.has_r else None
-        dg = torch.empty(D, dtype=torch.float32, device=x.device)
-        db = torch.empty(D, dtype=torch.float32, device=x.device)
+        dgb = torch.empty(2 * D, dtype=torch.float32, device=x.device)     # contiguous [dgamma | dbeta]: one reduction launch
+        dg, db = dgb[:D], dgb[D:]
         K.layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dg, db, rows, D, dy2=dyb, dy3=dypb, dz_bf=dzb)   # sums the three grads in-kernel
         if dzb is not None:
             dz._tdb_bf16 = dzb
