@@ -212,3 +212,40 @@ def test_joint_backbone_batch_equals_two_passes():
     for n in res[True][2]:
         a, c = res[True][2][n], res[False][2][n]
         assert (a - c).abs().max().item() <= 1e-5 * (c.abs().max().item() + 1e-12), n
+
+
+@pytest.mark.parametrize("name", ["cfg1", "notsa"])
+def test_slow_frames_alias_fast_dedup(name):
+    """opt-in contract `slow_frames_alias_fast` (the slow frames ARE fast frames [::k], reference datasets/vidstg.py:250-251):
+    the backbone runs once per distinct frame.  Same parity with the reference fixtures as the two-pass path, and the two
+    paths agree with each other to bf16 noise (the batch size selects different tile schedules)."""
+    from tubedetr_b200 import NestedTensor
+    g = load_gold(name)
+    cfg = g["cfg"]
+    model, crit, wd = _model(cfg)
+    b = batch_for(cfg)
+    assert torch.equal(b["frames_slow"], b["frames_fast"][::cfg["stride"]])          # the contract holds for these inputs
+    samples = NestedTensor(b["frames_slow"].cuda(), b["mask_slow"].cuda())
+    fast = NestedTensor(b["frames_fast"].cuda(), b["mask_fast"].cuda())
+    caps = (b["input_ids"].cuda(), b["attention_mask"].cuda())
+    res = {}
+    for flag in (False, True):
+        model.slow_frames_alias_fast = flag
+        model.zero_grad(set_to_none=True)
+        mc = model(samples, cfg["durations"], caps, encode_and_save=True, samples_fast=fast)
+        out = model(samples, cfg["durations"], caps, encode_and_save=False, memory_cache=mc)
+        (out["pred_boxes"].float().square().sum() + out["pred_sted"].float().square().sum()).backward()
+        res[flag] = (out, mc, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None})
+    model.slow_frames_alias_fast = False
+    out, mc, gr = res[True]
+    e_box, e_sted = _err(out["pred_boxes"], g["pred_boxes"]), _err(out["pred_sted"], g["pred_sted"])
+    e_mem = _err(mc["img_memory"], g["img_memory"])
+    _log(f"{name} (dedup): img_memory err {e_mem:.4g} pred_boxes {e_box:.4g} pred_sted {e_sted:.4g}")
+    assert e_box <= 2e-2 and e_sted <= 2e-2 * max(1.0, g["pred_sted"].abs().max().item())
+    assert e_mem <= 3e-2 * g["img_memory"].abs().max().item()
+    assert _err(out["pred_boxes"], res[False][0]["pred_boxes"]) <= 1e-2
+    assert gr.keys() == res[False][2].keys()
+    for n in ("input_proj.weight", "backbone.0.body.layer3.5.conv2.weight", "transformer.fast_encoder.weight"):
+        a, c = gr[n].float(), res[False][2][n].float()
+        cos = (a * c).sum() / (a.norm() * c.norm() + 1e-20)
+        assert cos > 0.99, (n, cos.item())

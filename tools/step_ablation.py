@@ -112,5 +112,28 @@ def backbone_fwd_bwd():
 
 
 rows.append(("backbone forward (125 frames) + backward (25 slow frames)", timed_graph(backbone_fwd_bwd)))
+eng = model._engine
+N = fr_s.shape[0] + fr_f.shape[0]
+H, Wd = fr_s.shape[2:]
+
+
+def upto(li_hi):
+    def f():
+        with torch.no_grad():
+            x = eng._stem([fr_s, fr_f], W, "abl3")
+            if li_hi:
+                eng._stages(x, N, W, False, "abl3", 1, li_hi, H, Wd)
+    return f
+
+
+prev = 0.0
+for li, nm in enumerate(["stem (im2col + conv1 GEMM + maxpool)", "+ layer1", "+ layer2", "+ layer3", "+ layer4"]):
+    t = timed_graph(upto(li))
+    rows.append((f"backbone forward 125 frames up to: {nm}   [stage alone: {t - prev:.3f} ms]", t))
+    prev = t
+model.slow_frames_alias_fast = True
+st3 = bench.Step(model, crit, wd, dev, 0, 1, use_graph=True)
+rows.append(("full step, train mode, slow_frames_alias_fast (100 backbone frames)", timed_graph(st3.body)))
+model.slow_frames_alias_fast = False
 for k, v in rows:
     print(f"{v:8.3f} ms  {k}")

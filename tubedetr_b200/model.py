@@ -344,6 +344,12 @@ class TubeDETR(nn.Module):
         self.text_side_stream = True   # RoBERTa on its own CUDA stream, concurrent with the backbone (forward and backward)
         self.joint_backbone = True  # slow + fast frames share one backbone batch when their spatial sizes agree
         self.fast_l2_chunk = None   # frames per chunk for the L2-resident schedule of stem+layer1+layer2 in the no-grad pass
+        # Opt-in contract: samples.tensors[b, i] IS samples_fast.tensors[b, i*k] (what the reference's datasets produce:
+        # datasets/vidstg.py:250-251 returns images[:, ::stride] next to images).  The reference then runs the backbone on those
+        # frames twice (models/tubedetr.py:121 with grad, :128 under no_grad) with identical results; with this flag the
+        # backbone runs once per distinct frame (T instead of T + ceil(T/k) frames) and the fast branch reuses the slow
+        # frames' features (detached, as the fast branch never backpropagates into the backbone).
+        self.slow_frames_alias_fast = False
         self.text_autocast = False  # True: RoBERTa (library call) runs its GEMMs under bf16 autocast (bench.py sets it)
 
     # ------------------------------------------------------------------ helpers
@@ -371,6 +377,23 @@ class TubeDETR(nn.Module):
             valid = tt[None] < dur[:, None]
             clip_of_t = (torch.arange(B)[:, None] * n_clips + tt[None] // k).flatten()
             c[key] = tuple(t.to(dev) for t in (dur, tt, valid, clip_of_t))
+        return c[key]
+
+    def _dedup_index_tensors(self, B, T, k, dev):
+        """slow frames = fast frames [::k] of every video (uniform durations): indices of the fast frames that are NOT slow
+        frames, and for every fast frame its row in the joint batch [slow frames | remaining fast frames]."""
+        key = ("dedup", B, T, k, str(dev))
+        c = self.__dict__.setdefault("_idx_cache", {})
+        if key not in c:
+            n_clips = math.ceil(T / k)
+            t = torch.arange(B * T)
+            tv, bv = t % T, t // T
+            is_slow = tv % k == 0
+            rest_idx = t[~is_slow]
+            order = torch.empty(B * T, dtype=torch.long)
+            order[is_slow] = (bv * n_clips + tv // k)[is_slow]
+            order[~is_slow] = B * n_clips + torch.arange(rest_idx.numel())
+            c[key] = (rest_idx.to(dev), order.to(dev))
         return c[key]
 
     def trunk_outputs(self):
@@ -425,8 +448,14 @@ class TubeDETR(nn.Module):
         feat_f = None
         joint = (self.fast and self.joint_backbone and samples_fast is not None
                  and samples_fast.tensors.shape[2:] == frames.shape[2:])
+        dedup = (joint and self.slow_frames_alias_fast and k > 1 and all(d == T for d in durations)
+                 and samples_fast.tensors.shape[0] == B * T and frames.shape[0] == B * n_clips)
+        order = None
         if joint:      # slow + fast frames as one backbone batch (same launches, better SM fill); fast rows carry no grad
             ffr = samples_fast.tensors.float()
+            if dedup:  # only the fast frames that are not slow frames; `order` maps fast frame -> row block of the joint batch
+                rest_idx, order = self._dedup_index_tensors(B, T, k, dev)
+                ffr = ffr.index_select(0, rest_idx)
             if names and torch.is_grad_enabled():
                 feat, feat_f = ops.BackboneJointFn.apply(frames.float(), ffr, self._engine, W, names, "joint",
                                                          *[sd[n] for n in names])
@@ -461,7 +490,10 @@ class TubeDETR(nn.Module):
                 else:
                     hf, wf = h, w
                 m_f = self._resize_mask(fm_, hf, wf)
-            fsrc_all = ops.linear(feat_f, Win, bin_).view(-1, HW, D_MODEL)       # input_proj gets weight-grad here too
+            if order is not None:    # joint batch rows [slow | rest] -> fast frame order; slow features enter detached
+                fsrc_all = ops.linear(torch.cat([feat.detach(), feat_f], 0), Win, bin_).view(-1, HW, D_MODEL).index_select(0, order)
+            else:
+                fsrc_all = ops.linear(feat_f, Win, bin_).view(-1, HW, D_MODEL)   # input_proj gets weight-grad here too
             ragged = any(d != T for d in durations)
             if ragged:
                 idx = ((torch.cumsum(dur, 0) - dur)[:, None] + tt[None]).clamp(max=ff.shape[0] - 1).flatten()
