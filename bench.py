@@ -229,7 +229,9 @@ class Step:
         if self.use_graph:
             try:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # N>1: NCCL's watchdog thread polls events of earlier collectives; in the default "global" capture mode such a
+                # call from another thread invalidates the capture
+                with torch.cuda.graph(g, capture_error_mode="thread_local" if self.world > 1 else "global"):
                     self.body()
                 self.graph = g
             except Exception as e:  # keep going eagerly, say so
@@ -358,6 +360,25 @@ def optim_probe(device, pk, n=184_640_000):
             "algorithmic_bytes": nbytes, "l2": "5 x 739 MB streams >> 126 MB L2"}
 
 
+def shutdown(st=None):
+    """Leave without hanging: CUDA graphs that captured NCCL kernels must be gone before the communicator is torn down, and a
+    teardown that does not come back within 20 s (seen once with captured collectives) must not hold the job: every rank has
+    already passed the final barrier and rank 0 has printed its line."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if st is not None:
+        st.graph = None
+    torch.cuda.synchronize()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        t = threading.Thread(target=torch.distributed.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=20)
+        sys.stdout.flush()
+        os._exit(0)
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -410,8 +431,7 @@ def run_ours(args):
         sampler.join(timeout=2)
     loss_val = float(st.loss.item())
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
+        shutdown(st)
         return
     probe = kernel_probe(device, pk)
     try:
@@ -464,8 +484,7 @@ def run_ours(args):
                          "frac_of_sustained_peak": FLOP_PER_CLIP / (per_step * 1e-3) / 1e12 / pk["tf_sustained"]},
             "roofline": probe, "dedup_slow_frames": dedup, "optimizer_step": oprobe, "cpu_baseline": cpu, "clocks": sampler.summary() if sampler else None}
     print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    shutdown(st)
 
 
 def main():

@@ -107,14 +107,20 @@ int tdb_cast_add_bf16(const float* x, const float* add, void* y, int64_t n, void
  * LayerNorm with fused residual add (post-norm blocks, reference models/transformer.py:641-645, 721-750, 581;
  * FeatureResizer LN eps 1e-12 :765).  D must be 256.  z = x + r; y = LN(z).  Optional bf16 copies of y and y + pos
  * (the operand of the next projection GEMM).  Backward returns dz (gradient of both x and r) and dgamma/dbeta.
+ * Residual dropout (reference transformer.py:641-645 `src + self.dropout1(src2)` etc.): with drop_seed != NULL the kernel
+ * computes z = x + keep * r / (1 - p), the keep bits coming from the same counter-based hash as tdb_dropout_mask(seed, site)
+ * at element index row * D + col; backward regenerates them and writes dr = keep * dz / (1 - p) (fp32 and/or bf16) next to
+ * dz (which then is the gradient of x only).  No mask tensor exists.
  * ------------------------------------------------------------------------------------------------ */
 int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta, const float* pos, float* y,
-                      void* y_bf, void* ypos_bf, float* mean, float* rstd, int rows, int D, float eps, void* stream);
+                      void* y_bf, void* ypos_bf, float* mean, float* rstd, int rows, int D, float eps,
+                      const int64_t* drop_seed, int64_t drop_site, float drop_p, void* stream);
 int tdb_layernorm_bwd_blocks(int rows); /* partial workspace = blocks * 2 * D floats */
 /* incoming gradient = dy (fp32, may be NULL) + dy2_bf + dy3_bf (bf16, may be NULL): grads of y, bf16(y), bf16(y+pos) */
 int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void* dy3_bf, const float* x, const float* r,
                       const float* gamma, const float* mean, const float* rstd, float* dz, void* dz_bf /* optional bf16 copy */,
-                      float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate, void* stream);
+                      float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate,
+                      const int64_t* drop_seed, int64_t drop_site, float drop_p, float* dr, void* dr_bf, void* stream);
 /* column sums of a bf16 [rows][N] matrix (bias gradients), two-stage fixed order; partial = nparts * N floats */
 int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* partial, int nparts, float* out, int accumulate,
                     void* stream);
@@ -154,6 +160,15 @@ int64_t tdb_xattn_workspace_bytes(int F, int S);
 int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, const void* wkv, const float* bv,
                         const uint8_t* kpm, const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar,
                         void* workspace, int64_t ws_bytes, int F, int S, float scale, void* stream);
+
+/* Dropout keep mask (1 = keep, probability 1 - p) from a counter-based hash of (seed[0] in DEVICE memory, site, index):
+ * replaces torch.rand -> compare -> cast at the attention-dropout sites (reference models/transformer.py:613, dropout=0.1).
+ * The host bumps seed[0] once per training step (a captured op), `site` numbers the call sites within a step. */
+int tdb_dropout_mask(uint8_t* keep, int64_t n, const int64_t* seed, int64_t site, float p, void* stream);
+
+/* y = keep ? x / (1 - p) : 0 on a bf16 buffer, keep bits = the stream of tdb_dropout_mask(seed, site) (FFN hidden dropout,
+ * reference models/transformer.py:644, 749).  Its backward is done by the consuming GEMM (mask = y > 0, scale 1 / (1 - p)). */
+int tdb_dropout_bf16(const void* x, void* y, int64_t n, const int64_t* seed, int64_t site, float p, void* stream);
 
 /* Backward of the one-query-per-frame attention core (the cross-attention above; K/V are re-projected by tdb_gemm first):
  *   q, dout [F][256] bf16;  k, v [F*S][256] bf16 projected keys / values;  p [F][8][S] fp32 probabilities (before dropout);

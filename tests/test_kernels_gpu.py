@@ -298,3 +298,98 @@ def test_colsum_vector_path(rows, N):
     out2 = torch.zeros(N, device="cuda")
     K.colsum_bf16(x, out2)
     assert torch.equal(out, out2)
+
+
+def test_dropout_mask_kernel_statistics_and_streams():
+    """keep masks from the counter-based hash: keep rate 1 - p, independent across sites and seeds, reproducible for the same
+    (seed, site); odd lengths (tail path)"""
+    from tubedetr_b200 import kernels as K
+    n, p = 1_000_003, 0.1
+    seed = torch.tensor([1234], dtype=torch.int64, device="cuda")
+    a = K.dropout_mask(torch.empty(n, dtype=torch.uint8, device="cuda"), seed, 1, p)
+    a2 = K.dropout_mask(torch.empty(n, dtype=torch.uint8, device="cuda"), seed, 1, p)
+    b = K.dropout_mask(torch.empty(n, dtype=torch.uint8, device="cuda"), seed, 2, p)
+    seed.add_(1)
+    c = K.dropout_mask(torch.empty(n, dtype=torch.uint8, device="cuda"), seed, 1, p)
+    assert a.max().item() == 1 and a.min().item() == 0
+    assert torch.equal(a, a2)
+    sigma = math.sqrt(p * (1 - p) / n)
+    for m in (a, b, c):
+        assert abs(m.float().mean().item() - (1 - p)) < 5 * sigma
+    # independence: P(both dropped) = p^2
+    for x, y in ((a, b), (a, c)):
+        both = ((x == 0) & (y == 0)).float().mean().item()
+        assert abs(both - p * p) < 5 * math.sqrt(p * p * (1 - p * p) / n)
+    # no short-range structure: lag-1 autocorrelation of the drop indicator ~ 0
+    d = (a == 0).float()
+    ac = ((d[1:] - p) * (d[:-1] - p)).mean().item() / (p * (1 - p))
+    assert abs(ac) < 5 / math.sqrt(n)
+
+
+def test_layernorm_fused_residual_dropout():
+    """y = LN(x + dropout(r)) with the keep bits generated inside the LayerNorm kernels == the same computation with the explicit
+    mask of tdb_dropout_mask(seed, site) (same hash stream), forward and backward (dz for x, dr = keep * dz / (1-p) for r)"""
+    from tubedetr_b200 import kernels as K
+    rows, D, p = 777, 256, 0.1
+    x, r = _r((rows, D), 80, torch.float32), _r((rows, D), 81, torch.float32)
+    gm, bt = _r((D,), 82, torch.float32) * 0.1 + 1, _r((D,), 83, torch.float32) * 0.1
+    seed = torch.tensor([987654321], dtype=torch.int64, device="cuda")
+    site = 17
+    keep = K.dropout_mask(torch.empty(rows * D, dtype=torch.uint8, device="cuda"), seed, site, p).view(rows, D).float()
+    assert 0.88 < keep.mean().item() < 0.92
+    y, yb = torch.empty_like(x), torch.empty(rows, D, dtype=torch.bfloat16, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    K.layernorm_fwd(x, r, gm, bt, None, y, yb, None, mean, rstd, rows, D, 1e-5, drop=(seed, site, p))
+    xr, rr = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    ref = F.layer_norm(xr + rr * keep / (1 - p), (D,), gm, bt, 1e-5)
+    _close(y, ref, 1e-5)
+    dy = _r((rows, D), 84, torch.float32)
+    ref.backward(dy)
+    dz, dr = torch.empty_like(x), torch.empty_like(x)
+    drb = torch.empty(rows, D, dtype=torch.bfloat16, device="cuda")
+    dgb = torch.empty(2 * D, device="cuda")
+    K.layernorm_bwd(dy, x, r, gm, mean, rstd, dz, dgb[:D], dgb[D:], rows, D, drop=(seed, site, p), dr=dr, dr_bf=drb)
+    _close(dz, xr.grad, 1e-4)
+    _close(dr, rr.grad, 1e-4)
+    _close(drb, rr.grad, 1e-2)
+    assert ((dr == 0) == (keep == 0)).all()              # exactly the dropped positions carry no gradient
+    # a different site draws a different mask
+    y2 = torch.empty_like(x)
+    K.layernorm_fwd(x, r, gm, bt, None, y2, yb, None, mean, rstd, rows, D, 1e-5, drop=(seed, site + 1, p))
+    assert not torch.equal(y, y2)
+
+
+def test_ffn_hidden_dropout_fused_backward():
+    """linear1(relu, masked_by_consumer) -> hidden_dropout -> linear2(mask_dx, dx_scale): forward equals the explicit-mask
+    computation, and the gradients equal autograd through relu -> mask/(1-p) -> linear (bf16 operands, fp32 reference)"""
+    from tubedetr_b200 import kernels as K
+    from tubedetr_b200 import ops
+    R, D, Hd, p = 384, 256, 2048, 0.1
+    x = _r((R, D), 90)
+    W1, b1 = (_r((Hd, D), 91, torch.float32) / 16).requires_grad_(True), (_r((Hd,), 92, torch.float32) * 0.1).requires_grad_(True)
+    W2, b2 = (_r((D, Hd), 93, torch.float32) / 45).requires_grad_(True), (_r((D,), 94, torch.float32) * 0.1).requires_grad_(True)
+    st = ops._drop_state(x.device)
+    site = st[1] + 1                                     # the site hidden_dropout will draw
+    xg = x.clone().requires_grad_(True)
+    h = ops.linear(xg, W1, b1, relu=True, masked_by_consumer=True)
+    hd = ops.hidden_dropout(h, p)
+    out = ops.linear(hd, W2, b2, out_fp32=True, mask_dx=True, dx_scale=1 / (1 - p))
+    keep = K.dropout_mask(torch.empty(R * Hd, dtype=torch.uint8, device="cuda"), st[0], site, p).view(R, Hd).float()
+    s32 = (1.0 / (torch.tensor(1.0) - torch.tensor(p, dtype=torch.float32))).item()        # the kernel's fp32 1 / (1 - p)
+    assert torch.equal(hd, (h.float() * (keep * s32)).bfloat16())
+    dy = _r((R, D), 95, torch.float32)
+    out.backward(dy)
+    # fp32 reference on the same bf16-rounded operands
+    xr = x.float().requires_grad_(True)
+    W1r, b1r, W2r, b2r = (t.detach().clone().requires_grad_(True) for t in (W1, b1, W2, b2))
+    hr = torch.relu(xr @ W1r.bfloat16().float().t() + b1r).bfloat16().float()
+    hdr = (hr * keep / (1 - p)).bfloat16().float()
+    outr = hdr @ W2r.bfloat16().float().t() + b2r
+    _close(out, outr, 2e-2)
+    # gradient reference: straight-through the bf16 roundings
+    hr2 = torch.relu(xr @ W1r.bfloat16().float().t() + b1r)
+    (((hr2 * keep / (1 - p)) @ W2r.bfloat16().float().t() + b2r) * dy).sum().backward()
+    for got, ref in ((xg.grad, xr.grad), (W1.grad, W1r.grad), (b1.grad, b1r.grad), (W2.grad, W2r.grad), (b2.grad, b2r.grad)):
+        _close(got, ref, 3e-2)
+        a = (got.float() * ref).sum() / (ref * ref).sum()
+        assert abs(a.item() - 1) < 1e-2, a.item()

@@ -230,13 +230,37 @@ __global__ void cast_add_bf16_kernel(const float* __restrict__ x, const float* _
   reinterpret_cast<uint2*>(y)[idx] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t keep4(unsigned long long r, uint32_t thr) {   // four 16-bit lanes -> four 0/1 bytes
+  uint32_t o = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) o |= (uint32_t)(((uint32_t)(r >> (16 * t)) & 0xFFFFu) >= thr) << (8 * t);
+  return o;
+}
+// per-element view of the same stream: element e uses 16-bit lane (e & 3) of hash number (e >> 2) -- identical to what
+// dropout_mask_kernel writes at keep[e], so a fused consumer and an explicit mask of the same (seed, site) agree bit for bit
+__device__ __forceinline__ unsigned long long drop_base(const long long* seed, unsigned long long site) {
+  return splitmix64((unsigned long long)seed[0] * 0xD1342543DE82EF95ull + site);
+}
+__device__ __forceinline__ bool drop_keep(unsigned long long base, long long e, uint32_t thr) {
+  const unsigned long long r = splitmix64(base + (unsigned long long)(e >> 2));
+  return (((uint32_t)(r >> (16 * (e & 3)))) & 0xFFFFu) >= thr;
+}
+
 // ------------------------------------------------------------------ LayerNorm over d=256 with fused residual add.  One warp per row.
 // z = x + r (r optional, fp32);  y = (z - mean) * rstd * gamma + beta.  Writes y fp32, optional bf16 copy of y and of (y + pos).
 template <int D>
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, const float* __restrict__ pos, float* __restrict__ y,
                                      bf16* __restrict__ y_bf, bf16* __restrict__ ypos_bf, float* __restrict__ mean_out,
-                                     float* __restrict__ rstd_out, int rows, float eps) {
+                                     float* __restrict__ rstd_out, int rows, float eps,
+                                     const long long* __restrict__ drop_seed, unsigned long long drop_site, uint32_t drop_thr,
+                                     float drop_scale) {
   pdl_wait();
   pdl_trigger();
   constexpr int PER = D / 32;
@@ -244,12 +268,15 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
   int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* xr = x + (long long)warp * D;
+  const unsigned long long dbase = drop_seed ? drop_base(drop_seed, drop_site) : 0ull;
   float v[PER];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     int c = i * 32 + lane;
-    v[i] = xr[c] + (r ? r[(long long)warp * D + c] : 0.f);
+    float rv = r ? r[(long long)warp * D + c] : 0.f;
+    if (drop_seed) rv = drop_keep(dbase, (long long)warp * D + c, drop_thr) ? rv * drop_scale : 0.f;   // residual dropout on r
+    v[i] = xr[c] + rv;
     s += v[i];
   }
   float mean = warp_sum(s) * (1.f / D);
@@ -280,10 +307,13 @@ template <int D>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ dy3,
                                      const float* __restrict__ x, const float* __restrict__ r,
                                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     float* __restrict__ dz, bf16* __restrict__ dz_bf, float* __restrict__ partial, int rows) {
+                                     float* __restrict__ dz, bf16* __restrict__ dz_bf, float* __restrict__ partial, int rows,
+                                     const long long* __restrict__ drop_seed, unsigned long long drop_site, uint32_t drop_thr,
+                                     float drop_scale, float* __restrict__ dr, bf16* __restrict__ dr_bf) {
   pdl_wait();
   pdl_trigger();
   constexpr int PER = D / 32;
+  const unsigned long long dbase = drop_seed ? drop_base(drop_seed, drop_site) : 0ull;
   __shared__ float sg[8][D];
   __shared__ float sb[8][D];
   int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -298,7 +328,9 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
     for (int i = 0; i < PER; ++i) {
       int c = i * 32 + lane;
       long long o = (long long)row * D + c;
-      float z = x[o] + (r ? r[o] : 0.f);
+      float rv = r ? r[o] : 0.f;
+      if (drop_seed) rv = drop_keep(dbase, o, drop_thr) ? rv * drop_scale : 0.f;
+      float z = x[o] + rv;
       xh[i] = (z - m) * rs;
       float d = dy ? dy[o] : 0.f;
       if (dy2) d += __bfloat162float(dy2[o]);
@@ -314,8 +346,16 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       float o = rs * (g[i] - s1 - xh[i] * s2);
-      dz[(long long)row * D + i * 32 + lane] = o;
-      if (dz_bf) dz_bf[(long long)row * D + i * 32 + lane] = __float2bfloat16(o);
+      const long long e = (long long)row * D + i * 32 + lane;
+      dz[e] = o;
+      if (drop_seed) {     // gradient of the dropped residual branch: d r = d z * keep / (1 - p); dz stays the gradient of x
+        const float od = drop_keep(dbase, e, drop_thr) ? o * drop_scale : 0.f;
+        if (dr) dr[e] = od;
+        if (dr_bf) dr_bf[e] = __float2bfloat16(od);
+        if (dz_bf) dz_bf[e] = __float2bfloat16(o);
+      } else if (dz_bf) {
+        dz_bf[e] = __float2bfloat16(o);
+      }
     }
   }
 #pragma unroll
@@ -435,6 +475,64 @@ __global__ void __launch_bounds__(256) colsum_bf16_v8_kernel(const bf16* __restr
   }
 }
 
+// ------------------------------------------------------------------ dropout keep masks from a counter-based hash
+// keep[i] = 1 with probability 1 - p.  Randomness = splitmix64(seed_dev[0], site, i / 4): the seed lives in DEVICE memory and
+// is bumped once per training step by the host module (inside the captured CUDA graph), `site` distinguishes the call sites
+// of one step, so a graph replay draws fresh masks without any host involvement.  One launch replaces torch's
+// rand -> compare -> cast chain (3 launches and 6 x the bytes) at every attention-dropout site (reference transformer.py:613).
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ keep, long long n, const long long* __restrict__ seed,
+                                                           unsigned long long site, uint32_t thr) {
+  pdl_wait();
+  pdl_trigger();
+  const unsigned long long base = drop_base(seed, site);
+  const long long n16 = n >> 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    uint4 o;
+    o.x = keep4(splitmix64(base + 4ull * i), thr);
+    o.y = keep4(splitmix64(base + 4ull * i + 1), thr);
+    o.z = keep4(splitmix64(base + 4ull * i + 2), thr);
+    o.w = keep4(splitmix64(base + 4ull * i + 3), thr);
+    reinterpret_cast<uint4*>(keep)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {      // tail: fewer than 16 bytes
+    const long long e = (n16 << 4) + threadIdx.x;
+    const unsigned long long r = splitmix64(base + (unsigned long long)(e >> 2));
+    keep[e] = (uint8_t)((((uint32_t)(r >> (16 * (e & 3)))) & 0xFFFFu) >= thr);
+  }
+}
+
+// y = keep ? x / (1 - p) : 0 on bf16 (FFN hidden dropout, reference transformer.py:644,749 `self.dropout(self.activation(...))`);
+// keep bits = the stream of tdb_dropout_mask(seed, site).  8 elements (16 bytes) per thread.
+__global__ void __launch_bounds__(256) dropout_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n,
+                                                           const long long* __restrict__ seed, unsigned long long site, uint32_t thr,
+                                                           float scale) {
+  pdl_wait();
+  pdl_trigger();
+  const unsigned long long base = drop_base(seed, site);
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const unsigned long long r0 = splitmix64(base + 2ull * i), r1 = splitmix64(base + 2ull * i + 1);
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const unsigned long long r = t < 2 ? r0 : r1;
+      const int sh = 32 * (t & 1);
+      const bool k0 = (((uint32_t)(r >> sh)) & 0xFFFFu) >= thr, k1 = (((uint32_t)(r >> (sh + 16))) & 0xFFFFu) >= thr;
+      const float2 f = unpack_bf16x2(in[t]);
+      out[t] = pack_bf16x2(k0 ? f.x * scale : 0.f, k1 ? f.y * scale : 0.f);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const long long e = (n8 << 3) + threadIdx.x;
+    y[e] = drop_keep(base, e, thr) ? __float2bfloat16(__bfloat162float(x[e]) * scale) : __float2bfloat16(0.f);
+  }
+}
+
 }  // namespace tdb
 
 using namespace tdb;
@@ -504,11 +602,15 @@ extern "C" int tdb_cast_add_bf16(const float* x, const float* add, void* y, int6
 }
 extern "C" int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta, const float* pos,
                                  float* y, void* y_bf, void* ypos_bf, float* mean, float* rstd, int rows, int D, float eps,
-                                 void* stream_) {
+                                 const int64_t* drop_seed, int64_t drop_site, float drop_p, void* stream_) {
   TDB_REQUIRE(x && gamma && beta && y && rows > 0 && D == 256, "tdb_layernorm_fwd: only D=256 (got %d)", D);
   TDB_REQUIRE(!ypos_bf || pos, "tdb_layernorm_fwd: ypos needs pos");
+  TDB_REQUIRE(!drop_seed || (r && drop_p > 0.f && drop_p < 1.f), "tdb_layernorm_fwd: residual dropout needs r and 0 < p < 1");
+  const uint32_t thr = drop_seed ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
+  const float dscale = drop_seed ? 1.f / (1.f - drop_p) : 1.f;
   TDB_CHECK_CUDA(tdb_launch(layernorm_fwd_kernel<256>, dim3(nblocks((long long)rows * 32, 256)), dim3(256), 0, STREAM, x, r, gamma, beta, pos, y, (bf16*)y_bf,
-                                                                                    (bf16*)ypos_bf, mean, rstd, rows, eps));
+                                                                                    (bf16*)ypos_bf, mean, rstd, rows, eps,
+                                                                                    (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale));
   LAUNCH_OK();
 }
 extern "C" int tdb_layernorm_bwd_blocks(int rows) {
@@ -517,10 +619,15 @@ extern "C" int tdb_layernorm_bwd_blocks(int rows) {
 }
 extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void* dy3_bf, const float* x, const float* r,
                                  const float* gamma, const float* mean, const float* rstd, float* dz, void* dz_bf,
-                                 float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate, void* stream_) {
+                                 float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate,
+                                 const int64_t* drop_seed, int64_t drop_site, float drop_p, float* dr, void* dr_bf, void* stream_) {
   TDB_REQUIRE((dy || dy2_bf || dy3_bf) && x && gamma && mean && rstd && dz && partial && rows > 0 && D == 256, "tdb_layernorm_bwd: bad args");
+  TDB_REQUIRE(!drop_seed || (r && drop_p > 0.f && drop_p < 1.f && (dr || dr_bf)), "tdb_layernorm_bwd: residual dropout needs r, 0 < p < 1 and a dr output");
+  const uint32_t thr = drop_seed ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
+  const float dscale = drop_seed ? 1.f / (1.f - drop_p) : 1.f;
   int blocks = tdb_layernorm_bwd_blocks(rows);
-  TDB_CHECK_CUDA(tdb_launch(layernorm_bwd_kernel<256>, dim3(blocks), dim3(256), 0, STREAM, dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows));
+  TDB_CHECK_CUDA(tdb_launch(layernorm_bwd_kernel<256>, dim3(blocks), dim3(256), 0, STREAM, dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows,
+                            (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale, dr, (bf16*)dr_bf));
   TDB_CHECK_CUDA(cudaGetLastError());
   if (dgamma && dbeta == dgamma + D) {   // [dgamma | dbeta] contiguous: the partial rows [2D] reduce in ONE launch
     TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((2 * D + 31) / 32), dim3(32, 8), 0, STREAM, partial, blocks, 2 * D, 2 * D, dgamma, accumulate));
@@ -560,4 +667,26 @@ extern "C" int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(2);
   return TDB_OK;
+}
+
+extern "C" int tdb_dropout_mask(uint8_t* keep, int64_t n, const int64_t* seed, int64_t site, float p, void* stream_) {
+  TDB_REQUIRE(keep && seed && n > 0 && p >= 0.f && p < 1.f, "tdb_dropout_mask: bad args");
+  TDB_REQUIRE(((uintptr_t)keep & 15) == 0, "tdb_dropout_mask: keep must be 16-byte aligned");
+  const uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
+  long long want = ((n >> 4) + 255) / 256;
+  int nb = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  TDB_CHECK_CUDA(tdb_launch(dropout_mask_kernel, dim3(nb), dim3(256), 0, STREAM, keep, (long long)n, (const long long*)seed,
+                            (unsigned long long)site, thr));
+  LAUNCH_OK();
+}
+
+extern "C" int tdb_dropout_bf16(const void* x, void* y, int64_t n, const int64_t* seed, int64_t site, float p, void* stream_) {
+  TDB_REQUIRE(x && y && seed && n > 0 && p >= 0.f && p < 1.f, "tdb_dropout_bf16: bad args");
+  TDB_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "tdb_dropout_bf16: buffers must be 16-byte aligned");
+  const uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
+  long long want = ((n >> 3) + 255) / 256;
+  int nb = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  TDB_CHECK_CUDA(tdb_launch(dropout_bf16_kernel, dim3(nb), dim3(256), 0, STREAM, (const bf16*)x, (bf16*)y, (long long)n,
+                            (const long long*)seed, (unsigned long long)site, thr, 1.f / (1.f - p)));
+  LAUNCH_OK();
 }

@@ -43,16 +43,21 @@ def cast_add_bf16(x, add, y):
     check(lib().tdb_cast_add_bf16(ptr(x), ptr(add), ptr(y), _i64(x.numel()), stream_ptr()), "cast_add_bf16")
 
 
-def layernorm_fwd(x, r, gamma, beta, pos, y, y_bf, ypos_bf, mean, rstd, rows, D, eps):
+def layernorm_fwd(x, r, gamma, beta, pos, y, y_bf, ypos_bf, mean, rstd, rows, D, eps, drop=None):
+    """drop = (seed tensor, site, p): residual dropout on r inside the kernel (no mask tensor)"""
+    seed, site, p = drop if drop is not None else (None, 0, 0.0)
     check(lib().tdb_layernorm_fwd(ptr(x), ptr(r), ptr(gamma), ptr(beta), ptr(pos), ptr(y), ptr(y_bf), ptr(ypos_bf),
-                                  ptr(mean), ptr(rstd), rows, D, _f(eps), stream_ptr()), "layernorm_fwd")
+                                  ptr(mean), ptr(rstd), rows, D, _f(eps), ptr(seed), _i64(site), _f(p), stream_ptr()), "layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dgamma, dbeta, rows, D, accumulate=False, dy2=None, dy3=None, dz_bf=None):
+def layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dgamma, dbeta, rows, D, accumulate=False, dy2=None, dy3=None, dz_bf=None,
+                  drop=None, dr=None, dr_bf=None):
     nb = int(lib().tdb_layernorm_bwd_blocks(rows))
     partial = torch.empty(nb * 2 * D, dtype=torch.float32, device=x.device)
+    seed, site, p = drop if drop is not None else (None, 0, 0.0)
     check(lib().tdb_layernorm_bwd(ptr(dy), ptr(dy2), ptr(dy3), ptr(x), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), ptr(dz), ptr(dz_bf), ptr(dgamma),
-                                  ptr(dbeta), ptr(partial), rows, D, int(accumulate), stream_ptr()), "layernorm_bwd")
+                                  ptr(dbeta), ptr(partial), rows, D, int(accumulate), ptr(seed), _i64(site), _f(p), ptr(dr), ptr(dr_bf),
+                                  stream_ptr()), "layernorm_bwd")
 
 
 def colsum_bf16(x, out, accumulate=False):
@@ -91,3 +96,13 @@ def xattn_bwd(q, kp, vp, dout, p, dpbar, dq, dk, dv, F, S, scale, keep=None, kee
     """one-query-per-frame attention backward: q, dout [F,256]; kp, vp [F*S,256] (contiguous bf16); p [F,8,1,S] fp32"""
     check(lib().tdb_xattn_bwd(ptr(q), ptr(kp), ptr(vp), ptr(dout), ptr(p), ptr(keep), _f(keep_scale), ptr(dpbar), ptr(dq), ptr(dk),
                               ptr(dv), F, S, _f(scale), stream_ptr()), "xattn_bwd")
+
+
+def dropout_mask(keep, seed, site, p):
+    check(lib().tdb_dropout_mask(ptr(keep), _i64(keep.numel()), ptr(seed), _i64(site), _f(p), stream_ptr()), "dropout_mask")
+    return keep
+
+
+def dropout_bf16(x, y, seed, site, p):
+    check(lib().tdb_dropout_bf16(ptr(x), ptr(y), _i64(x.numel()), ptr(seed), _i64(site), _f(p), stream_ptr()), "dropout_bf16")
+    return y

@@ -269,10 +269,11 @@ class Transformer(nn.Module):
 
     def _ffn(self, l, xb, dp):
         """linear2(dropout(relu(linear1(x)))) -> fp32.  Without dropout the ReLU backward rides in linear2's dgrad epilogue."""
-        if dp > 0:
-            hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True)
-            hdn = F.dropout(hdn, dp, True)
-            return F.dropout(ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True), dp, True)
+        if dp > 0:      # the dropout on the FFN output is applied by the add_layernorm that consumes it (drop_p=dp)
+            # hidden dropout: one kernel forward; its backward and the ReLU backward ride in linear2's dgrad epilogue
+            hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True, masked_by_consumer=True)
+            hdn = ops.hidden_dropout(hdn, dp)
+            return ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True, mask_dx=True, dx_scale=1.0 / (1.0 - dp))
         hdn = ops.linear(xb, l.linear1.weight, l.linear1.bias, relu=True, masked_by_consumer=True)
         return ops.linear(hdn, l.linear2.weight, l.linear2.bias, out_fp32=True, mask_dx=True)
 
@@ -281,13 +282,11 @@ class Transformer(nn.Module):
         qk, v = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((0, 512), (512, 768)), xpb, xb)
         o, _ = ops.mha(qk, None, v, kpm, n, NHEAD, S, S, 32 ** -0.5, packed=True, drop_p=dp)
         att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
-        if dp > 0:
-            att = F.dropout(att, dp, True)
-        x32, xb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias)
+        x32, xb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, drop_p=dp)      # residual dropouts ride in the LN kernels
         f = self._ffn(l, xb, dp)
         if need_pos:
-            return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias, pos)
-        return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias) + (None,)
+            return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias, pos, drop_p=dp)
+        return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias, drop_p=dp) + (None,)
 
     # ---- one decoder layer (reference transformer.py:684-751); rows are (b,t) batch-major
     def _dec_layer(self, l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S):
@@ -302,9 +301,7 @@ class Transformer(nn.Module):
             qk, v = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((0, 512), (512, 768)), xqb, xb)
             o, w = ops.mha(qk, None, v, kpm_q, B, NHEAD, T, T, 32 ** -0.5, packed=True, drop_p=dp)
             att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
-        if dp > 0:
-            att = F.dropout(att, dp, True)
-        x32, xb, xqb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, qp)
+        x32, xb, xqb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, qp, drop_p=dp)
         c = l.cross_attn_image
         if self.fused_xattn and S >= 43:                # K/V projection fused into the attention kernel (K, V never reach HBM)
             (q,) = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256),), xqb)
@@ -313,11 +310,9 @@ class Transformer(nn.Module):
             q, k, v = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256), (256, 512), (512, 768)), xqb, mempb, memb)
             o, cw = ops.mha(q, k, v, kpm_mem, B * T, NHEAD, 1, S, 32 ** -0.5, drop_p=dp)
         att = ops.linear(o, c.out_proj.weight, c.out_proj.bias, out_fp32=True)
-        if dp > 0:
-            att = F.dropout(att, dp, True)
-        x32, xb = ops.add_layernorm(x32, att, l.norm3.weight, l.norm3.bias)
+        x32, xb = ops.add_layernorm(x32, att, l.norm3.weight, l.norm3.bias, drop_p=dp)
         f = self._ffn(l, xb, dp)
-        x32, xb, xqb = ops.add_layernorm(x32, f, l.norm4.weight, l.norm4.bias, qp)
+        x32, xb, xqb = ops.add_layernorm(x32, f, l.norm4.weight, l.norm4.bias, qp, drop_p=dp)
         return x32, xb, xqb, w, cw
 
 
@@ -431,6 +426,8 @@ class TubeDETR(nn.Module):
         # are independent of the backbone in forward AND backward (autograd replays a node on the stream it ran on), so they
         # fill the launch gaps of the convolution GEMMs instead of extending the critical path.  Joined right before first use.
         ids, am = self._tokenize(captions, dev)
+        if self.training:
+            ops.advance_dropout_seed(dev)
         side = self.text_side_stream
         if side:
             tstream = _TEXT_STREAMS.get(dev)

@@ -28,6 +28,30 @@ def adopt_bf16_weight(w, wb):
     _WCACHE[(w.data_ptr(), tuple(w.shape))] = ((w._version,), wb)
 
 
+_DROP = {}          # device -> [seed tensor (int64, device), host site counter]
+
+
+def _drop_state(device):
+    st = _DROP.get(device)
+    if st is None:
+        seed = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFF], dtype=torch.int64, device=device)
+        st = _DROP[device] = [seed, 0]
+    return st
+
+
+def advance_dropout_seed(device):
+    """once per training step (TubeDETR._encode): a captured in-place add, so every CUDA-graph replay draws new masks"""
+    _drop_state(device)[0].add_(1)
+
+
+def dropout_keep(shape, p, device):
+    """uint8 keep mask of `shape` (1 = keep with probability 1 - p) from ONE kernel launch"""
+    st = _drop_state(device)
+    st[1] += 1
+    keep = torch.empty(shape, dtype=torch.uint8, device=device)
+    return K.dropout_mask(keep, st[0], st[1], p)
+
+
 def _as_bf16(t):
     """bf16 view of a gradient.  Kernels that produce an fp32 gradient (LayerNorm backward) also write its bf16 copy and
     attach it as `_tdb_bf16`, so the consumer's GEMM operand needs no separate cast kernel."""
@@ -56,10 +80,11 @@ class LinearFn(torch.autograd.Function):
     """y = relu?(x @ W^T + b): x bf16 [R,K], W fp32 [N,K] (bf16 copy cached), y bf16 or fp32 [R,N]."""
 
     @staticmethod
-    def forward(ctx, x, W, b, relu, out_fp32, mask_dx=False, masked_by_consumer=False):
+    def forward(ctx, x, W, b, relu, out_fp32, mask_dx=False, masked_by_consumer=False, dx_scale=1.0):
         # mask_dx: x is a post-ReLU activation -> dgrad applies (x > 0) in its epilogue (ReLU backward of the producer);
-        # masked_by_consumer: this op's own ReLU backward is done by the consumer that way.
-        ctx.mask_dx, ctx.masked_by_consumer = mask_dx, masked_by_consumer
+        # masked_by_consumer: this op's own ReLU backward is done by the consumer that way;
+        # dx_scale: constant factor on dx in the same epilogue (1 / (1 - p) when x went through HiddenDropoutFn).
+        ctx.mask_dx, ctx.masked_by_consumer, ctx.dx_scale = mask_dx, masked_by_consumer, float(dx_scale)
         assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
         Wb = bf16_weight(W)
         R, Kd = x.shape
@@ -83,16 +108,48 @@ class LinearFn(torch.autograd.Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(R, Kd, dtype=torch.bfloat16, device=x.device)
-            gemm(dyb, Wb, dx, R, Kd, N, b_major=1, mask=x if ctx.mask_dx else None)
+            gemm(dyb, Wb, dx, R, Kd, N, b_major=1, mask=x if ctx.mask_dx else None,
+                 scale=_const_vec(x.device, Kd, ctx.dx_scale) if ctx.dx_scale != 1.0 else None)
         if ctx.needs_input_grad[1]:
             dW = wgrad_into(dyb, x, torch.empty(N, Kd, dtype=torch.float32, device=x.device))
         if ctx.needs_input_grad[2]:
             db = K.colsum_bf16(dyb, torch.empty(N, dtype=torch.float32, device=x.device))
-        return dx, dW, db, None, None, None, None
+        return dx, dW, db, None, None, None, None, None
 
 
-def linear(x, W, b, relu=False, out_fp32=False, mask_dx=False, masked_by_consumer=False):
-    return LinearFn.apply(x, W, b, relu, out_fp32, mask_dx, masked_by_consumer)
+def linear(x, W, b, relu=False, out_fp32=False, mask_dx=False, masked_by_consumer=False, dx_scale=1.0):
+    return LinearFn.apply(x, W, b, relu, out_fp32, mask_dx, masked_by_consumer, dx_scale)
+
+
+_CONST = {}
+
+
+def _const_vec(device, n, value):
+    key = (device, n, value)
+    if key not in _CONST:
+        _CONST[key] = torch.full((n,), value, dtype=torch.float32, device=device)
+    return _CONST[key]
+
+
+class HiddenDropoutFn(torch.autograd.Function):
+    """y = keep * x / (1 - p) on a post-ReLU bf16 activation (FFN hidden dropout).  ONE kernel, no mask tensor; the backward
+    is the identity because the consuming linear does it in its dgrad epilogue (mask_dx=True: y > 0 <=> kept and ReLU-active;
+    dx_scale = 1 / (1 - p)) and the producing linear is built with masked_by_consumer=True."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        st = _drop_state(x.device)
+        st[1] += 1
+        x = x.contiguous()
+        return K.dropout_bf16(x, torch.empty_like(x), st[0], st[1], p)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, None
+
+
+def hidden_dropout(x, p):
+    return HiddenDropoutFn.apply(x, float(p))
 
 
 class InProjFn(torch.autograd.Function):
@@ -157,7 +214,7 @@ class MHAFn(torch.autograd.Function):
         pbar = torch.empty(B, Lq, Lk, dtype=torch.float32, device=q.device)
         keep = pdrop = None
         if drop_p > 0:
-            keep = (torch.rand(B, H, Lq, Lk, device=q.device) >= drop_p).to(torch.uint8)
+            keep = dropout_keep((B, H, Lq, Lk), drop_p, q.device)
             pdrop = torch.empty_like(p)
         K.mha_fwd(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pdrop, keep_scale=1.0 / (1.0 - drop_p))
         ctx.cfg = (B, H, Lq, Lk, scale, packed, drop_p)
@@ -200,7 +257,7 @@ class XAttnFusedFn(torch.autograd.Function):
         o = torch.empty(F, 256, dtype=torch.bfloat16, device=q.device)
         p = torch.empty(F, 8, 1, S, dtype=torch.float32, device=q.device)
         pbar = torch.empty(F, 1, S, dtype=torch.float32, device=q.device)
-        keep = (torch.rand(F, 8, 1, S, device=q.device) >= drop_p).to(torch.uint8) if drop_p > 0 else None
+        keep = dropout_keep((F, 8, 1, S), drop_p, q.device) if drop_p > 0 else None
         K.xattn_fused_fwd(q, mempb, memb, Wb[256:768], b[512:768], kpm, o, p, pbar, F, S, scale, keep=keep,
                           keep_scale=1.0 / (1.0 - drop_p))
         ctx.cfg = (F, S, scale, drop_p)
@@ -246,10 +303,12 @@ def xattn_fused(q, mempb, memb, W, b, kpm, F, S, scale, drop_p=0.0):
 
 
 class AddLayerNormFn(torch.autograd.Function):
-    """y = LayerNorm(x + r) over d=256 (fp32 statistics).  Returns (y fp32, y bf16, (y + pos) bf16 or None)."""
+    """y = LayerNorm(x + dropout_p(r)) over d=256 (fp32 statistics).  Returns (y fp32, y bf16, (y + pos) bf16 or None).
+    drop_p > 0: the residual dropout of the reference (`src + self.dropoutN(src2)`, transformer.py:641-645, 721-750) runs inside
+    the LayerNorm kernels from a counter-based hash (forward and backward regenerate the same keep bits; no mask tensor)."""
 
     @staticmethod
-    def forward(ctx, x, r, gamma, beta, pos, eps):
+    def forward(ctx, x, r, gamma, beta, pos, eps, drop_p=0.0):
         assert x.dtype == torch.float32 and x.is_contiguous()
         rows, D = x.shape
         if r is not None:
@@ -260,9 +319,15 @@ class AddLayerNormFn(torch.autograd.Function):
         ypb = torch.empty_like(yb) if pos is not None else None
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
-        K.layernorm_fwd(x, r, gamma, beta, pos, y, yb, ypb, mean, rstd, rows, D, eps)
+        drop = None
+        if drop_p > 0 and r is not None:
+            st = _drop_state(x.device)
+            st[1] += 1
+            drop = (st[0], st[1], float(drop_p))
+        K.layernorm_fwd(x, r, gamma, beta, pos, y, yb, ypb, mean, rstd, rows, D, eps, drop=drop)
         ctx.save_for_backward(x, r, gamma, mean, rstd)
         ctx.has_r = r is not None
+        ctx.drop = drop
         ctx.pos_dtype = pos.dtype if pos is not None else None
         if ypb is None:
             return y, yb
@@ -273,25 +338,32 @@ class AddLayerNormFn(torch.autograd.Function):
         x, r, gamma, mean, rstd = ctx.saved_tensors
         rows, D = x.shape
         if dy is None and dyb is None and dypb is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         dy = dy.contiguous() if dy is not None else None
         dyb = dyb.contiguous() if dyb is not None else None
         dypb = dypb.contiguous() if dypb is not None else None
         dz = torch.empty_like(x)
-        dzb = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device) if ctx.has_r else None
+        dzb = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device) if (ctx.has_r and ctx.drop is None) else None
         dgb = torch.empty(2 * D, dtype=torch.float32, device=x.device)     # contiguous [dgamma | dbeta]: one reduction launch
         dg, db = dgb[:D], dgb[D:]
-        K.layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dg, db, rows, D, dy2=dyb, dy3=dypb, dz_bf=dzb)   # sums the three grads in-kernel
+        dr = drb = None
+        if ctx.drop is not None:
+            dr, drb = torch.empty_like(x), torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
+        K.layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dg, db, rows, D, dy2=dyb, dy3=dypb, dz_bf=dzb,   # sums the three grads in-kernel
+                        drop=ctx.drop, dr=dr, dr_bf=drb)
         if dzb is not None:
             dz._tdb_bf16 = dzb
+        if dr is not None:
+            dr._tdb_bf16 = drb
         dpos = None
         if ctx.needs_input_grad[4] and dypb is not None:   # (y + pos): pos is the time-query embedding in the decoder
             dpos = dypb.to(ctx.pos_dtype)
-        return dz, (dz if ctx.has_r else None), dg, db, dpos, None
+        gr = (dr if dr is not None else dz) if ctx.has_r else None
+        return dz, gr, dg, db, dpos, None, None
 
 
-def add_layernorm(x, r, gamma, beta, pos=None, eps=1e-5):
-    return AddLayerNormFn.apply(x, r, gamma, beta, pos, eps)
+def add_layernorm(x, r, gamma, beta, pos=None, eps=1e-5, drop_p=0.0):
+    return AddLayerNormFn.apply(x, r, gamma, beta, pos, eps, float(drop_p))
 
 
 class BackboneJointFn(torch.autograd.Function):
