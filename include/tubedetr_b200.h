@@ -115,12 +115,15 @@ int tdb_cast_add_bf16(const float* x, const float* add, void* y, int64_t n, void
 int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta, const float* pos, float* y,
                       void* y_bf, void* ypos_bf, float* mean, float* rstd, int rows, int D, float eps,
                       const int64_t* drop_seed, int64_t drop_site, float drop_p, void* stream);
-int tdb_layernorm_bwd_blocks(int rows); /* partial workspace = blocks * 2 * D floats */
+int tdb_layernorm_bwd_blocks(int rows); /* partial workspace = blocks * 3 * D floats */
 /* incoming gradient = dy (fp32, may be NULL) + dy2_bf + dy3_bf (bf16, may be NULL): grads of y, bf16(y), bf16(y+pos) */
 int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void* dy3_bf, const float* x, const float* r,
                       const float* gamma, const float* mean, const float* rstd, float* dz, void* dz_bf /* optional bf16 copy */,
                       float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate,
-                      const int64_t* drop_seed, int64_t drop_site, float drop_p, float* dr, void* dr_bf, void* stream);
+                      const int64_t* drop_seed, int64_t drop_site, float drop_p, float* dr, void* dr_bf,
+                      float* dbias /* optional [D]: column sums of the gradient of r = bias gradient of the layer that produced r;
+                                      one reduction launch when [dgamma | dbeta | dbias] are contiguous */,
+                      void* stream);
 /* column sums of a bf16 [rows][N] matrix (bias gradients), two-stage fixed order; partial = nparts * N floats */
 int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* partial, int nparts, float* out, int accumulate,
                     void* stream);

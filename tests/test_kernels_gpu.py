@@ -347,8 +347,11 @@ def test_layernorm_fused_residual_dropout():
     ref.backward(dy)
     dz, dr = torch.empty_like(x), torch.empty_like(x)
     drb = torch.empty(rows, D, dtype=torch.bfloat16, device="cuda")
-    dgb = torch.empty(2 * D, device="cuda")
-    K.layernorm_bwd(dy, x, r, gm, mean, rstd, dz, dgb[:D], dgb[D:], rows, D, drop=(seed, site, p), dr=dr, dr_bf=drb)
+    dgb = torch.empty(3 * D, device="cuda")
+    K.layernorm_bwd(dy, x, r, gm, mean, rstd, dz, dgb[:D], dgb[D:2 * D], rows, D, drop=(seed, site, p), dr=dr, dr_bf=drb,
+                    dbias=dgb[2 * D:])
+    _close(dgb[2 * D:], rr.grad.sum(0), 1e-4)            # bias gradient of the layer that produced r, for free
+    _close(dgb[D:2 * D], dy.sum(0), 1e-4)
     _close(dz, xr.grad, 1e-4)
     _close(dr, rr.grad, 1e-4)
     _close(drb, rr.grad, 1e-2)

@@ -1,4 +1,5 @@
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/dp_check.py 2>&1 | grep -v "Warning\|warn" | tail -12 | tee gpurun_out/dp_check.txt
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 10 --warmup 3 2>gpurun_out/bench2_err.log | tail -1 > gpurun_out/bench_n2_overlap.json; cut -c1-700 gpurun_out/bench_n2_overlap.json; tail -2 gpurun_out/bench2_err.log
-TDB_OVERLAP=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 2 --steps 10 --warmup 3 2>gpurun_out/bench2s_err.log | tail -1 > gpurun_out/bench_n2_serial.json; cut -c1-700 gpurun_out/bench_n2_serial.json; tail -2 gpurun_out/bench2s_err.log
+tools/run_gpu_tests.sh tests/test_kernels_gpu.py tests/test_model_gpu.py tests/test_fullsize_gpu.py tests/test_backbone_gpu.py
+python bench.py --steps 10 --warmup 3 --skip-cpu 2>gpurun_out/bench_err.log | tail -1 > gpurun_out/bench_r01e.json; cat gpurun_out/bench_r01e.json | cut -c1-600; python -c "
+import json; d=json.load(open('gpurun_out/bench_r01e.json')); print('dedup', d.get('dedup_slow_frames')); print('e2e', d['e2e']); print('optim', d['optimizer_step'].get('ms'))"; tail -3 gpurun_out/bench_err.log
+python tools/step_ablation.py > gpurun_out/step_ablation.txt 2> gpurun_out/step_ablation.err; cat gpurun_out/step_ablation.txt; grep -v Warn gpurun_out/step_ablation.err | tail -3

@@ -316,10 +316,11 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
   const unsigned long long dbase = drop_seed ? drop_base(drop_seed, drop_site) : 0ull;
   __shared__ float sg[8][D];
   __shared__ float sb[8][D];
+  __shared__ float sr[8][D];
   int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float ag[PER], ab[PER];
-#pragma unroll
-  for (int i = 0; i < PER; ++i) ag[i] = ab[i] = 0.f;
+  float ag[PER], ab[PER], ar[PER];     // column sums of dy * xhat (dgamma), dy (dbeta), and the gradient of r (bias gradient of the
+#pragma unroll                       // linear layer that produced r: its separate column-sum launches disappear)
+  for (int i = 0; i < PER; ++i) ag[i] = ab[i] = ar[i] = 0.f;
   for (int row = blockIdx.x * 8 + wib; row < rows; row += gridDim.x * 8) {
     float m = mean[row], rs = rstd[row];
     float g[PER], xh[PER];
@@ -353,8 +354,10 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
         if (dr) dr[e] = od;
         if (dr_bf) dr_bf[e] = __float2bfloat16(od);
         if (dz_bf) dz_bf[e] = __float2bfloat16(o);
-      } else if (dz_bf) {
-        dz_bf[e] = __float2bfloat16(o);
+        ar[i] += od;
+      } else {
+        if (dz_bf) dz_bf[e] = __float2bfloat16(o);
+        ar[i] += o;
       }
     }
   }
@@ -362,17 +365,20 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
   for (int i = 0; i < PER; ++i) {
     sg[wib][i * 32 + lane] = ag[i];
     sb[wib][i * 32 + lane] = ab[i];
+    sr[wib][i * 32 + lane] = ar[i];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, cc = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       a += sg[w][c];
       b += sb[w][c];
+      cc += sr[w][c];
     }
-    partial[((long long)blockIdx.x * 2 + 0) * D + c] = a;
-    partial[((long long)blockIdx.x * 2 + 1) * D + c] = b;
+    partial[((long long)blockIdx.x * 3 + 0) * D + c] = a;
+    partial[((long long)blockIdx.x * 3 + 1) * D + c] = b;
+    partial[((long long)blockIdx.x * 3 + 2) * D + c] = cc;
   }
 }
 // out[c] (+)= sum_b partial[b][c] in fixed order; used for dgamma/dbeta (stride 2*D) and generic column sums.
@@ -620,7 +626,8 @@ extern "C" int tdb_layernorm_bwd_blocks(int rows) {
 extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void* dy3_bf, const float* x, const float* r,
                                  const float* gamma, const float* mean, const float* rstd, float* dz, void* dz_bf,
                                  float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate,
-                                 const int64_t* drop_seed, int64_t drop_site, float drop_p, float* dr, void* dr_bf, void* stream_) {
+                                 const int64_t* drop_seed, int64_t drop_site, float drop_p, float* dr, void* dr_bf, float* dbias,
+                                 void* stream_) {
   TDB_REQUIRE((dy || dy2_bf || dy3_bf) && x && gamma && mean && rstd && dz && partial && rows > 0 && D == 256, "tdb_layernorm_bwd: bad args");
   TDB_REQUIRE(!drop_seed || (r && drop_p > 0.f && drop_p < 1.f && (dr || dr_bf)), "tdb_layernorm_bwd: residual dropout needs r, 0 < p < 1 and a dr output");
   const uint32_t thr = drop_seed ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
@@ -629,14 +636,18 @@ extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void
   TDB_CHECK_CUDA(tdb_launch(layernorm_bwd_kernel<256>, dim3(blocks), dim3(256), 0, STREAM, dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows,
                             (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale, dr, (bf16*)dr_bf));
   TDB_CHECK_CUDA(cudaGetLastError());
-  if (dgamma && dbeta == dgamma + D) {   // [dgamma | dbeta] contiguous: the partial rows [2D] reduce in ONE launch
-    TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((2 * D + 31) / 32), dim3(32, 8), 0, STREAM, partial, blocks, 2 * D, 2 * D, dgamma, accumulate));
+  if (dgamma && dbeta == dgamma + D) {   // [dgamma | dbeta (| dbias)] contiguous: the partial rows reduce in ONE launch
+    const int cols = (dbias == dgamma + 2 * D) ? 3 * D : 2 * D;
+    TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((cols + 31) / 32), dim3(32, 8), 0, STREAM, partial, blocks, 3 * D, cols, dgamma, accumulate));
+    if (dbias && cols == 2 * D)
+      TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial + 2 * D, blocks, 3 * D, D, dbias, accumulate));
     TDB_CHECK_CUDA(cudaGetLastError());
     tdb_count_launch(2);
     return TDB_OK;
   }
-  if (dgamma) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial, blocks, 2 * D, D, dgamma, accumulate));
-  if (dbeta) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial + D, blocks, 2 * D, D, dbeta, accumulate));
+  if (dgamma) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial, blocks, 3 * D, D, dgamma, accumulate));
+  if (dbeta) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial + D, blocks, 3 * D, D, dbeta, accumulate));
+  if (dbias) TDB_CHECK_CUDA(tdb_launch(colsum_partials_kernel, dim3((D + 31) / 32), dim3(32, 8), 0, STREAM, partial + 2 * D, blocks, 3 * D, D, dbias, accumulate));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(3);
   return TDB_OK;

@@ -51,12 +51,12 @@ def layernorm_fwd(x, r, gamma, beta, pos, y, y_bf, ypos_bf, mean, rstd, rows, D,
 
 
 def layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dgamma, dbeta, rows, D, accumulate=False, dy2=None, dy3=None, dz_bf=None,
-                  drop=None, dr=None, dr_bf=None):
+                  drop=None, dr=None, dr_bf=None, dbias=None):
     nb = int(lib().tdb_layernorm_bwd_blocks(rows))
-    partial = torch.empty(nb * 2 * D, dtype=torch.float32, device=x.device)
+    partial = torch.empty(nb * 3 * D, dtype=torch.float32, device=x.device)
     seed, site, p = drop if drop is not None else (None, 0, 0.0)
     check(lib().tdb_layernorm_bwd(ptr(dy), ptr(dy2), ptr(dy3), ptr(x), ptr(r), ptr(gamma), ptr(mean), ptr(rstd), ptr(dz), ptr(dz_bf), ptr(dgamma),
-                                  ptr(dbeta), ptr(partial), rows, D, int(accumulate), ptr(seed), _i64(site), _f(p), ptr(dr), ptr(dr_bf),
+                                  ptr(dbeta), ptr(partial), rows, D, int(accumulate), ptr(seed), _i64(site), _f(p), ptr(dr), ptr(dr_bf), ptr(dbias),
                                   stream_ptr()), "layernorm_bwd")
 
 

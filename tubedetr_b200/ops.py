@@ -113,7 +113,11 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dW = wgrad_into(dyb, x, torch.empty(N, Kd, dtype=torch.float32, device=x.device))
         if ctx.needs_input_grad[2]:
-            db = K.colsum_bf16(dyb, torch.empty(N, dtype=torch.float32, device=x.device))
+            pre = getattr(dy, "_tdb_colsum", None)       # LayerNorm backward already summed this gradient over rows
+            if pre is not None and pre.numel() == N and not (ctx.relu and not ctx.masked_by_consumer):
+                db = pre
+            else:
+                db = K.colsum_bf16(dyb, torch.empty(N, dtype=torch.float32, device=x.device))
         return dx, dW, db, None, None, None, None, None
 
 
@@ -344,17 +348,23 @@ class AddLayerNormFn(torch.autograd.Function):
         dypb = dypb.contiguous() if dypb is not None else None
         dz = torch.empty_like(x)
         dzb = torch.empty(rows, D, dtype=torch.bfloat16, device=x.device) if (ctx.has_r and ctx.drop is None) else None
-        dgb = torch.empty(2 * D, dtype=torch.float32, device=x.device)     # contiguous [dgamma | dbeta]: one reduction launch
-        dg, db = dgb[:D], dgb[D:]
+        # contiguous [dgamma | dbeta | column sums of r's gradient]: one reduction launch; the third block IS the bias gradient of
+        # the linear layer that produced r (out_proj / linear2), handed over through the `_tdb_colsum` side channel
+        dgb = torch.empty(3 * D if ctx.has_r else 2 * D, dtype=torch.float32, device=x.device)
+        dg, db = dgb[:D], dgb[D:2 * D]
+        dbias = dgb[2 * D:] if ctx.has_r else None
         dr = drb = None
         if ctx.drop is not None:
             dr, drb = torch.empty_like(x), torch.empty(rows, D, dtype=torch.bfloat16, device=x.device)
         K.layernorm_bwd(dy, x, r, gamma, mean, rstd, dz, dg, db, rows, D, dy2=dyb, dy3=dypb, dz_bf=dzb,   # sums the three grads in-kernel
-                        drop=ctx.drop, dr=dr, dr_bf=drb)
+                        drop=ctx.drop, dr=dr, dr_bf=drb, dbias=dbias)
         if dzb is not None:
             dz._tdb_bf16 = dzb
         if dr is not None:
             dr._tdb_bf16 = drb
+            dr._tdb_colsum = dbias
+        elif ctx.has_r:
+            dz._tdb_colsum = dbias
         dpos = None
         if ctx.needs_input_grad[4] and dypb is not None:   # (y + pos): pos is the time-query embedding in the decoder
             dpos = dypb.to(ctx.pos_dtype)
