@@ -8,6 +8,50 @@ from .gemm import effective_splits, gemm, splitk_reduce
 
 _WCACHE = {}
 
+# ---- weight-gradient work on a second stream ------------------------------------------------------------------------------
+# In backward only the data gradients (dgrad) feed the next node; weight gradients (wgrad GEMM + split-K reduce + bias column
+# sums) are leaves.  Most backward GEMMs of this model fill less than one wave of the 148 SMs (25 slow frames, 3525 encoder
+# tokens, 100 time queries), so every backward node forks its wgrad work onto a side stream that runs concurrently with its
+# dgrad, and joins before it returns (the caching allocator and the reused scratch buffers never see cross-stream lifetimes
+# beyond one node).  Captured by CUDA graphs as parallel branches.  TDB_WGRAD_STREAM=0 disables it.
+import os as _os
+
+WGRAD_STREAM = _os.environ.get("TDB_WGRAD_STREAM", "1") != "0"
+_SIDE = {}
+
+
+class wgrad_scope:
+    """with sc: ...   -> the enclosed launches go to the side stream, ordered after everything enqueued on the main stream so
+    far; sc.join() -> the main stream waits for the side stream."""
+
+    def __init__(self, device):
+        self.on = WGRAD_STREAM and torch.device(device).type == "cuda"
+        if self.on:
+            self.main = torch.cuda.current_stream(device)
+            side = _SIDE.get(device)
+            if side is None:
+                side = _SIDE[device] = torch.cuda.Stream(device=device)
+            self.side = side
+            self.used = False
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.main)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+            self.used = True
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self._ctx.__exit__(*a)
+        return False
+
+    def join(self):
+        if self.on and self.used:
+            self.main.wait_stream(self.side)
+            self.used = False
+
 
 def bf16_weight(w):
     """bf16 copy of an fp32 parameter, refreshed when the parameter changes (optimizer steps bump _version)."""
@@ -106,18 +150,21 @@ class LinearFn(torch.autograd.Function):
         R, Kd = x.shape
         N = W.shape[0]
         dx = dW = db = None
+        sc = wgrad_scope(x.device)
+        with sc:                                          # weight / bias gradients: side stream, concurrent with the dgrad below
+            if ctx.needs_input_grad[1]:
+                dW = wgrad_into(dyb, x, torch.empty(N, Kd, dtype=torch.float32, device=x.device))
+            if ctx.needs_input_grad[2]:
+                pre = getattr(dy, "_tdb_colsum", None)       # LayerNorm backward already summed this gradient over rows
+                if pre is not None and pre.numel() == N and not (ctx.relu and not ctx.masked_by_consumer):
+                    db = pre
+                else:
+                    db = K.colsum_bf16(dyb, torch.empty(N, dtype=torch.float32, device=x.device))
         if ctx.needs_input_grad[0]:
             dx = torch.empty(R, Kd, dtype=torch.bfloat16, device=x.device)
             gemm(dyb, Wb, dx, R, Kd, N, b_major=1, mask=x if ctx.mask_dx else None,
                  scale=_const_vec(x.device, Kd, ctx.dx_scale) if ctx.dx_scale != 1.0 else None)
-        if ctx.needs_input_grad[1]:
-            dW = wgrad_into(dyb, x, torch.empty(N, Kd, dtype=torch.float32, device=x.device))
-        if ctx.needs_input_grad[2]:
-            pre = getattr(dy, "_tdb_colsum", None)       # LayerNorm backward already summed this gradient over rows
-            if pre is not None and pre.numel() == N and not (ctx.relu and not ctx.masked_by_consumer):
-                db = pre
-            else:
-                db = K.colsum_bf16(dyb, torch.empty(N, dtype=torch.float32, device=x.device))
+        sc.join()
         return dx, dW, db, None, None, None, None, None
 
 
@@ -180,21 +227,24 @@ class InProjFn(torch.autograd.Function):
         dW = torch.zeros_like(W) if ctx.needs_input_grad[0] else None
         db = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device) if ctx.needs_input_grad[1] else None
         dxs = []
+        sc = wgrad_scope(W.device)
         for i, ((lo, hi), x, dy) in enumerate(zip(ctx.segs, xs, dys)):
             if dy is None:
                 dxs.append(None)
                 continue
             dyb = _as_bf16(dy).contiguous()
-            if dW is not None:
-                wgrad_into(dyb, x, dW[lo:hi])
-            if db is not None:
-                K.colsum_bf16(dyb, db[lo:hi])
+            with sc:
+                if dW is not None:
+                    wgrad_into(dyb, x, dW[lo:hi])
+                if db is not None:
+                    K.colsum_bf16(dyb, db[lo:hi])
             if ctx.needs_input_grad[3 + i]:
                 dx = torch.empty_like(x)
                 gemm(dyb, Wb[lo:hi], dx, x.shape[0], x.shape[1], hi - lo, b_major=1)
                 dxs.append(dx)
             else:
                 dxs.append(None)
+        sc.join()
         return (dW, db, None) + tuple(dxs)
 
 
@@ -286,12 +336,14 @@ class XAttnFusedFn(torch.autograd.Function):
         K.xattn_bwd(q.contiguous(), kp, vp, do, p, dpbar, dq, dk, dv, F, S, scale, keep=keep, keep_scale=1.0 / (1.0 - drop_p))
         dW = torch.zeros_like(W) if ctx.needs_input_grad[3] else None
         db = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device) if ctx.needs_input_grad[4] else None
-        if dW is not None:
-            wgrad_into(dk, mempb, dW[256:512])
-            wgrad_into(dv, memb, dW[512:768])
-        if db is not None:
-            K.colsum_bf16(dk, db[256:512])
-            K.colsum_bf16(dv, db[512:768])
+        sc = wgrad_scope(q.device)
+        with sc:
+            if dW is not None:
+                wgrad_into(dk, mempb, dW[256:512])
+                wgrad_into(dv, memb, dW[512:768])
+            if db is not None:
+                K.colsum_bf16(dk, db[256:512])
+                K.colsum_bf16(dv, db[512:768])
         dmp = dmb = None
         if ctx.needs_input_grad[1]:
             dmp = torch.empty_like(mempb)
@@ -299,6 +351,7 @@ class XAttnFusedFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             dmb = torch.empty_like(memb)
             gemm(dv, Wb[512:768], dmb, R, 256, 256, b_major=1)
+        sc.join()
         return dq, dmp, dmb, dW, db, None, None, None, None, None
 
 

@@ -228,9 +228,12 @@ class ResNet101Engine:
     def backward(self, ctx, W, g_out, grads, prefix="backbone.0.body."):
         """g_out: bf16 [N*h*w, 2048] = dL/d(pre-ReLU output of layer4.2), already masked by (feat > 0).
         grads: dict name -> fp32 tensor (torch layout) written in place for every layer2-4 conv weight."""
+        from .ops import wgrad_scope
         N, tag = ctx["N"], ctx["tag"]
         blocks = ctx["blocks"]
+        sc = wgrad_scope(g_out.device)       # weight gradients on a side stream, concurrent with the dgrad chain of the same block
         for i in range(len(blocks) - 1, -1, -1):
+            sc.join()                        # the scratch gradients (g2 / g1 / gout) of the previous block are about to be overwritten
             r = blocks[i]
             name, h, w, ho, wo, width, cin, cout = (r[k] for k in ("name", "h", "w", "ho", "wo", "width", "cin", "cout"))
             R, Ro = N * h * w, N * ho * wo
@@ -240,7 +243,8 @@ class ResNet101Engine:
             x, y1, y2 = r["x"], r["y1"], r["y2"]
             last = i == 0                                   # layer2.0: its input is the frozen layer1 output
             # ---- conv3
-            self._wgrad(g_out, y2, cout, width, Ro, s3, grads[prefix + name + "conv3.weight"])
+            with sc:
+                self._wgrad(g_out, y2, cout, width, Ro, s3, grads[prefix + name + "conv3.weight"])
             if r["stride"] == 1:
                 Rp = N * (h + 2) * (w + 2)
                 wp = w + 2
@@ -248,24 +252,28 @@ class ResNet101Engine:
                 g2 = self.buf(f"{tag}:g2p", (Rp, width), zero=True)
                 gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=REMAP_C2P, img_hw=(h, w))
                 # ---- conv2 (implicit 3x3 over the haloed grid)
-                self._wgrad(g2, y1, width, width, Rp, s2, grads[prefix + name + "conv2.weight"], z_b_off1=taps)
+                with sc:
+                    self._wgrad(g2, y1, width, width, Rp, s2, grads[prefix + name + "conv2.weight"], z_b_off1=taps)
                 g1 = self.buf(f"{tag}:g1", (R, width))
                 gemm(g2, w2s, g1, Rp, width, width, b_major=1, ntaps=9, a_off1=[-t for t in taps],
                      b_off0=[t * width for t in range(9)], mask=y1, remap=REMAP_P2C, img_hw=(h, w))
             else:
                 g2 = self.buf(f"{tag}:g2c", (Ro, width))
                 gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2)
-                self._wgrad(g2, r["col"], width, 9 * width, Ro, s2, grads[prefix + name + "conv2.weight"], taps=9)
+                with sc:
+                    self._wgrad(g2, r["col"], width, 9 * width, Ro, s2, grads[prefix + name + "conv2.weight"], taps=9)
                 dcol = self.buf(f"{tag}:dcol", (Ro, 9 * width))
                 gemm(g2, w2s, dcol, Ro, 9 * width, width, b_major=1)
                 g1 = self.buf(f"{tag}:g1", (R, width))
                 K.col2im3x3s2_mask(dcol, y1, g1, N, h, w, width)
             # ---- conv1
-            self._wgrad(g1, x, width, cin, R, s1, grads[prefix + name + "conv1.weight"])
+            with sc:
+                self._wgrad(g1, x, width, cin, R, s1, grads[prefix + name + "conv1.weight"])
             resid = g_out
             if r["first"]:
                 _, wds, sdn, _ = W[name + "downsample.0"]
-                self._wgrad(g_out, r["xs"], cout, cin, Ro, sdn, grads[prefix + name + "downsample.0.weight"])
+                with sc:
+                    self._wgrad(g_out, r["xs"], cout, cin, Ro, sdn, grads[prefix + name + "downsample.0.weight"])
                 if not last:
                     dxs = self.buf(f"{tag}:dxs", (Ro, cin))
                     gemm(g_out, wds, dxs, Ro, cin, cout, b_major=1)
@@ -278,4 +286,5 @@ class ResNet101Engine:
             gprev = self.buf(f"{tag}:gout{i % 2}", (R, cin))
             gemm(g1, w1s, gprev, R, cin, width, b_major=1, residual=resid, mask=x)
             g_out = gprev
+        sc.join()
         return grads
