@@ -52,6 +52,18 @@ class wgrad_scope:
             self.main.wait_stream(self.side)
             self.used = False
 
+    def mark(self):
+        """event after everything enqueued on the side stream so far (None when the side stream is off / idle)"""
+        if not (self.on and self.used):
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        return ev
+
+    def wait(self, ev):
+        if ev is not None:
+            self.main.wait_event(ev)
+
 
 def bf16_weight(w):
     """bf16 copy of an fp32 parameter, refreshed when the parameter changes (optimizer steps bump _version)."""

@@ -231,9 +231,15 @@ class ResNet101Engine:
         from .ops import wgrad_scope
         N, tag = ctx["N"], ctx["tag"]
         blocks = ctx["blocks"]
-        sc = wgrad_scope(g_out.device)       # weight gradients on a side stream, concurrent with the dgrad chain of the same block
+        # Weight gradients run on a side stream, concurrent with the dgrad chain.  The scratch gradients are double buffered by
+        # block parity (the block-output gradient triple buffered), so the main stream only has to wait for the side work of the
+        # block TWO iterations back before it overwrites that block's scratch: the dgrad chain never stalls on the latest wgrad.
+        sc = wgrad_scope(g_out.device)
+        pending = []
         for i in range(len(blocks) - 1, -1, -1):
-            sc.join()                        # the scratch gradients (g2 / g1 / gout) of the previous block are about to be overwritten
+            if len(pending) >= 2:
+                sc.wait(pending.pop(0))
+            par = i % 2
             r = blocks[i]
             name, h, w, ho, wo, width, cin, cout = (r[k] for k in ("name", "h", "w", "ho", "wo", "width", "cin", "cout"))
             R, Ro = N * h * w, N * ho * wo
@@ -249,22 +255,22 @@ class ResNet101Engine:
                 Rp = N * (h + 2) * (w + 2)
                 wp = w + 2
                 taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
-                g2 = self.buf(f"{tag}:g2p", (Rp, width), zero=True)
+                g2 = self.buf(f"{tag}:g2p{par}", (Rp, width), zero=True)
                 gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=REMAP_C2P, img_hw=(h, w))
                 # ---- conv2 (implicit 3x3 over the haloed grid)
                 with sc:
                     self._wgrad(g2, y1, width, width, Rp, s2, grads[prefix + name + "conv2.weight"], z_b_off1=taps)
-                g1 = self.buf(f"{tag}:g1", (R, width))
+                g1 = self.buf(f"{tag}:g1{par}", (R, width))
                 gemm(g2, w2s, g1, Rp, width, width, b_major=1, ntaps=9, a_off1=[-t for t in taps],
                      b_off0=[t * width for t in range(9)], mask=y1, remap=REMAP_P2C, img_hw=(h, w))
             else:
-                g2 = self.buf(f"{tag}:g2c", (Ro, width))
+                g2 = self.buf(f"{tag}:g2c{par}", (Ro, width))
                 gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2)
                 with sc:
                     self._wgrad(g2, r["col"], width, 9 * width, Ro, s2, grads[prefix + name + "conv2.weight"], taps=9)
-                dcol = self.buf(f"{tag}:dcol", (Ro, 9 * width))
+                dcol = self.buf(f"{tag}:dcol{par}", (Ro, 9 * width))
                 gemm(g2, w2s, dcol, Ro, 9 * width, width, b_major=1)
-                g1 = self.buf(f"{tag}:g1", (R, width))
+                g1 = self.buf(f"{tag}:g1{par}", (R, width))
                 K.col2im3x3s2_mask(dcol, y1, g1, N, h, w, width)
             # ---- conv1
             with sc:
@@ -275,16 +281,17 @@ class ResNet101Engine:
                 with sc:
                     self._wgrad(g_out, r["xs"], cout, cin, Ro, sdn, grads[prefix + name + "downsample.0.weight"])
                 if not last:
-                    dxs = self.buf(f"{tag}:dxs", (Ro, cin))
+                    dxs = self.buf(f"{tag}:dxs{par}", (Ro, cin))
                     gemm(g_out, wds, dxs, Ro, cin, cout, b_major=1)
                     resid = dxs
                     if r["stride"] == 2:
-                        resid = self.buf(f"{tag}:dxsu", (R, cin))
+                        resid = self.buf(f"{tag}:dxsu{par}", (R, cin))
                         K.upsample2_zero(dxs, resid, N, h, w, cin)
             if last:
                 break
-            gprev = self.buf(f"{tag}:gout{i % 2}", (R, cin))
+            gprev = self.buf(f"{tag}:gout{i % 3}", (R, cin))
             gemm(g1, w1s, gprev, R, cin, width, b_major=1, residual=resid, mask=x)
             g_out = gprev
+            pending.append(sc.mark())
         sc.join()
         return grads
