@@ -10,6 +10,8 @@ Data layout: NHWC bf16 "pixel rows" [N*H*W][C].  The input of every stride-1 3x3
 backward is the `mask` epilogue of the producing dgrad GEMM, so no elementwise pass ever touches HBM on its own.
 This module only sequences kernel launches; every FLOP runs in libtdb.so.
 """
+import os
+
 import torch
 
 from . import kernels as K
@@ -17,6 +19,9 @@ from .gemm import REMAP_C2P, REMAP_P2C, effective_splits, gemm, splitk_reduce
 
 STAGES = ((64, 3, 1), (128, 4, 2), (256, 23, 2), (512, 3, 2))  # width, blocks, stride of first block
 BN_EPS = 1e-5
+
+
+WGRAD_LAG = max(1, min(2, int(os.environ.get("TDB_WGRAD_LAG", "2"))))
 
 
 def conv_out(h, k, s, p):
@@ -237,7 +242,7 @@ class ResNet101Engine:
         sc = wgrad_scope(g_out.device)
         pending = []
         for i in range(len(blocks) - 1, -1, -1):
-            if len(pending) >= 2:
+            while len(pending) >= WGRAD_LAG:    # 2 = what the buffering allows; 1 = wait for the previous block (TDB_WGRAD_LAG)
                 sc.wait(pending.pop(0))
             par = i % 2
             r = blocks[i]
