@@ -21,7 +21,7 @@ STAGES = ((64, 3, 1), (128, 4, 2), (256, 23, 2), (512, 3, 2))  # width, blocks, 
 BN_EPS = 1e-5
 
 
-WGRAD_LAG = max(1, min(2, int(os.environ.get("TDB_WGRAD_LAG", "2"))))
+WGRAD_LAG = max(1, min(2, int(os.environ.get("TDB_WGRAD_LAG", "1"))))
 
 
 def conv_out(h, k, s, p):
@@ -237,12 +237,14 @@ class ResNet101Engine:
         N, tag = ctx["N"], ctx["tag"]
         blocks = ctx["blocks"]
         # Weight gradients run on a side stream, concurrent with the dgrad chain.  The scratch gradients are double buffered by
-        # block parity (the block-output gradient triple buffered), so the main stream only has to wait for the side work of the
-        # block TWO iterations back before it overwrites that block's scratch: the dgrad chain never stalls on the latest wgrad.
+        # block parity (the block-output gradient triple buffered), so the main stream could run up to TWO blocks ahead of the
+        # side stream (TDB_WGRAD_LAG=2).  Measured on B200 (cfg-2 step, same box): lag 1 (wait for the previous block's weight
+        # gradients before starting a block) 20.68 ms, lag 2 21.25 ms -- the extra run-ahead only adds contention between the
+        # dgrad chain and a longer queue of split-K wgrad CTAs -- so lag 1 is the default.
         sc = wgrad_scope(g_out.device)
         pending = []
         for i in range(len(blocks) - 1, -1, -1):
-            while len(pending) >= WGRAD_LAG:    # 2 = what the buffering allows; 1 = wait for the previous block (TDB_WGRAD_LAG)
+            while len(pending) >= WGRAD_LAG:
                 sc.wait(pending.pop(0))
             par = i % 2
             r = blocks[i]
