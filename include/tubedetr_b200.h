@@ -158,6 +158,13 @@ int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
  * S must be >= 43 (a 128-row tile may touch at most 4 frames).
  * ------------------------------------------------------------------------------------------------ */
 int64_t tdb_xattn_workspace_bytes(int F, int S);
+/* measurement hook: buf = device int64 [tiles][4] (NULL = off).  Subsequent tdb_xattn_fused_fwd launches store per 128-row tile
+ * the SM clock at kernel entry, first tcgen05.mma issue, completion of the last tcgen05.mma, CTA exit (tensor
+ * pipe utilisation of the fused kernel over its MMA phase = 4096 MMA cycles / (stamp[2] - stamp[1])). */
+int tdb_xattn_set_timing_buffer(void* buf);
+/* kernel variant of tdb_xattn_fused_fwd: 0 = one CTA per 128-row tile, 1 = CTA pair (cluster of 2, tcgen05 cta_group::2) per
+ * 256 rows, each CTA staging half of the weight rows (default: env TDB_XATTN_PAIR, else 0).  Results are bit-identical. */
+int tdb_xattn_set_pair(int on);
 /* keep [F][8][S] (1 = kept) + keep_scale = 1/(1-p): attention dropout (train mode); p stays pre-dropout, pbar averages
  * the dropped probabilities.  keep == NULL disables it. */
 int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, const void* wkv, const float* bv,

@@ -396,3 +396,36 @@ def test_ffn_hidden_dropout_fused_backward():
         _close(got, ref, 3e-2)
         a = (got.float() * ref).sum() / (ref * ref).sum()
         assert abs(a.item() - 1) < 1e-2, a.item()
+
+
+@pytest.mark.parametrize("F,S", [(100, 141), (8, 59), (3, 43), (37, 200), (1, 141)])
+def test_xattn_pair_variant_is_bit_identical(F, S):
+    """CTA-pair (cta_group::2) variant of the fused cross-attention kernel == the 1-CTA kernel, bit for bit (same k-block
+    order into the same fp32 accumulators); odd and single tile counts exercise the idle-peer path"""
+    from tubedetr_b200 import kernels as K
+    from tubedetr_b200._lib import lib
+    d, H = 256, 8
+    scale = 1 / math.sqrt(32)
+    q = _r((F, d), 40)
+    mem, pos = _r((F * S, d), 41), _r((F * S, d), 42) * 0.5
+    memb, mempb = mem, (mem.float() + pos.float()).bfloat16()
+    W = (_r((3 * d, d), 43, torch.float32) / 16).bfloat16()
+    b = _r((3 * d,), 44, torch.float32) * 0.1
+    kpm = torch.zeros(F, S, dtype=torch.uint8, device="cuda")
+    kpm[:, S - S // 4:] = 1
+    kpm[0] = 0
+    outs = []
+    try:
+        for pair in (0, 1):
+            lib().tdb_xattn_set_pair(pair)
+            o = torch.zeros(F, d, dtype=torch.bfloat16, device="cuda")
+            p = torch.zeros(F, H, 1, S, device="cuda")
+            pbar = torch.zeros(F, 1, S, device="cuda")
+            K.xattn_fused_fwd(q, mempb, memb, W[d:], b[2 * d:], kpm, o, p, pbar, F, S, scale)
+            torch.cuda.synchronize()
+            outs.append((o, p, pbar))
+    finally:
+        lib().tdb_xattn_set_pair(0)
+    assert torch.isfinite(outs[1][0].float()).all()
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)

@@ -13,6 +13,8 @@
 // The K bias bk only shifts all scores of a frame by q.bk, which the softmax cancels, so it is not applied; bv is added
 // after normalisation (sum_j p = 1).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = consumers (one TMEM lane = one memory token).
+#include <stdlib.h>
+
 #include "../../include/tubedetr_b200.h"
 #include "tdb_common.cuh"
 
@@ -33,7 +35,7 @@ constexpr int XTHREADS = 256;
 
 struct XattnSmem {
   // after the stage ring
-  uint64_t full[XSTAGES], empty[XSTAGES], kfull, vfull;
+  uint64_t full[8], empty[8], kfull, vfull;      // 8 = ring capacity of either kernel variant
   uint32_t tmem_slot, pad;
   float qs[XMAXF][XD];             // scale * q of the frames in this tile
   float owarp[4][XMAXF][XD];       // per-consumer-warp partial contexts
@@ -41,6 +43,10 @@ struct XattnSmem {
   float wsum[4][XMAXF][XH];
 };
 constexpr int XSMEM_BYTES = XSTAGES * XSTAGE_BYTES + 1024 + (int)sizeof(XattnSmem);
+// pair variant (cta_group::2): per k-block a CTA stages its own 128 A rows (16 KB) and HALF of the weight rows (16 KB)
+constexpr int X2STAGES = 6;
+constexpr int X2STAGE_BYTES = XBM * 64 * 2 + (XD / 2) * 64 * 2;
+constexpr int X2SMEM_BYTES = X2STAGES * X2STAGE_BYTES + 1024 + (int)sizeof(XattnSmem);
 
 struct XattnParams {
   const bf16* q;        // [F][256] projected queries (bias included), unscaled
@@ -53,92 +59,17 @@ struct XattnParams {
   float* part_o;        // [tiles][XMAXF][256]
   int R, S, F;
   float scale;
+  long long* timing;    // optional [tiles][4] SM clock stamps: kernel entry, first MMA issue, last MMA complete, CTA exit
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __launch_bounds__(XTHREADS, 1)
-xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ XattnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment as an OFFSET on the __shared__ pointer: an integer round trip would turn every access below into a
-  // generic LD/ST instead of LDS/STS
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  XattnSmem& sh = *reinterpret_cast<XattnSmem*>(smem + XSTAGES * XSTAGE_BYTES);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int row0 = tile * XBM;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    tma_prefetch_desc(&tmW);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < XSTAGES; ++s) {
-      mbar_init(&sh.full[s], 1);
-      mbar_init(&sh.empty[s], 1);
-    }
-    mbar_init(&sh.kfull, 1);
-    mbar_init(&sh.vfull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(&sh.tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = sh.tmem_slot;
-  pdl_wait();
-  pdl_trigger();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < 8; ++it) {        // 4 k-blocks for K, then 4 for V
-        const int kk = it & 3;
-        mbar_wait(&sh.empty[stage], phase ^ 1, 11);
-        mbar_expect_tx(&sh.full[stage], XSTAGE_BYTES);
-        uint8_t* sA = smem + stage * XSTAGE_BYTES;
-        uint8_t* sB = sA + XBM * 64 * 2;
-        tma_load_2d(sA, it < 4 ? &tmK : &tmV, &sh.full[stage], kk * 64, row0);
-        tma_load_2d(sB, &tmW, &sh.full[stage], kk * 64, it < 4 ? 0 : XD);   // Wk rows [0,256), Wv rows [256,512)
-        if (++stage == XSTAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(XBM, XD, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < 8; ++it) {
-        mbar_wait(&sh.full[stage], phase, 12);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * XSTAGE_BYTES);
-        const uint32_t b_base = a_base + XBM * 64 * 2;
-        const uint32_t d_tmem = tmem_base + (it < 4 ? 0 : XD);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          umma_bf16(d_tmem, umma_smem_desc(a_base + s * 32, 16, 1024), umma_smem_desc(b_base + s * 32, 16, 1024), idesc,
-                    ((it & 3) > 0 || s > 0) ? 1u : 0u);
-        umma_commit(&sh.empty[stage]);
-        if (it == 3) umma_commit(&sh.kfull);
-        if (it == 7) umma_commit(&sh.vfull);
-        if (++stage == XSTAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp >= 4) {
+// consumers (warps 4-7 of a CTA): thread = memory token = TMEM lane of this CTA's 128-row tile; K accumulator in TMEM columns
+// [0,256), V in [256,512); shared by the 1-CTA and the pair kernel
+__device__ __forceinline__ void xattn_consume(XattnSmem& sh, const XattnParams& p, const int tile, const int row0,
+                                              const uint32_t tmem_base, const int warp, const int lane) {
     // ------------------------------------------------------------------ consumers: thread = memory token (TMEM lane)
     const int wq = warp & 3;
     const int tid = threadIdx.x - 128;                    // 0..127
@@ -263,13 +194,216 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       p.part_m[((long long)tile * XMAXF + ff) * XH + h] = m;
       p.part_l[((long long)tile * XMAXF + ff) * XH + h] = l;
     }
+}
+
+__global__ void __launch_bounds__(XTHREADS, 1)
+xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ XattnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment as an OFFSET on the __shared__ pointer: an integer round trip would turn every access below into a
+  // generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  XattnSmem& sh = *reinterpret_cast<XattnSmem*>(smem + XSTAGES * XSTAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int row0 = tile * XBM;
+  if (p.timing && threadIdx.x == 32) p.timing[tile * 4 + 0] = clock64();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < XSTAGES; ++s) {
+      mbar_init(&sh.full[s], 1);
+      mbar_init(&sh.empty[s], 1);
+    }
+    mbar_init(&sh.kfull, 1);
+    mbar_init(&sh.vfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&sh.tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < 8; ++it) {        // 4 k-blocks for K, then 4 for V
+        const int kk = it & 3;
+        mbar_wait(&sh.empty[stage], phase ^ 1, 11);
+        mbar_expect_tx(&sh.full[stage], XSTAGE_BYTES);
+        uint8_t* sA = smem + stage * XSTAGE_BYTES;
+        uint8_t* sB = sA + XBM * 64 * 2;
+        tma_load_2d(sA, it < 4 ? &tmK : &tmV, &sh.full[stage], kk * 64, row0);
+        tma_load_2d(sB, &tmW, &sh.full[stage], kk * 64, it < 4 ? 0 : XD);   // Wk rows [0,256), Wv rows [256,512)
+        if (++stage == XSTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(XBM, XD, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < 8; ++it) {
+        mbar_wait(&sh.full[stage], phase, 12);
+        tc_fence_after();
+        if (p.timing && it == 0) p.timing[tile * 4 + 1] = clock64();
+        const uint32_t a_base = smem_u32(smem + stage * XSTAGE_BYTES);
+        const uint32_t b_base = a_base + XBM * 64 * 2;
+        const uint32_t d_tmem = tmem_base + (it < 4 ? 0 : XD);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma_bf16(d_tmem, umma_smem_desc(a_base + s * 32, 16, 1024), umma_smem_desc(b_base + s * 32, 16, 1024), idesc,
+                    ((it & 3) > 0 || s > 0) ? 1u : 0u);
+        umma_commit(&sh.empty[stage]);
+        if (it == 3) umma_commit(&sh.kfull);
+        if (it == 7) umma_commit(&sh.vfull);
+        if (++stage == XSTAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (p.timing) {             // MMA phase = first issue .. completion of the last tcgen05.mma (observed on the V barrier)
+        mbar_wait(&sh.vfull, 0, 15);
+        p.timing[tile * 4 + 2] = clock64();
+      }
+    }
+  } else if (warp >= 4) {
+    xattn_consume(sh, p, tile, row0, tmem_base, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.timing && threadIdx.x == 32) p.timing[tile * 4 + 3] = clock64();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Pair variant: a CTA pair (cluster of 2, tcgen05 cta_group::2) projects 256 memory rows per k-step with ONE MMA (M = 256,
+// N = 256).  Each CTA stages its own 128 A rows and only HALF of the weight rows (both tensor cores read both halves), so a
+// CTA pulls 8 x 32 KB = 256 KB through the L2 -> SM path instead of 8 x 48 KB = 384 KB for the same 4096 tensor-pipe
+// cycles: the 1-CTA kernel's MMA phase is bound by exactly that feed (tools/xattn_phase.py).  Accumulators land in each
+// CTA's own TMEM (rows of rank r in CTA r), so the consumer code is unchanged.  Barrier protocol = tdb_gemm2_kernel:
+// every TMA load signals the LEADER's full barrier, the leader's commits are multicast to both CTAs.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(XTHREADS, 1)
+xattn_fused2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ XattnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  XattnSmem& sh = *reinterpret_cast<XattnSmem*>(smem + X2STAGES * X2STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int tile = blockIdx.x;                 // 128-row tile of this CTA; the pair owns tiles (2i, 2i+1)
+  const int row0 = tile * XBM;
+  const int ntiles = (p.R + XBM - 1) / XBM;
+  if (p.timing && threadIdx.x == 32 && tile < ntiles) p.timing[tile * 4 + 0] = clock64();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < X2STAGES; ++s) {
+      mbar_init(&sh.full[s], 1);
+      mbar_init(&sh.empty[s], 1);
+    }
+    mbar_init(&sh.kfull, 1);
+    mbar_init(&sh.vfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(&sh.tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {                          // both CTAs: own A rows + own half of the weight rows, leader's barrier
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < 8; ++it) {        // 4 k-blocks for K, then 4 for V
+        const int kk = it & 3;
+        mbar_wait(&sh.empty[stage], phase ^ 1, 31);
+        if (rank == 0) mbar_expect_tx(&sh.full[stage], 2 * X2STAGE_BYTES);
+        uint8_t* sA = smem + stage * X2STAGE_BYTES;
+        uint8_t* sB = sA + XBM * 64 * 2;
+        tma_load_2d_2sm(sA, it < 4 ? &tmK : &tmV, &sh.full[stage], kk * 64, row0);
+        tma_load_2d_2sm(sB, &tmW, &sh.full[stage], kk * 64, (it < 4 ? 0 : XD) + (int)rank * (XD / 2));
+        if (++stage == X2STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {             // leader only
+      const uint32_t idesc = umma_idesc_bf16(2 * XBM, XD, 0, 0);
+      const uint64_t hi = umma_smem_desc(0, 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < 8; ++it) {
+        mbar_wait(&sh.full[stage], phase, 32);
+        tc_fence_after();
+        if (p.timing && it == 0) {
+          const long long t = clock64();
+          p.timing[tile * 4 + 1] = t;
+          if (tile + 1 < ntiles) p.timing[(tile + 1) * 4 + 1] = t;
+        }
+        const uint32_t a_base = smem_u32(smem + stage * X2STAGE_BYTES);
+        const uint64_t ad = umma_desc_at(hi, a_base);
+        const uint64_t bd = umma_desc_at(hi, a_base + XBM * 64 * 2);
+        const uint32_t d_tmem = tmem_base + (it < 4 ? 0 : XD);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) umma2_bf16(d_tmem, ad + s * 2u, bd + s * 2u, idesc, ((it & 3) > 0 || s > 0) ? 1u : 0u);
+        umma2_commit_mc(&sh.empty[stage]);
+        if (it == 3) umma2_commit_mc(&sh.kfull);
+        if (it == 7) umma2_commit_mc(&sh.vfull);
+        if (++stage == X2STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (p.timing) {
+        mbar_wait(&sh.vfull, 0, 35);
+        const long long t = clock64();
+        p.timing[tile * 4 + 2] = t;
+        if (tile + 1 < ntiles) p.timing[(tile + 1) * 4 + 2] = t;
+      }
+    }
+  } else if (warp >= 4) {
+    if (tile < ntiles) xattn_consume(sh, p, tile, row0, tmem_base, warp, lane);     // an odd tile count leaves the last peer idle
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (p.timing && threadIdx.x == 32 && tile < ntiles) p.timing[tile * 4 + 3] = clock64();
+  cluster_sync_all();       // both CTAs are done with each other's shared memory, barriers and TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -505,6 +639,20 @@ extern "C" int tdb_xattn_bwd(const void* q, const void* k, const void* v, const 
   return TDB_OK;
 }
 
+// measurement hook (tools/xattn_phase.py): when set, every fused forward launch writes 4 SM clock stamps per tile
+static long long* g_xattn_timing = nullptr;
+extern "C" int tdb_xattn_set_timing_buffer(void* buf) {
+  g_xattn_timing = (long long*)buf;
+  return TDB_OK;
+}
+
+// kernel variant: 0 = one CTA per 128-row tile, 1 = CTA pair per 256 rows (cta_group::2); default from env TDB_XATTN_PAIR
+static int g_xattn_pair = -1;
+extern "C" int tdb_xattn_set_pair(int on) {
+  g_xattn_pair = on ? 1 : 0;
+  return TDB_OK;
+}
+
 extern "C" int64_t tdb_xattn_workspace_bytes(int F, int S) {
   int64_t tiles = ((int64_t)F * S + XBM - 1) / XBM;
   return tiles * XMAXF * (XH * 2 + XD) * (int64_t)sizeof(float);
@@ -543,8 +691,25 @@ extern "C" int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void*
   prm.S = S;
   prm.F = F;
   prm.scale = scale;
+  prm.timing = g_xattn_timing;
   cudaStream_t st = (cudaStream_t)stream_;
-  TDB_CHECK_CUDA(tdb_launch(xattn_fused_kernel, dim3(tiles), dim3(XTHREADS), XSMEM_BYTES, st, tmK, tmV, tmW, prm));
+  if (g_xattn_pair < 0) {
+    const char* e = getenv("TDB_XATTN_PAIR");
+    g_xattn_pair = e ? atoi(e) : 0;
+  }
+  if (g_xattn_pair) {
+    static bool attr2 = false;
+    if (!attr2) {
+      TDB_CHECK_CUDA(cudaFuncSetAttribute(xattn_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X2SMEM_BYTES));
+      attr2 = true;
+    }
+    CUtensorMap tmWh;      // weight box = half of the 256 rows of Wk (or Wv)
+    if ((rc = tdb_make_tmap_bf16(&tmWh, wkv, 2 * XD, XD, XD, XD / 2))) return rc;
+    const int ctas = ((tiles + 1) / 2) * 2;
+    TDB_CHECK_CUDA(tdb_launch(xattn_fused2_kernel, dim3(ctas), dim3(XTHREADS), X2SMEM_BYTES, st, tmK, tmV, tmWh, prm));
+  } else {
+    TDB_CHECK_CUDA(tdb_launch(xattn_fused_kernel, dim3(tiles), dim3(XTHREADS), XSMEM_BYTES, st, tmK, tmV, tmW, prm));
+  }
   TDB_CHECK_CUDA(cudaGetLastError());
   TDB_CHECK_CUDA(tdb_launch(xattn_merge_kernel, dim3(F), dim3(256), 0, st, prm.part_m, prm.part_l, prm.part_o, bv, p, pbar, (bf16*)o, keep, keep_scale, S, F));
   TDB_CHECK_CUDA(cudaGetLastError());
