@@ -1,0 +1,70 @@
+"""Measurement probes shared by bench.py and tools/ (no product logic here)."""
+import ctypes as C
+import math
+
+import torch
+
+from . import kernels as K
+from ._lib import lib
+
+XATTN_MMA_CYCLES = 2 * 16 * 128      # K and V projection of a 128-row tile: 16 tcgen05.mma (M128 N256 K16) each, 128 cycles per MMA
+
+
+def xattn_phase(F=100, S=141, pair=0, reps=24):
+    """Decoder cross-attention kernel (fused KV projection + attention, reference models/transformer.py:724-745) at F frames x S
+    memory tokens.  Returns (i) the tensor-pipe utilisation over the kernel's MMA phase from in-kernel SM
+    clock stamps: 4096 MMA cycles / (last MMA complete - first MMA issue), median over tiles, and (ii) the streaming view:
+    algorithmic bytes (memory + pos read once, weights) / device time of fused + merge kernels in a CUDA-graph replay over
+    rotating HBM-resident inputs."""
+    d = 256
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(F, d, generator=g).bfloat16().to(dev)
+    nb = 8                       # rotate memory buffers so the timed launches read HBM, not L2
+    mems = [(torch.randn(F * S, d, generator=g).bfloat16().to(dev), torch.randn(F * S, d, generator=g).bfloat16().to(dev))
+            for _ in range(nb)]
+    W = (torch.randn(2 * d, d, generator=g) / 16).bfloat16().to(dev)
+    bv = torch.zeros(d, device=dev)
+    kpm = torch.zeros(F, S, dtype=torch.uint8, device=dev)
+    o = torch.empty(F, d, dtype=torch.bfloat16, device=dev)
+    p = torch.empty(F, 8, 1, S, device=dev)
+    pbar = torch.empty(F, 1, S, device=dev)
+    tiles = (F * S + 127) // 128
+    stamps = torch.zeros(tiles, 4, dtype=torch.int64, device=dev)
+
+    def run(i):
+        K.xattn_fused_fwd(q, mems[i % nb][0], mems[i % nb][1], W, bv, kpm, o, p, pbar, F, S, 1 / math.sqrt(32))
+    lib().tdb_xattn_set_pair(int(pair))
+    try:
+        for i in range(4):
+            run(i)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()          # replay a graph: the eager ctypes launch path (~10 us per call) would hide the kernels
+        with torch.cuda.graph(gr):
+            for i in range(reps):
+                run(i)
+        gr.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / (5 * reps) * 1e3
+        lib().tdb_xattn_set_timing_buffer(C.c_void_p(stamps.data_ptr()))
+        run(5)
+        torch.cuda.synchronize()
+    finally:
+        lib().tdb_xattn_set_timing_buffer(None)
+        lib().tdb_xattn_set_pair(0)
+    st = stamps.cpu().double()
+    lead = st[::2] if pair else st           # the pair kernel stamps both tiles of a pair with the leader's clock
+    mma = lead[:, 2] - lead[:, 1]
+    life = lead[:, 3] - lead[:, 0]
+    alg = 2 * F * S * d * 2 + 2 * d * d * 2
+    return {"kernel": "xattn_fused2_kernel (CTA pair, cta_group::2)" if pair else "xattn_fused_kernel", "frames": F, "tokens": S, "tiles": tiles,
+            "mma_phase_cycles_median": float(mma.median()), "mma_phase_cycles_min": float(mma.min()), "mma_phase_cycles_max": float(mma.max()),
+            "tensor_pipe_pct_over_mma_phase": 100.0 * XATTN_MMA_CYCLES / float(mma.median()),
+            "cta_lifetime_cycles_median": float(life.median()),
+            "tensor_pipe_pct_of_cta_lifetime": 100.0 * XATTN_MMA_CYCLES / float(life.median()),
+            "us_per_layer_fused_plus_merge": us, "algorithmic_bytes": alg, "algorithmic_gbs": alg / us / 1e3}
