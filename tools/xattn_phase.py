@@ -18,3 +18,7 @@ for pair, F, S in ((0, 100, 141), (1, 100, 141), (0, 400, 141), (1, 400, 141), (
     print(f"   MMA phase (first issue -> last MMA complete): median {r['mma_phase_cycles_median']:.0f} cycles, min {r['mma_phase_cycles_min']:.0f}, "
           f"max {r['mma_phase_cycles_max']:.0f}  => tensor pipe over the MMA phase = {r['tensor_pipe_pct_over_mma_phase']:.1f} % (ideal {XATTN_MMA_CYCLES} cycles)")
     print(f"   CTA lifetime median {r['cta_lifetime_cycles_median']:.0f} cycles;  MMA share of the lifetime {r['tensor_pipe_pct_of_cta_lifetime']:.1f} %")
+    if r["globaltimer"]:
+        g = r["globaltimer"]
+        print(f"   %globaltimer: CTA entry spread across the grid {g['cta_entry_spread_us']:.2f} us, first entry -> last exit {g['first_entry_to_last_exit_us']:.2f} us, "
+              f"CTA lifetime median {g['cta_lifetime_us_median']:.2f} us")

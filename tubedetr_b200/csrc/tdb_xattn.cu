@@ -59,9 +59,15 @@ struct XattnParams {
   float* part_o;        // [tiles][XMAXF][256]
   int R, S, F;
   float scale;
-  long long* timing;    // optional [tiles][4] SM clock stamps: kernel entry, first MMA issue, last MMA complete, CTA exit
+  long long* timing;    // optional [tiles][4] SM clock stamps: kernel entry, first MMA issue, last MMA complete, CTA exit;
+                        // followed by [tiles][2] %globaltimer (ns) at CTA entry / exit (CTA launch skew across the grid)
 };
 
+__device__ __forceinline__ long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return (long long)t;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -207,7 +213,10 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int row0 = tile * XBM;
-  if (p.timing && threadIdx.x == 32) p.timing[tile * 4 + 0] = clock64();
+  if (p.timing && threadIdx.x == 32) {
+    p.timing[tile * 4 + 0] = clock64();
+    p.timing[(long long)gridDim.x * 4 + tile * 2 + 0] = globaltimer_ns();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmK);
@@ -287,7 +296,10 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (p.timing && threadIdx.x == 32) p.timing[tile * 4 + 3] = clock64();
+  if (p.timing && threadIdx.x == 32) {
+    p.timing[tile * 4 + 3] = clock64();
+    p.timing[(long long)gridDim.x * 4 + tile * 2 + 1] = globaltimer_ns();
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -30,7 +30,7 @@ def xattn_phase(F=100, S=141, pair=0, reps=24):
     p = torch.empty(F, 8, 1, S, device=dev)
     pbar = torch.empty(F, 1, S, device=dev)
     tiles = (F * S + 127) // 128
-    stamps = torch.zeros(tiles, 4, dtype=torch.int64, device=dev)
+    stamps = torch.zeros(tiles * 6 + 8, dtype=torch.int64, device=dev)     # [tiles][4] SM clocks + [tiles][2] globaltimer ns
 
     def run(i):
         K.xattn_fused_fwd(q, mems[i % nb][0], mems[i % nb][1], W, bv, kpm, o, p, pbar, F, S, 1 / math.sqrt(32))
@@ -57,7 +57,14 @@ def xattn_phase(F=100, S=141, pair=0, reps=24):
     finally:
         lib().tdb_xattn_set_timing_buffer(None)
         lib().tdb_xattn_set_pair(0)
-    st = stamps.cpu().double()
+    raw = stamps.cpu()
+    st = raw[:tiles * 4].view(tiles, 4).double()
+    skew = None
+    if not pair:                             # (the pair kernel does not write the global timer stamps)
+        gt = raw[tiles * 4:tiles * 6].view(tiles, 2).double()
+        skew = {"cta_entry_spread_us": float(gt[:, 0].max() - gt[:, 0].min()) / 1e3,
+                "first_entry_to_last_exit_us": float(gt[:, 1].max() - gt[:, 0].min()) / 1e3,
+                "cta_lifetime_us_median": float((gt[:, 1] - gt[:, 0]).median()) / 1e3}
     lead = st[::2] if pair else st           # the pair kernel stamps both tiles of a pair with the leader's clock
     mma = lead[:, 2] - lead[:, 1]
     life = lead[:, 3] - lead[:, 0]
@@ -67,4 +74,4 @@ def xattn_phase(F=100, S=141, pair=0, reps=24):
             "tensor_pipe_pct_over_mma_phase": 100.0 * XATTN_MMA_CYCLES / float(mma.median()),
             "cta_lifetime_cycles_median": float(life.median()),
             "tensor_pipe_pct_of_cta_lifetime": 100.0 * XATTN_MMA_CYCLES / float(life.median()),
-            "us_per_layer_fused_plus_merge": us, "algorithmic_bytes": alg, "algorithmic_gbs": alg / us / 1e3}
+            "us_per_layer_fused_plus_merge": us, "globaltimer": skew, "algorithmic_bytes": alg, "algorithmic_gbs": alg / us / 1e3}
