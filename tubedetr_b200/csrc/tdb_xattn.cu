@@ -213,10 +213,7 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int row0 = tile * XBM;
-  if (p.timing && threadIdx.x == 32) {
-    p.timing[tile * 4 + 0] = clock64();
-    p.timing[(long long)gridDim.x * 4 + tile * 2 + 0] = globaltimer_ns();
-  }
+  if (p.timing && threadIdx.x == 32) p.timing[tile * 4 + 0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmK);
@@ -242,6 +239,9 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const uint32_t tmem_base = sh.tmem_slot;
   pdl_wait();
   pdl_trigger();
+  // %globaltimer reads take microseconds: a lane of the idle warp 3 does them, after the prologue barrier, so that they sit
+  // neither in the MMA thread's path nor in front of a CTA-wide barrier
+  if (p.timing && threadIdx.x == 96) p.timing[(long long)gridDim.x * 4 + tile * 2 + 0] = globaltimer_ns();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -296,10 +296,8 @@ xattn_fused_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (p.timing && threadIdx.x == 32) {
-    p.timing[tile * 4 + 3] = clock64();
-    p.timing[(long long)gridDim.x * 4 + tile * 2 + 1] = globaltimer_ns();
-  }
+  if (p.timing && threadIdx.x == 32) p.timing[tile * 4 + 3] = clock64();
+  if (p.timing && threadIdx.x == 96) p.timing[(long long)gridDim.x * 4 + tile * 2 + 1] = globaltimer_ns();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
