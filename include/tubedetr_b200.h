@@ -135,8 +135,8 @@ int tdb_colsum_bf16(const void* x, int64_t ld, int rows, int N, float* partial, 
  * p [B][H][Lq][Lk] probabilities (kept for backward); pbar [B][Lq][Lk] = mean over heads (guided-attention loss) or NULL.
  * Backward takes dO and optionally dPbar and returns dq/dk/dv in the layout of q/k/v.
  * Attention dropout (train mode, reference nn.MultiheadAttention(dropout=0.1)): keep [B][H][Lq][Lk] (1 = kept) and
- * keep_scale = 1/(1-p); p then holds the pre-dropout probabilities, pdrop the dropped ones (which pbar averages).
- * keep == NULL disables it.
+ * keep_scale = 1/(1-p); p then holds the pre-dropout probabilities, pdrop the dropped ones (which pbar averages; pdrop may
+ * be NULL when pbar is NULL: the encoder never reads its attention weights).  keep == NULL disables it.
  */
 int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm,
                 void* o, int64_t ldo, float* p, float* pbar, const uint8_t* keep, float* pdrop, float keep_scale, int B, int H,

@@ -92,3 +92,18 @@ def test_model_without_cuda_fails_loudly(built):
     s = NestedTensor(torch.zeros(2, 3, 64, 64), torch.zeros(2, 64, 64, dtype=torch.bool))
     with pytest.raises(RuntimeError):
         built[0](s, [4], ["a caption"], encode_and_save=True, samples_fast=s)
+
+
+def test_dedup_index_tensors_reconstruct_the_fast_order(built):
+    """host logic of the opt-in slow_frames_alias_fast path: joint batch = [slow frames | remaining fast frames]; `order` must
+    map every fast frame (b, t) to its row block, slow frames being the fast frames [::k] of every video"""
+    model = built[0]
+    for B, T, k in ((1, 100, 4), (2, 8, 2), (3, 10, 4), (1, 7, 5)):
+        n_clips = -(-T // k)
+        rest_idx, order = model._dedup_index_tensors(B, T, k, "cpu")
+        fast = torch.arange(B * T)                                   # frame ids in fast order
+        slow = torch.cat([fast[b * T:(b + 1) * T][::k] for b in range(B)])
+        assert slow.numel() == B * n_clips
+        joint = torch.cat([slow, fast[rest_idx]])                     # what the backbone sees
+        assert joint.numel() == B * T and torch.equal(joint.sort().values, fast)
+        assert torch.equal(joint[order], fast)                        # gather restores the fast order

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams 
     const long long prow_off = (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
     float* pg = a.p + prow_off;
     const uint8_t* kp = a.keep ? a.keep + prow_off : nullptr;
-    float* pd = a.keep ? a.pdrop + prow_off : nullptr;
+    float* pd = (a.keep && a.pdrop) ? a.pdrop + prow_off : nullptr;   // only needed when the head-mean weights are requested
 #pragma unroll
     for (int c = 0; c < kMaxChunks; ++c) {
       const int j = c * 32 + lane;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams 
         pg[j] = e * inv;
         if (kp) {                   // P <- P * keep / (1 - p); the context uses the dropped probabilities
           e = kp[j] ? e * a.keep_scale : 0.f;
-          pd[j] = e * inv;
+          if (pd) pd[j] = e * inv;
         }
         pw[j] = e;
       }
@@ -342,7 +342,7 @@ static int attn_init() {
 extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            const uint8_t* kpm, void* o, int64_t ldo, float* p, float* pbar, const uint8_t* keep, float* pdrop,
                            float keep_scale, int B, int H, int Lq, int Lk, float scale, void* stream_) {
-  TDB_REQUIRE(!keep || pdrop, "tdb_mha_fwd: dropout needs the pdrop output");
+  TDB_REQUIRE(!(keep && pbar) || pdrop, "tdb_mha_fwd: head-mean weights under dropout need the pdrop output");
   TDB_REQUIRE(q && k && v && o && p && B > 0 && H > 0 && Lq > 0 && Lk > 0, "tdb_mha_fwd: bad args");
   size_t smem = attn_smem_bytes(Lk, kAttnThreads);
   TDB_REQUIRE(Lk <= 32 * tdb::kMaxChunks, "tdb_mha_fwd: Lk=%d > %d keys", Lk, 32 * tdb::kMaxChunks);

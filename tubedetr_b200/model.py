@@ -280,7 +280,7 @@ class Transformer(nn.Module):
     def _enc_layer(self, l, x32, xb, xpb, pos, kpm, n, S, need_pos):
         a, dp = l.self_attn, self._drop()
         qk, v = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((0, 512), (512, 768)), xpb, xb)
-        o, _ = ops.mha(qk, None, v, kpm, n, NHEAD, S, S, 32 ** -0.5, packed=True, drop_p=dp)
+        o, _ = ops.mha(qk, None, v, kpm, n, NHEAD, S, S, 32 ** -0.5, packed=True, drop_p=dp, need_weights=False)
         att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
         x32, xb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, drop_p=dp)      # residual dropouts ride in the LN kernels
         f = self._ffn(l, xb, dp)

@@ -270,21 +270,26 @@ class MHAFn(torch.autograd.Function):
     attention-probability dropout (mask drawn with torch.rand, applied inside the kernel; pbar averages the dropped P)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, kpm, B, H, Lq, Lk, scale, packed, drop_p):
+    def forward(ctx, q, k, v, kpm, B, H, Lq, Lk, scale, packed, drop_p, need_weights=True):
         if packed:
             qv, kv = q[:, :256], q[:, 256:]
         else:
             qv, kv = q, k
         o = torch.empty(B * Lq, H * 32, dtype=torch.bfloat16, device=q.device)
         p = torch.empty(B, H, Lq, Lk, dtype=torch.float32, device=q.device)
-        pbar = torch.empty(B, Lq, Lk, dtype=torch.float32, device=q.device)
+        # the encoder never reads its attention weights (reference transformer.py:638-640 discards them): no head-mean launch and,
+        # under dropout, no second probability tensor
+        pbar = torch.empty(B, Lq, Lk, dtype=torch.float32, device=q.device) if need_weights else None
         keep = pdrop = None
         if drop_p > 0:
             keep = dropout_keep((B, H, Lq, Lk), drop_p, q.device)
-            pdrop = torch.empty_like(p)
+            pdrop = torch.empty_like(p) if need_weights else None
         K.mha_fwd(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pdrop, keep_scale=1.0 / (1.0 - drop_p))
         ctx.cfg = (B, H, Lq, Lk, scale, packed, drop_p)
         ctx.save_for_backward(q, k if not packed else None, v, p, keep)
+        if pbar is None:
+            pbar = p.new_empty(0)
+            ctx.mark_non_differentiable(pbar)
         return o, pbar
 
     @staticmethod
@@ -294,6 +299,8 @@ class MHAFn(torch.autograd.Function):
         if do is None:
             do = torch.zeros(B * Lq, H * 32, dtype=torch.bfloat16, device=q.device)
         do = _as_bf16(do).contiguous()
+        if dpbar is not None and dpbar.numel() == 0:      # need_weights=False: placeholder output
+            dpbar = None
         if dpbar is not None:
             dpbar = dpbar.contiguous().float()
         ds = torch.empty_like(p)
@@ -302,14 +309,14 @@ class MHAFn(torch.autograd.Function):
         if packed:
             dqk = torch.empty_like(q)
             K.mha_bwd(q[:, :256], q[:, 256:], v, do, p, dpbar, ds, dqk[:, :256], dqk[:, 256:], dv, B, H, Lq, Lk, scale, **kw)
-            return (dqk, None, dv) + (None,) * 8
+            return (dqk, None, dv) + (None,) * 9
         dq, dk = torch.empty_like(q), torch.empty_like(k)
         K.mha_bwd(q, k, v, do, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, **kw)
-        return (dq, dk, dv) + (None,) * 8
+        return (dq, dk, dv) + (None,) * 9
 
 
-def mha(q, k, v, kpm, B, H, Lq, Lk, scale, packed=False, drop_p=0.0):
-    return MHAFn.apply(q, k, v, kpm, B, H, Lq, Lk, scale, packed, float(drop_p))
+def mha(q, k, v, kpm, B, H, Lq, Lk, scale, packed=False, drop_p=0.0, need_weights=True):
+    return MHAFn.apply(q, k, v, kpm, B, H, Lq, Lk, scale, packed, float(drop_p), bool(need_weights))
 
 
 class XAttnFusedFn(torch.autograd.Function):
