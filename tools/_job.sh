@@ -1,3 +1,1 @@
-tools/run_gpu_tests.sh tests/test_kernels_gpu.py tests/test_model_gpu.py tests/test_fullsize_gpu.py
-python bench.py --steps 10 --warmup 3 --skip-cpu 2>gpurun_out/bench_err.log | tail -1 > gpurun_out/bench_r01h.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_r01h.json')); print('ms', d['ms_per_step'], 'value', d['value'], 'launches', d['gpu_launches']); print('dedup', d['dedup_slow_frames']['ms_per_step']); print('e2e', d['e2e']); print('xattn', d['decoder_attn'].get('tensor_pipe_pct_over_mma_phase'), d['decoder_attn'].get('globaltimer'), d['decoder_attn'].get('cta_lifetime_cycles_median'))"; grep -v "Warn\|warn" gpurun_out/bench_err.log | tail -3
+timeout 500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -4

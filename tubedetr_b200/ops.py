@@ -1,6 +1,8 @@
 """torch.autograd glue around the C-ABI kernels.  Each Function only marshals buffers: forward and backward math
 runs in libtdb.so (tcgen05 GEMM, attention, LayerNorm kernels).  Activations that feed a GEMM are bf16, the residual
 stream and normalisation statistics are fp32, parameters/gradients stay fp32 (master weights)."""
+import weakref
+
 import torch
 
 from . import kernels as K
@@ -65,23 +67,33 @@ class wgrad_scope:
             self.main.wait_event(ev)
 
 
+def _root(w):
+    return w._base if w._base is not None else w
+
+
 def bf16_weight(w):
-    """bf16 copy of an fp32 parameter, refreshed when the parameter changes (optimizer steps bump _version)."""
+    """bf16 copy of an fp32 parameter, refreshed when the parameter changes (optimizer steps bump _version).
+    The entry holds a weak reference to the parameter (its base tensor for views): an address can be recycled by the caching
+    allocator for a different tensor of the same shape and version, which must never hit a stale copy."""
     key = (w.data_ptr(), tuple(w.shape))
     ck = (w._version,)
+    root = _root(w)
     ent = _WCACHE.get(key)
-    if ent is None or ent[0] != ck:
-        wb = ent[1] if (ent is not None and ent[1].shape == w.shape) else torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    if ent is None or ent[0] != ck or ent[2]() is not root:
+        wb = ent[1] if (ent is not None and ent[1].shape == w.shape and ent[2]() is root) else torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
         K.cast_add_bf16(w.detach().contiguous(), None, wb)
-        ent = (ck, wb)
+        ent = (ck, wb, weakref.ref(root))
         _WCACHE[key] = ent
+        if len(_WCACHE) > 4096:              # drop entries whose parameter is gone
+            for k_ in [k_ for k_, e in _WCACHE.items() if e[2]() is None]:
+                del _WCACHE[k_]
     return ent[1]
 
 
 def adopt_bf16_weight(w, wb):
     """register an up-to-date bf16 copy of `w` produced elsewhere (optim.FusedAdamWEMA writes it in the optimizer kernel),
     so the next forward does not launch a cast kernel for it"""
-    _WCACHE[(w.data_ptr(), tuple(w.shape))] = ((w._version,), wb)
+    _WCACHE[(w.data_ptr(), tuple(w.shape))] = ((w._version,), wb, weakref.ref(_root(w)))
 
 
 _DROP = {}          # device -> [seed tensor (int64, device), host site counter]
