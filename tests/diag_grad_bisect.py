@@ -1,5 +1,6 @@
-"""GPU-box diagnostic: per-parameter-group gradient error (signed) vs the reference fixture, and intermediate-tensor
-gradients (feat, src, enc, mem) vs the CPU oracle.  Writes gpurun_out/grad_debug.txt"""
+"""GPU-box diagnostic (a checker, hence under tests/: it runs the CPU oracle; not collected by pytest): per-parameter-group
+gradient error (signed) vs the reference fixture, and intermediate-tensor gradients (feat, src, enc, mem) vs the CPU oracle.
+  python tests/diag_grad_bisect.py        -> gpurun_out/grad_debug.txt"""
 import collections
 import os
 import sys
@@ -8,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from helpers import batch_for, load_gold, run_oracle, state_dict  # noqa: E402
 import test_model_gpu as T  # noqa: E402
 
