@@ -8,6 +8,9 @@
  *   - only enqueues work on the given stream, never synchronises, never allocates;
  *   - returns 0 on success or a negative TDB_ERR_* code; tdb_last_error_string() explains it.
  * The caller (PyTorch, or any host) owns every buffer including workspaces.
+ * Process-wide state: the cached driver entry point / SM count (mutex-guarded), per-kernel function attributes set on first use,
+ * the launch counter, and two measurement / A-B switches (tdb_xattn_set_timing_buffer, tdb_xattn_set_pair) that are meant to be
+ * flipped from a single host thread between launches.  Everything else is re-entrant; the error string is thread-local.
  */
 #ifndef TUBEDETR_B200_H
 #define TUBEDETR_B200_H
