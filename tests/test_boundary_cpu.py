@@ -107,3 +107,25 @@ def test_dedup_index_tensors_reconstruct_the_fast_order(built):
         joint = torch.cat([slow, fast[rest_idx]])                     # what the backbone sees
         assert joint.numel() == B * T and torch.equal(joint.sort().values, fast)
         assert torch.equal(joint[order], fast)                        # gather restores the fast order
+
+
+def test_pack_clips_equals_reference_from_tensor_list():
+    """a1: our clip packing == the reference's NestedTensor.from_tensor_list (util/misc.py:142-172) on ragged clips.
+    Runs only where the reference checkout is mounted (the build container); skipped on the GPU box."""
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not mounted")
+    sys.path.insert(0, ref)
+    try:
+        from util.misc import NestedTensor as RefNT
+    except Exception as e:      # optional third-party imports of the reference's util package
+        pytest.skip(f"reference util.misc not importable here: {e}")
+    finally:
+        sys.path.remove(ref)
+    from tubedetr_b200.synthetic import pack_clips
+    g = torch.Generator().manual_seed(3)
+    clips = [torch.randn(3, 5, 40, 56, generator=g), torch.randn(3, 3, 48, 32, generator=g), torch.randn(3, 4, 48, 56, generator=g)]
+    frames, mask = pack_clips(clips)
+    r = RefNT.from_tensor_list(clips)
+    assert torch.equal(frames, r.tensors) and torch.equal(mask, r.mask)
