@@ -129,7 +129,7 @@ def _ref_attn(q, k, v, kpm, H, scale):
     return (p @ vh).transpose(1, 2).reshape(B, Lq, d), p
 
 
-@pytest.mark.parametrize("B,Lq,Lk", [(5, 59, 59), (2, 100, 100), (12, 1, 141), (1, 200, 200)])
+@pytest.mark.parametrize("B,Lq,Lk", [(5, 59, 59), (2, 100, 100), (12, 1, 141), (1, 200, 200), (1, 7, 180), (1, 5, 300), (1, 3, 500)])
 def test_mha_fwd_bwd(B, Lq, Lk):
     from tubedetr_b200 import kernels as K
     H, d = 8, 256

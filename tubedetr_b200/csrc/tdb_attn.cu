@@ -34,7 +34,8 @@ struct AttnParams {
 
 // Shared-memory layout of the row kernels (fp32): [32][Lkp] transposed operand (odd pitch: conflict-free column reads),
 // [Lk4][32] row-major operand (rows >= Lk zero), [warps][Lk4] per-warp probability row, [warps][32] per-warp query row.
-constexpr int kMaxChunks = 8;            // Lk <= 256 keys in registers (32 lanes x 8 chunks)
+constexpr int kMaxChunks = 16;           // Lk <= 512 keys in registers (32 lanes x 16 chunks); kernels are instantiated for
+                                         // NC = 4, 5, 6, 8, 12, 16 chunks so that no predicated-off chunk costs issue slots
 
 // stage head h of two bf16 [L][ld] matrices: T -> transposed [32][Lkp], R -> row-major [Lk4][32]; 16-byte global loads
 // (thread = one 8-channel group of one row: a row of a head is 64 B = 4 groups)
@@ -68,17 +69,18 @@ __device__ __forceinline__ void stage_head(const bf16* __restrict__ tsrc, long l
 }
 
 // s[c] = sum_d qrow[d] * T[d][c*32 + lane]  for the chunks c < nc (register blocked: one broadcast read of q per d)
-__device__ __forceinline__ void row_scores(const float* __restrict__ qrow, const float* __restrict__ tmat, int Lkp, int lane, int nc,
-                                           float (&s)[kMaxChunks]) {
+// (chunks beyond Lk read in-bounds garbage of the next row / the following buffer; the callers overwrite those lanes)
+template <int NC>
+__device__ __forceinline__ void row_scores(const float* __restrict__ qrow, const float* __restrict__ tmat, int Lkp, int lane,
+                                           float (&s)[NC]) {
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) s[c] = 0.f;
+  for (int c = 0; c < NC; ++c) s[c] = 0.f;
 #pragma unroll 8
   for (int d = 0; d < HD; ++d) {
     const float qv = qrow[d];
     const float* tr = tmat + d * Lkp + lane;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c)
-      if (c < nc) s[c] = fmaf(qv, tr[c * 32], s[c]);
+    for (int c = 0; c < NC; ++c) s[c] = fmaf(qv, tr[c * 32], s[c]);
   }
 }
 
@@ -96,6 +98,7 @@ __device__ __forceinline__ float row_combine(const float* __restrict__ w, const 
   return (a0 + a1) + (a2 + a3);
 }
 
+template <int NC>
 __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams a) {
   pdl_wait();
   pdl_trigger();
@@ -114,31 +117,27 @@ __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams 
   const uint8_t* mk = a.kpm ? a.kpm + (long long)b * a.Lk : nullptr;
   float* pw = prow + warp * Lk4;
   float* qw = qsm + warp * HD;
-  const int nc = (a.Lk + 31) >> 5;
   if (lane < Lk4 - a.Lk) pw[a.Lk + lane] = 0.f;          // zero tail of the probability row (read by row_combine)
   for (int i = blockIdx.y * nwarps + warp; i < a.Lq; i += gridDim.y * nwarps) {
     const bf16* qr = a.q + ((long long)b * a.Lq + i) * a.ldq + h * HD;
     qw[lane] = __bfloat162float(qr[lane]) * a.scale;
     __syncwarp();
-    float s[kMaxChunks];
-    row_scores(qw, kt, Lkp, lane, nc, s);
+    float s[NC];
+    row_scores<NC>(qw, kt, Lkp, lane, s);
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int j = c * 32 + lane;
-      if (c < nc) {
-        if (j >= a.Lk || (mk && mk[j])) s[c] = -INFINITY;
-        mx = fmaxf(mx, s[c]);
-      }
+      if (j >= a.Lk || (mk && mk[j])) s[c] = -INFINITY;
+      mx = fmaxf(mx, s[c]);
     }
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c)
-      if (c < nc) {
-        s[c] = (mx == -INFINITY || s[c] == -INFINITY) ? 0.f : __expf(s[c] - mx);
-        sum += s[c];
-      }
+    for (int c = 0; c < NC; ++c) {
+      s[c] = (mx == -INFINITY || s[c] == -INFINITY) ? 0.f : __expf(s[c] - mx);
+      sum += s[c];
+    }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;  // all keys masked -> NaN, exactly like the reference softmax
     const long long prow_off = (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
@@ -146,9 +145,9 @@ __global__ void __launch_bounds__(kAttnThreads) mha_fwd_kernel(const AttnParams 
     const uint8_t* kp = a.keep ? a.keep + prow_off : nullptr;
     float* pd = (a.keep && a.pdrop) ? a.pdrop + prow_off : nullptr;   // only needed when the head-mean weights are requested
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int j = c * 32 + lane;
-      if (c < nc && j < a.Lk) {
+      if (j < a.Lk) {
         float e = s[c];
         pg[j] = e * inv;
         if (kp) {                   // P <- P * keep / (1 - p); the context uses the dropped probabilities
@@ -193,6 +192,7 @@ struct AttnBwdParams {
 };
 
 // row pass: one warp per query row: dP = dO V^T (+ dPbar/H), dS, dQ = scale * dS K
+template <int NC>
 __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwdParams a) {
   pdl_wait();
   pdl_trigger();
@@ -210,7 +210,6 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
   __syncthreads();
   float* dw = drow + warp * Lk4;
   float* dov = dosm + warp * HD;
-  const int nc = (a.Lk + 31) >> 5;
   const float invH = 1.f / a.H;
   if (lane < Lk4 - a.Lk) dw[a.Lk + lane] = 0.f;
   for (int i = blockIdx.y * nwarps + warp; i < a.Lq; i += gridDim.y * nwarps) {
@@ -220,14 +219,14 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
     const float* pr = a.p + roff;
     const float* dpb = a.dpbar ? a.dpbar + ((long long)b * a.Lq + i) * a.Lk : nullptr;
     const uint8_t* kr = a.keep ? a.keep + roff : nullptr;
-    float dp[kMaxChunks], pj[kMaxChunks];
-    row_scores(dov, vt, Lkp, lane, nc, dp);
+    float dp[NC], pj[NC];
+    row_scores<NC>(dov, vt, Lkp, lane, dp);
     float rs = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int j = c * 32 + lane;
       pj[c] = 0.f;
-      if (c < nc && j < a.Lk) {
+      if (j < a.Lk) {
         float d = dp[c];
         if (dpb) d += dpb[j] * invH;
         if (kr) d = kr[j] ? d * a.keep_scale : 0.f;      // d(pre-dropout P) = d(post) * keep / (1 - p)
@@ -240,9 +239,9 @@ __global__ void __launch_bounds__(kAttnThreads) mha_bwd_row_kernel(const AttnBwd
     float* dsg = a.ds + roff;
     float* pdg = kr ? a.pd_scratch + roff : nullptr;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int j = c * 32 + lane;
-      if (c < nc && j < a.Lk) {
+      if (j < a.Lk) {
         const float d = pj[c] > 0.f ? pj[c] * (dp[c] - rs) : 0.f;  // masked keys have P = 0 exactly
         dw[j] = d;
         dsg[j] = d;
@@ -329,15 +328,34 @@ static int attn_grid_y(int BH, int Lq) {
   return want < per ? want : per;
 }
 
+template <int NC>
+static int attn_init_nc() {
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_row_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return TDB_OK;
+}
 static int attn_init() {
   static bool attr = false;
   if (!attr) {
-    TDB_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TDB_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int rc;
+    if ((rc = attn_init_nc<4>()) || (rc = attn_init_nc<5>()) || (rc = attn_init_nc<6>()) || (rc = attn_init_nc<8>()) ||
+        (rc = attn_init_nc<12>()) || (rc = attn_init_nc<16>()))
+      return rc;
     attr = true;
   }
   return TDB_OK;
 }
+// smallest instantiated chunk count covering Lk keys
+#define TDB_ATTN_DISPATCH(Lk, KERNEL, ...)                                              \
+  do {                                                                                  \
+    const int nc_ = ((Lk) + 31) / 32;                                                   \
+    if (nc_ <= 4) TDB_CHECK_CUDA(tdb_launch(KERNEL<4>, __VA_ARGS__));                   \
+    else if (nc_ <= 5) TDB_CHECK_CUDA(tdb_launch(KERNEL<5>, __VA_ARGS__));              \
+    else if (nc_ <= 6) TDB_CHECK_CUDA(tdb_launch(KERNEL<6>, __VA_ARGS__));              \
+    else if (nc_ <= 8) TDB_CHECK_CUDA(tdb_launch(KERNEL<8>, __VA_ARGS__));              \
+    else if (nc_ <= 12) TDB_CHECK_CUDA(tdb_launch(KERNEL<12>, __VA_ARGS__));            \
+    else TDB_CHECK_CUDA(tdb_launch(KERNEL<16>, __VA_ARGS__));                           \
+  } while (0)
 
 extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            const uint8_t* kpm, void* o, int64_t ldo, float* p, float* pbar, const uint8_t* keep, float* pdrop,
@@ -345,13 +363,13 @@ extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   TDB_REQUIRE(!(keep && pbar) || pdrop, "tdb_mha_fwd: head-mean weights under dropout need the pdrop output");
   TDB_REQUIRE(q && k && v && o && p && B > 0 && H > 0 && Lq > 0 && Lk > 0, "tdb_mha_fwd: bad args");
   size_t smem = attn_smem_bytes(Lk, kAttnThreads);
-  TDB_REQUIRE(Lk <= 32 * tdb::kMaxChunks, "tdb_mha_fwd: Lk=%d > %d keys", Lk, 32 * tdb::kMaxChunks);
+  TDB_REQUIRE(Lk <= 32 * tdb::kMaxChunks && smem <= 200 * 1024, "tdb_mha_fwd: Lk=%d > %d keys", Lk, 32 * tdb::kMaxChunks);
   TDB_REQUIRE((((uintptr_t)k | (uintptr_t)v) & 15) == 0 && ldk % 8 == 0 && ldv % 8 == 0, "tdb_mha_fwd: k/v need 16-byte aligned head slices");
   int rc = attn_init();
   if (rc) return rc;
   AttnParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, kpm, (bf16*)o, ldo, p, pdrop, keep, keep_scale, B, H, Lq, Lk, scale};
   dim3 grid(B * H, attn_grid_y(B * H, Lq));
-  TDB_CHECK_CUDA(tdb_launch(mha_fwd_kernel, dim3(grid), dim3(kAttnThreads), smem, (cudaStream_t)stream_, a));
+  TDB_ATTN_DISPATCH(Lk, mha_fwd_kernel, dim3(grid), dim3(kAttnThreads), smem, (cudaStream_t)stream_, a);
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   if (pbar) {
@@ -370,7 +388,7 @@ extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
                            float scale, void* stream_) {
   TDB_REQUIRE(q && k && v && dout && p && ds_scratch && dq && dk && dv, "tdb_mha_bwd: null pointer");
   size_t smem = attn_smem_bytes(Lk, kAttnThreads);
-  TDB_REQUIRE(Lk <= 32 * tdb::kMaxChunks, "tdb_mha_bwd: Lk=%d > %d keys", Lk, 32 * tdb::kMaxChunks);
+  TDB_REQUIRE(Lk <= 32 * tdb::kMaxChunks && smem <= 200 * 1024, "tdb_mha_bwd: Lk=%d > %d keys", Lk, 32 * tdb::kMaxChunks);
   TDB_REQUIRE((((uintptr_t)k | (uintptr_t)v) & 15) == 0 && ldk % 8 == 0 && ldv % 8 == 0, "tdb_mha_bwd: k/v need 16-byte aligned head slices");
   int rc = attn_init();
   if (rc) return rc;
@@ -378,7 +396,7 @@ extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
   AttnBwdParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)dout, ldq, ldk, ldv, lddo, p, keep, keep_scale,
                   pd_scratch, dpbar, ds_scratch, (bf16*)dq, (bf16*)dk, (bf16*)dv, lddq, lddk, lddv, B, H, Lq, Lk, scale};
   dim3 g1(B * H, attn_grid_y(B * H, Lq));
-  TDB_CHECK_CUDA(tdb_launch(mha_bwd_row_kernel, dim3(g1), dim3(kAttnThreads), smem, (cudaStream_t)stream_, a));
+  TDB_ATTN_DISPATCH(Lk, mha_bwd_row_kernel, dim3(g1), dim3(kAttnThreads), smem, (cudaStream_t)stream_, a);
   dim3 g2(B * H, (Lk + kColKeys - 1) / kColKeys);
   TDB_CHECK_CUDA(tdb_launch(mha_bwd_col_kernel, dim3(g2), dim3(kAttnThreads), 0, (cudaStream_t)stream_, a));
   TDB_CHECK_CUDA(cudaGetLastError());
