@@ -129,3 +129,40 @@ def test_pack_clips_equals_reference_from_tensor_list():
     frames, mask = pack_clips(clips)
     r = RefNT.from_tensor_list(clips)
     assert torch.equal(frames, r.tensors) and torch.equal(mask, r.mask)
+
+
+def test_criterion_random_ragged_batches_match_oracle(built):
+    """SetCriterion (batched over the 6 decoder layers, no host sync) == the oracle's per-layer restatement of reference
+    models/tubedetr.py:270-372 on random ragged batches (padded frames, different moments), values and gradients"""
+    from oracle import tubedetr_oracle as O
+    crit = built[1]
+    g = torch.Generator().manual_seed(17)
+    for trial in range(3):
+        B, T = 3, 12 + trial
+        durs = [T, T - 3, T - 5]
+        time_mask = torch.zeros(B, T, dtype=torch.bool)
+        for b, d in enumerate(durs):
+            time_mask[b, :d] = True
+        inter = [[1, 4], [2, d2 := durs[1] - 2], [0, 0]]
+        keep = torch.tensor([b * T + t for b, (s, e) in enumerate(inter) for t in range(s, e + 1)])
+        K_ = keep.numel()
+        tb = torch.cat([torch.rand(K_, 2, generator=g) * 0.5 + 0.25, torch.rand(K_, 2, generator=g) * 0.3 + 0.1], 1)
+
+        def layer():
+            w = torch.rand(B, T, T, generator=g).softmax(-1)
+            return {"pred_boxes": torch.cat([torch.rand(B * T, 2, generator=g) * 0.5 + 0.25, torch.rand(B * T, 2, generator=g) * 0.3 + 0.1], 1).requires_grad_(True),
+                    "pred_sted": torch.randn(B, T, 2, generator=g).requires_grad_(True), "weights": w.requires_grad_(True)}
+        layers = [layer() for _ in range(6)]
+        out = dict(layers[0], aux_outputs=layers[1:])
+        ref = O.criterion(out, tb, inter, time_mask, keep)
+        o = dict(out, pred_boxes=out["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in out["aux_outputs"]])
+        crit.static = None
+        got = crit(o, [{"boxes": tb[i:i + 1]} for i in range(K_)], inter, time_mask)
+        assert set(got) == set(ref)
+        for k_ in ref:
+            torch.testing.assert_close(got[k_], ref[k_], atol=1e-5, rtol=1e-5, msg=k_)
+        leaves = [t for l in layers for t in l.values()]
+        ga = torch.autograd.grad(sum(got.values()), leaves, retain_graph=True)
+        gb = torch.autograd.grad(sum(ref.values()), leaves)
+        for a, c in zip(ga, gb):
+            torch.testing.assert_close(a, c, atol=1e-6, rtol=1e-4)
