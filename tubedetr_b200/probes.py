@@ -40,7 +40,7 @@ def xattn_phase(F=100, S=141, pair=0, reps=24):
             run(i)
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()          # replay a graph: the eager ctypes launch path (~10 us per call) would hide the kernels
-        with torch.cuda.graph(gr):
+        with torch.cuda.graph(gr, capture_error_mode="thread_local"):   # an NCCL watchdog thread may be polling events (N > 1)
             for i in range(reps):
                 run(i)
         gr.replay()
