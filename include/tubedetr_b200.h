@@ -174,6 +174,18 @@ int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, cons
                         const uint8_t* kpm, const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar,
                         void* workspace, int64_t ws_bytes, int F, int S, float scale, void* stream);
 
+/* Self-attention forward with both contractions on tcgen05 (S and O accumulators in TMEM, Q/K/V by TMA, softmax on 128 threads;
+ * tdb_attn_tc.cu).  Same arguments and results as tdb_mha_fwd (without pbar: the caller averages p / pdrop); needs an even H and
+ * Lq, Lk <= 256.  Opt-in: tdb_mha_set_tc(1) or env TDB_MHA_TC=1 makes the Python layer route eligible shapes here. */
+int tdb_mha_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm,
+                   void* o, int64_t ldo, float* p, const uint8_t* keep, float* pdrop, float keep_scale, int B, int H, int Lq,
+                   int Lk, float scale, void* stream);
+int tdb_mha_tc_supported(int H, int Lq, int Lk);
+/* pbar[b][i][j] = mean over heads of p[b][h][i][j] (the weights nn.MultiheadAttention returns) */
+int tdb_head_mean(const float* p, float* pbar, int B, int H, int Lq, int Lk, void* stream);
+int tdb_mha_set_tc(int on);
+int tdb_mha_tc_enabled(void);
+
 /* Dropout keep mask (1 = keep, probability 1 - p) from a counter-based hash of (seed[0] in DEVICE memory, site, index):
  * replaces torch.rand -> compare -> cast at the attention-dropout sites (reference models/transformer.py:613, dropout=0.1).
  * The host bumps seed[0] once per training step (a captured op), `site` numbers the call sites within a step. */

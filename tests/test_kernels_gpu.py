@@ -1,5 +1,6 @@
 """GPU parity of the helper / attention / LayerNorm kernels (through the C ABI) against fp32 PyTorch."""
 import math
+import os
 
 import pytest
 import torch
@@ -429,3 +430,32 @@ def test_xattn_pair_variant_is_bit_identical(F, S):
     assert torch.isfinite(outs[1][0].float()).all()
     for a, c in zip(outs[0], outs[1]):
         assert torch.equal(a, c)
+
+
+@pytest.mark.skipif(os.environ.get("TDB_EXPERIMENTAL", "0") == "0", reason="opt-in tcgen05 self-attention (set TDB_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("B,Lq,Lk,drop", [(25, 141, 141, 0.0), (1, 100, 100, 0.1), (2, 200, 200, 0.0), (3, 59, 59, 0.1), (2, 7, 33, 0.0)])
+def test_mha_tc_forward_matches_cuda_core_kernel(B, Lq, Lk, drop):
+    """tcgen05 self-attention forward (S and O in TMEM) vs the CUDA-core kernel on the same packed bf16 operands: same
+    probabilities (fp32 softmax of bf16 x bf16 products on both sides) and context to bf16 rounding of P"""
+    from tubedetr_b200 import kernels as K
+    H, d = 8, 256
+    scale = 1 / math.sqrt(32)
+    qk, v = _r((B * Lq, 512), 120), _r((B * Lk, d), 121)
+    kpm = torch.zeros(B, Lk, dtype=torch.uint8, device="cuda")
+    kpm[:, Lk - Lk // 5:] = 1
+    kpm[0] = 0
+    keep = None
+    if drop > 0:
+        keep = (torch.rand(B, H, Lq, Lk, device="cuda", generator=torch.Generator(device="cuda").manual_seed(8)) >= drop).to(torch.uint8)
+    res = []
+    for tc in (False, True):
+        o = torch.zeros(B * Lq, d, dtype=torch.bfloat16, device="cuda")
+        p, pd = torch.zeros(B, H, Lq, Lk, device="cuda"), (torch.zeros(B, H, Lq, Lk, device="cuda") if keep is not None else None)
+        pbar = torch.zeros(B, Lq, Lk, device="cuda")
+        f = K.mha_tc_fwd if tc else K.mha_fwd
+        f(qk[:, :256], qk[:, 256:], v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pd, keep_scale=1 / (1 - drop) if drop else 1.0)
+        torch.cuda.synchronize()
+        res.append((o, p, pbar))
+    _close(res[1][1], res[0][1], 1e-4)
+    _close(res[1][2], res[0][2], 1e-4)
+    _close(res[1][0], res[0][0], 1e-2)

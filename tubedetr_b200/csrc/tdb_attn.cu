@@ -381,6 +381,15 @@ extern "C" int tdb_mha_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   return TDB_OK;
 }
 
+extern "C" int tdb_head_mean(const float* p, float* pbar, int B, int H, int Lq, int Lk, void* stream_) {
+  TDB_REQUIRE(p && pbar && B > 0 && H > 0 && Lq > 0 && Lk > 0, "tdb_head_mean: bad args");
+  long long LL = (long long)Lq * Lk;
+  TDB_CHECK_CUDA(tdb_launch(head_mean_kernel, dim3((unsigned)(((long long)B * LL + 255) / 256)), dim3(256), 0, (cudaStream_t)stream_, p, pbar, B, H, LL));
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(1);
+  return TDB_OK;
+}
+
 extern "C" int tdb_mha_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            const void* dout, int64_t lddo, const float* p, const uint8_t* keep, float keep_scale,
                            float* pd_scratch, const float* dpbar, float* ds_scratch, void* dq,

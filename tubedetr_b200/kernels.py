@@ -72,9 +72,20 @@ def colsum_bf16(x, out, accumulate=False):
 def mha_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=None, pdrop=None, keep_scale=1.0):
     """q,k,v: 2-D bf16 views [B*L, >=H*32] (row stride = .stride(0)); kpm uint8 [B,Lk] or None.
     keep (uint8 [B,H,Lq,Lk]) + pdrop enable attention-probability dropout."""
+    if lib().tdb_mha_tc_enabled() and lib().tdb_mha_tc_supported(H, Lq, Lk):     # opt-in tcgen05 path (tdb_attn_tc.cu)
+        return mha_tc_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pdrop, keep_scale=keep_scale)
     check(lib().tdb_mha_fwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(kpm),
                             ptr(o), _i64(o.stride(0)), ptr(p), ptr(pbar), ptr(keep), ptr(pdrop), _f(keep_scale),
                             B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_fwd")
+
+
+def mha_tc_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=None, pdrop=None, keep_scale=1.0):
+    """same contract as mha_fwd with QK^T and PV on tcgen05 (S / O accumulators in TMEM); pbar = head mean of p (or pdrop)"""
+    check(lib().tdb_mha_tc_fwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(kpm),
+                               ptr(o), _i64(o.stride(0)), ptr(p), ptr(keep), ptr(pdrop), _f(keep_scale),
+                               B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_tc_fwd")
+    if pbar is not None:
+        check(lib().tdb_head_mean(ptr(pdrop if keep is not None else p), ptr(pbar), B, H, Lq, Lk, stream_ptr()), "head_mean")
 
 
 def mha_bwd(q, k, v, dout, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, keep=None, keep_scale=1.0, pd_scratch=None):
