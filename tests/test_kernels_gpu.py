@@ -440,7 +440,11 @@ def test_mha_tc_forward_matches_cuda_core_kernel(B, Lq, Lk, drop):
     from tubedetr_b200 import kernels as K
     H, d = 8, 256
     scale = 1 / math.sqrt(32)
-    qk, v = _r((B * Lq, 512), 120), _r((B * Lk, d), 121)
+    if Lq == Lk:                        # packed self-attention operands as the model passes them ([R, 512] = q | k)
+        qk, v = _r((B * Lq, 512), 120), _r((B * Lk, d), 121)
+        qv, kv = qk[:, :256], qk[:, 256:]
+    else:
+        qv, kv, v = _r((B * Lq, d), 120), _r((B * Lk, d), 122), _r((B * Lk, d), 121)
     kpm = torch.zeros(B, Lk, dtype=torch.uint8, device="cuda")
     kpm[:, Lk - Lk // 5:] = 1
     kpm[0] = 0
@@ -453,7 +457,7 @@ def test_mha_tc_forward_matches_cuda_core_kernel(B, Lq, Lk, drop):
         p, pd = torch.zeros(B, H, Lq, Lk, device="cuda"), (torch.zeros(B, H, Lq, Lk, device="cuda") if keep is not None else None)
         pbar = torch.zeros(B, Lq, Lk, device="cuda")
         f = K.mha_tc_fwd if tc else K.mha_fwd
-        f(qk[:, :256], qk[:, 256:], v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pd, keep_scale=1 / (1 - drop) if drop else 1.0)
+        f(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pd, keep_scale=1 / (1 - drop) if drop else 1.0)
         torch.cuda.synchronize()
         res.append((o, p, pbar))
     _close(res[1][1], res[0][1], 1e-4)
