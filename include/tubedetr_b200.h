@@ -176,10 +176,18 @@ int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, cons
 
 /* Self-attention forward with both contractions on tcgen05 (S and O accumulators in TMEM, Q/K/V by TMA, softmax on 128 threads;
  * tdb_attn_tc.cu).  Same arguments and results as tdb_mha_fwd (without pbar: the caller averages p / pdrop); needs an even H and
- * Lq, Lk <= 256.  Opt-in: tdb_mha_set_tc(1) or env TDB_MHA_TC=1 makes the Python layer route eligible shapes here. */
+ * Lq, Lk <= 256.  Opt-in: tdb_mha_set_tc(1) or env TDB_MHA_TC=1 makes the Python layer route eligible shapes here
+ * (level 2 also routes the backward to tdb_mha_tc_bwd). */
 int tdb_mha_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm,
                    void* o, int64_t ldo, float* p, const uint8_t* keep, float* pdrop, float keep_scale, int B, int H, int Lq,
                    int Lk, float scale, void* stream);
+/* backward on the same scheme: dPd = dO V^T, dQ = dS K, dK = dS^T Q, dV = Pd^T dO all on tcgen05 (the bf16 dS / Pd tiles in shared
+ * memory serve as K-major AND MN-major A operands); same arguments as tdb_mha_bwd without the scratch buffers.  Drafted at the end of
+ * round 1, NOT yet run on hardware: reachable only through tdb_mha_set_tc(2) / TDB_MHA_TC=2. */
+int tdb_mha_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
+                   int64_t lddo, const float* p, const uint8_t* keep, float keep_scale, const float* dpbar, void* dq,
+                   int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale,
+                   void* stream);
 int tdb_mha_tc_supported(int H, int Lq, int Lk);
 /* pbar[b][i][j] = mean over heads of p[b][h][i][j] (the weights nn.MultiheadAttention returns) */
 int tdb_head_mean(const float* p, float* pbar, int B, int H, int Lq, int Lk, void* stream);

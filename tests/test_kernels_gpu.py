@@ -463,3 +463,36 @@ def test_mha_tc_forward_matches_cuda_core_kernel(B, Lq, Lk, drop):
     _close(res[1][1], res[0][1], 1e-4)
     _close(res[1][2], res[0][2], 1e-4)
     _close(res[1][0], res[0][0], 1e-2)
+
+
+@pytest.mark.skipif(os.environ.get("TDB_EXPERIMENTAL", "0") != "2", reason="tcgen05 attention backward: drafted, not yet run on hardware (TDB_EXPERIMENTAL=2)")
+@pytest.mark.parametrize("B,L,drop", [(25, 141, 0.0), (1, 100, 0.1), (2, 200, 0.0), (3, 59, 0.1)])
+def test_mha_tc_backward_matches_cuda_core_kernel(B, L, drop):
+    from tubedetr_b200 import kernels as K
+    H, d = 8, 256
+    scale = 1 / math.sqrt(32)
+    qk, v, do = _r((B * L, 512), 130), _r((B * L, d), 131), _r((B * L, d), 132)
+    kpm = torch.zeros(B, L, dtype=torch.uint8, device="cuda")
+    kpm[:, L - L // 5:] = 1
+    kpm[0] = 0
+    keep = None
+    if drop > 0:
+        keep = (torch.rand(B, H, L, L, device="cuda", generator=torch.Generator(device="cuda").manual_seed(8)) >= drop).to(torch.uint8)
+    o = torch.zeros(B * L, d, dtype=torch.bfloat16, device="cuda")
+    p, pd = torch.zeros(B, H, L, L, device="cuda"), (torch.zeros(B, H, L, L, device="cuda") if keep is not None else None)
+    pbar = torch.zeros(B, L, L, device="cuda")
+    ks = 1 / (1 - drop) if drop else 1.0
+    K.mha_fwd(qk[:, :256], qk[:, 256:], v, kpm, o, p, pbar, B, H, L, L, scale, keep=keep, pdrop=pd, keep_scale=ks)
+    dpbar = _r((B, L, L), 133, torch.float32)
+    res = []
+    for tc in (False, True):
+        dqk, dv = torch.zeros_like(qk), torch.zeros_like(v)
+        if tc:
+            K.mha_tc_bwd(qk[:, :256], qk[:, 256:], v, do, p, dpbar, dqk[:, :256], dqk[:, 256:], dv, B, H, L, L, scale, keep=keep, keep_scale=ks)
+        else:
+            K.mha_bwd(qk[:, :256], qk[:, 256:], v, do, p, dpbar, torch.empty_like(p), dqk[:, :256], dqk[:, 256:], dv, B, H, L, L, scale,
+                      keep=keep, keep_scale=ks, pd_scratch=torch.empty_like(p) if keep is not None else None)
+        torch.cuda.synchronize()
+        res.append((dqk, dv))
+    _close(res[1][0], res[0][0], 2e-2)
+    _close(res[1][1], res[0][1], 2e-2)

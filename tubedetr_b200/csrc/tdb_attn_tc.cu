@@ -233,13 +233,256 @@ mha_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward on the same scheme (opt-in with the forward).  Per (sequence b, head pair g), for head e and 128-row query tile mt:
+//   MMA1   dPd[128 x LKP]  = dO_e V_e^T                                  -> TMEM [0, LKP)
+//   rows   dP = dropout'(dPd + dPbar / H),  rs = sum_j P dP,  dS = scale P (dP - rs)        (thread = query row)
+//          dS and Pd (post-dropout P) as bf16 into two 128-byte-swizzled K-major tiles [128 x LKP] in shared memory
+//   MMA2a  dQ[128 x 64]    = dS K_pair        (A = dS K-major,  B = K MN-major)              -> TMEM [0, 64)  (dPd is consumed)
+//   MMA2b  dK[keys x 64]  += dS^T Q_pair      (A = the SAME dS tile read MN-major, B = Q MN-major) -> TMEM [256 + 64 mt', +64)
+//   MMA2c  dV[keys x 64]  += Pd^T dO_pair     (A = Pd tile read MN-major, B = dO MN-major)   -> TMEM [384 + 64 mt', +64)
+// dK / dV accumulate over the query tiles of a head and are written once per head; every result keeps the 32 columns of head e
+// of the 64-wide pair product.  The softmax scale is folded into dS, so dQ and dK come out scaled.
+struct TcBwdSmem {
+  uint64_t kvfull, qfull, s_full, p_full, mma2_done, dq_free, kv_free;
+  uint32_t tmem_slot, pad;
+};
+
+struct TcBwdParams {
+  const float* p;       // [B][H][Lq][Lk] normalised probabilities before dropout
+  const uint8_t* keep;  // [B][H][Lq][Lk] or null
+  float keep_scale;
+  const float* dpbar;   // [B][Lq][Lk] or null
+  bf16 *dq, *dk, *dv;
+  long long lddq, lddk, lddv;
+  int B, H, Lq, Lk, LKP, MT, KT;
+  float scale;
+};
+
+__device__ __forceinline__ void store_swizzled_row32(uint8_t* tile, int r, int c, const float (&x)[32]) {
+  // columns [32c, 32c + 32) of row r of a K-major 128-byte-swizzled tile made of 64-column blocks [128 x 128 B]
+  uint8_t* blk = tile + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const int chunk = ((c & 1) * 4 + q4) ^ (r & 7);
+    uint4 w;
+    w.x = pack_bf16x2(x[q4 * 8 + 0], x[q4 * 8 + 1]);
+    w.y = pack_bf16x2(x[q4 * 8 + 2], x[q4 * 8 + 3]);
+    w.z = pack_bf16x2(x[q4 * 8 + 4], x[q4 * 8 + 5]);
+    w.w = pack_bf16x2(x[q4 * 8 + 6], x[q4 * 8 + 7]);
+    *reinterpret_cast<uint4*>(blk + chunk * 16) = w;
+  }
+}
+__device__ __forceinline__ void store_row32_bf16(bf16* dst, const uint32_t (&v)[32], float mul) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4)
+    d4[q4] = make_uint4(pack_bf16x2(__uint_as_float(v[q4 * 8 + 0]) * mul, __uint_as_float(v[q4 * 8 + 1]) * mul),
+                        pack_bf16x2(__uint_as_float(v[q4 * 8 + 2]) * mul, __uint_as_float(v[q4 * 8 + 3]) * mul),
+                        pack_bf16x2(__uint_as_float(v[q4 * 8 + 4]) * mul, __uint_as_float(v[q4 * 8 + 5]) * mul),
+                        pack_bf16x2(__uint_as_float(v[q4 * 8 + 6]) * mul, __uint_as_float(v[q4 * 8 + 7]) * mul));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mha_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                  const __grid_constant__ TcBwdParams a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // layout: Q tile [128 x 128 B] | dO tile | K [LKP x 128 B] | V [LKP x 128 B] | dS blocks [2 KT][128 x 128 B] | Pd blocks | barriers
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + 16384;
+  uint8_t* sK = sdO + 16384;
+  uint8_t* sV = sK + a.LKP * 128;
+  uint8_t* sDS = sV + a.LKP * 128;
+  const int pblocks = 2 * a.KT;
+  uint8_t* sPD = sDS + pblocks * 16384;
+  TcBwdSmem& sh = *reinterpret_cast<TcBwdSmem*>(sPD + pblocks * 16384);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x % (a.H >> 1), b = blockIdx.x / (a.H >> 1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmdO);
+    mbar_init(&sh.kvfull, 1);
+    mbar_init(&sh.qfull, 1);
+    mbar_init(&sh.s_full, 1);
+    mbar_init(&sh.p_full, 128);
+    mbar_init(&sh.mma2_done, 1);
+    mbar_init(&sh.dq_free, 128);
+    mbar_init(&sh.kv_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&sh.tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh.tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  constexpr uint32_t DK_COL = 256, DV_COL = 384;
+  const int iters = 2 * a.MT;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&sh.kvfull, (uint32_t)(2 * a.LKP * 128));
+      tma_load_2d(sK, &tmK, &sh.kvfull, g * 64, b * a.Lk);
+      tma_load_2d(sV, &tmV, &sh.kvfull, g * 64, b * a.Lk);
+      const uint32_t idesc_p = umma_idesc_bf16(128, a.LKP, 0, 0);      // dPd: A = dO (K-major), B = V (K-major)
+      const uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);         // dQ:  A = dS (K-major), B = K (MN-major)
+      const uint32_t idesc_kv = umma_idesc_bf16(128, 64, 1, 1);        // dK / dV: A = dS / Pd read MN-major, B = Q / dO (MN-major)
+      const uint64_t k_hi = umma_smem_desc(0, 16, 1024);
+      const uint64_t mn_hi = umma_smem_desc(0, 8192, 1024);            // one 64-wide MN chunk
+      const uint64_t amn_hi = umma_smem_desc(0, 16384, 1024);          // A read MN-major: 64-column blocks are 16 KB apart
+      for (int it = 0; it < iters; ++it) {
+        const int e = it / a.MT, mt = it - e * a.MT;
+        const uint32_t ph = (uint32_t)(it & 1);
+        if (it > 0) mbar_wait(&sh.dq_free, ph ^ 1, 51);    // previous tile fully consumed: Q / dO buffers, dS / Pd tiles, TMEM [0, 256)
+        mbar_expect_tx(&sh.qfull, 2 * 16384);
+        tma_load_2d(sQ, &tmQ, &sh.qfull, g * 64, b * a.Lq + mt * 128);
+        tma_load_2d(sdO, &tmdO, &sh.qfull, g * 64, b * a.Lq + mt * 128);
+        if (it == 0) mbar_wait(&sh.kvfull, 0, 52);
+        mbar_wait(&sh.qfull, ph, 53);
+        tc_fence_after();
+        // ---- MMA1: dPd = dO_e V_e^T
+        const uint32_t da = smem_u32(sdO) + e * 64, va = smem_u32(sV) + e * 64;
+        umma_bf16(tmem_base, umma_desc_at(k_hi, da), umma_desc_at(k_hi, va), idesc_p, 0u);
+        umma_bf16(tmem_base, umma_desc_at(k_hi, da + 32), umma_desc_at(k_hi, va + 32), idesc_p, 1u);
+        umma_commit(&sh.s_full);
+        // ---- MMA2 once dS / Pd are in shared memory (and dPd has been read)
+        mbar_wait(&sh.p_full, ph, 54);
+        if (it == a.MT) mbar_wait(&sh.kv_free, 0, 55);     // head 1 starts: head 0's dK / dV accumulators have been read
+        tc_fence_after();
+        const uint32_t dsa = smem_u32(sDS), pda = smem_u32(sPD), ka = smem_u32(sK), qa = smem_u32(sQ), doa = smem_u32(sdO);
+        for (int ks = 0; ks < a.LKP / 16; ++ks)             // dQ: reduction over keys
+          umma_bf16(tmem_base, umma_desc_at(k_hi, dsa + (ks >> 2) * 16384 + (ks & 3) * 32), umma_desc_at(mn_hi, ka + ks * 2048), idesc_q,
+                    ks > 0 ? 1u : 0u);
+        for (int kt = 0; kt < a.KT; ++kt) {                 // dK, dV: reduction over the 128 query rows of this tile
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t acc = (mt > 0 || ks > 0) ? 1u : 0u;
+            umma_bf16(tmem_base + DK_COL + kt * 64, umma_desc_at(amn_hi, dsa + (2 * kt) * 16384 + ks * 2048),
+                      umma_desc_at(mn_hi, qa + ks * 2048), idesc_kv, acc);
+            umma_bf16(tmem_base + DV_COL + kt * 64, umma_desc_at(amn_hi, pda + (2 * kt) * 16384 + ks * 2048),
+                      umma_desc_at(mn_hi, doa + ks * 2048), idesc_kv, acc);
+          }
+        }
+        umma_commit(&sh.mma2_done);
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const int nch = a.LKP >> 5;
+    const float invH = 1.f / a.H;
+    for (int it = 0; it < iters; ++it) {
+      const int e = it / a.MT, mt = it - e * a.MT;
+      const uint32_t ph = (uint32_t)(it & 1);
+      const int h = 2 * g + e;
+      const int i = mt * 128 + r;
+      const bool valid = i < a.Lq;
+      const long long prow = (((long long)b * a.H + h) * a.Lq + i) * a.Lk;
+      const float* pr = a.p + prow;
+      const uint8_t* kr = a.keep ? a.keep + prow : nullptr;
+      const float* dpb = a.dpbar ? a.dpbar + ((long long)b * a.Lq + i) * a.Lk : nullptr;
+      mbar_wait(&sh.s_full, ph, 56);
+      tc_fence_after();
+      // pass A: rs = sum_j P dP
+      float rs = 0.f;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const int j = c * 32 + t;
+            if (j < a.Lk) {
+              float d = __uint_as_float(v[t]);
+              if (dpb) d += dpb[j] * invH;
+              if (kr) d = kr[j] ? d * a.keep_scale : 0.f;
+              rs += pr[j] * d;
+            }
+          }
+        }
+      }
+      // pass B: dS = scale P (dP - rs) and Pd, as bf16 into the swizzled tiles (zero rows / columns outside the sequence)
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + c * 32, v);
+        tmem_ld_wait();
+        float ds[32], pd[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int j = c * 32 + t;
+          float dsv = 0.f, pdv = 0.f;
+          if (valid && j < a.Lk) {
+            float d = __uint_as_float(v[t]);
+            if (dpb) d += dpb[j] * invH;
+            const bool kept = kr ? kr[j] != 0 : true;
+            if (kr) d = kept ? d * a.keep_scale : 0.f;
+            const float pj = pr[j];
+            dsv = pj > 0.f ? a.scale * pj * (d - rs) : 0.f;     // masked keys have P = 0 exactly
+            pdv = kr ? (kept ? pj * a.keep_scale : 0.f) : pj;
+          }
+          ds[t] = dsv;
+          pd[t] = pdv;
+        }
+        store_swizzled_row32(sDS, r, c, ds);
+        store_swizzled_row32(sPD, r, c, pd);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&sh.p_full);
+      // ---- dQ epilogue
+      mbar_wait(&sh.mma2_done, ph, 57);
+      tc_fence_after();
+      {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + e * 32, v);
+        tmem_ld_wait();
+        if (valid) store_row32_bf16(a.dq + ((long long)b * a.Lq + i) * a.lddq + h * 32, v, 1.f);
+      }
+      // ---- dK / dV epilogue after the last query tile of the head (thread = key row of each 128-key tile)
+      if (mt == a.MT - 1) {
+        for (int kt = 0; kt < a.KT; ++kt) {
+          const int j = kt * 128 + r;
+          uint32_t v[32];
+          tmem_ld_32x32(lane_addr + DK_COL + kt * 64 + e * 32, v);
+          tmem_ld_wait();
+          if (j < a.Lk) store_row32_bf16(a.dk + ((long long)b * a.Lk + j) * a.lddk + h * 32, v, 1.f);
+          tmem_ld_32x32(lane_addr + DV_COL + kt * 64 + e * 32, v);
+          tmem_ld_wait();
+          if (j < a.Lk) store_row32_bf16(a.dv + ((long long)b * a.Lk + j) * a.lddv + h * 32, v, 1.f);
+        }
+        tc_fence_before();
+        mbar_arrive(&sh.kv_free);
+      }
+      tc_fence_before();
+      mbar_arrive(&sh.dq_free);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace tdb
 
 using namespace tdb;
 
 static int g_mha_tc = -1;
-extern "C" int tdb_mha_set_tc(int on) {
-  g_mha_tc = on ? 1 : 0;
+extern "C" int tdb_mha_set_tc(int level) {      // 0 = CUDA-core kernels, 1 = tcgen05 forward, 2 = tcgen05 forward + backward
+  g_mha_tc = level < 0 ? 0 : (level > 2 ? 2 : level);
   return TDB_OK;
 }
 extern "C" int tdb_mha_tc_enabled(void) {
@@ -288,6 +531,53 @@ extern "C" int tdb_mha_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t
   }
   TDB_REQUIRE(smem <= 200 * 1024, "tdb_mha_tc_fwd: shared memory %zu", smem);
   TDB_CHECK_CUDA(tdb_launch(mha_tc_fwd_kernel, dim3(B * (H / 2)), dim3(TC_THREADS), smem, (cudaStream_t)stream_, tmQ, tmK, tmV, a));
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(1);
+  return TDB_OK;
+}
+
+extern "C" int tdb_mha_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
+                              int64_t lddo, const float* p, const uint8_t* keep, float keep_scale, const float* dpbar, void* dq,
+                              int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk,
+                              float scale, void* stream_) {
+  int rc = tdb_init_once();
+  if (rc) return rc;
+  TDB_REQUIRE(q && k && v && dout && p && dq && dk && dv && B > 0, "tdb_mha_tc_bwd: null argument");
+  TDB_REQUIRE(tdb_mha_tc_supported(H, Lq, Lk), "tdb_mha_tc_bwd: unsupported shape H=%d Lq=%d Lk=%d", H, Lq, Lk);
+  TDB_REQUIRE((((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0,
+              "tdb_mha_tc_bwd: gradient buffers must be 16-byte aligned with row strides %% 8 == 0");
+  TcBwdParams a;
+  a.p = p;
+  a.keep = keep;
+  a.keep_scale = keep_scale;
+  a.dpbar = dpbar;
+  a.dq = (bf16*)dq;
+  a.dk = (bf16*)dk;
+  a.dv = (bf16*)dv;
+  a.lddq = lddq;
+  a.lddk = lddk;
+  a.lddv = lddv;
+  a.B = B;
+  a.H = H;
+  a.Lq = Lq;
+  a.Lk = Lk;
+  a.LKP = (Lk + 31) / 32 * 32;
+  a.MT = (Lq + 127) / 128;
+  a.KT = (a.LKP + 127) / 128;
+  a.scale = scale;
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  if ((rc = tdb_make_tmap_bf16(&tmQ, q, (int64_t)B * Lq, (int64_t)H * 32, ldq, 128))) return rc;
+  if ((rc = tdb_make_tmap_bf16(&tmdO, dout, (int64_t)B * Lq, (int64_t)H * 32, lddo, 128))) return rc;
+  if ((rc = tdb_make_tmap_bf16(&tmK, k, (int64_t)B * Lk, (int64_t)H * 32, ldk, a.LKP))) return rc;
+  if ((rc = tdb_make_tmap_bf16(&tmV, v, (int64_t)B * Lk, (int64_t)H * 32, ldv, a.LKP))) return rc;
+  const size_t smem = 1024 + 2 * 16384 + 2 * (size_t)a.LKP * 128 + 2 * (size_t)(2 * a.KT) * 16384 + sizeof(TcBwdSmem);
+  static bool attr = false;
+  if (!attr) {
+    TDB_CHECK_CUDA(cudaFuncSetAttribute(mha_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  TDB_REQUIRE(smem <= 227 * 1024, "tdb_mha_tc_bwd: shared memory %zu", smem);
+  TDB_CHECK_CUDA(tdb_launch(mha_tc_bwd_kernel, dim3(B * (H / 2)), dim3(TC_THREADS), smem, (cudaStream_t)stream_, tmQ, tmK, tmV, tmdO, a));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   return TDB_OK;

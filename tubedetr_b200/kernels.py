@@ -88,7 +88,16 @@ def mha_tc_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=None, pdrop=N
         check(lib().tdb_head_mean(ptr(pdrop if keep is not None else p), ptr(pbar), B, H, Lq, Lk, stream_ptr()), "head_mean")
 
 
+def mha_tc_bwd(q, k, v, dout, p, dpbar, dq, dk, dv, B, H, Lq, Lk, scale, keep=None, keep_scale=1.0):
+    check(lib().tdb_mha_tc_bwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)),
+                               ptr(dout), _i64(dout.stride(0)), ptr(p), ptr(keep), _f(keep_scale), ptr(dpbar),
+                               ptr(dq), _i64(dq.stride(0)), ptr(dk), _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)),
+                               B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_tc_bwd")
+
+
 def mha_bwd(q, k, v, dout, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, keep=None, keep_scale=1.0, pd_scratch=None):
+    if lib().tdb_mha_tc_enabled() >= 2 and lib().tdb_mha_tc_supported(H, Lq, Lk):
+        return mha_tc_bwd(q, k, v, dout, p, dpbar, dq, dk, dv, B, H, Lq, Lk, scale, keep=keep, keep_scale=keep_scale)
     check(lib().tdb_mha_bwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)),
                             ptr(dout), _i64(dout.stride(0)), ptr(p), ptr(keep), _f(keep_scale), ptr(pd_scratch), ptr(dpbar),
                             ptr(ds), ptr(dq), _i64(dq.stride(0)), ptr(dk), _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)),
