@@ -70,7 +70,15 @@ CONFIGS = {
     "cfg1b": dict(durations=[6, 5], res=[(160, 160), (128, 160)], stride=2, ntok=[6, 4], flags=[], seed=1),
     "nofast": dict(durations=[6], res=(160, 160), stride=2, ntok=[6], flags=["--no_fast"], seed=2),
     "notsa": dict(durations=[6], res=(160, 160), stride=3, ntok=[5], flags=["--no_tsa", "--no_guided_attn"], seed=3),
+    # ---- full-size fixtures (BASELINE.json configs[1], [3], [4]); big tensors are stored as strided samples (`big`)
+    # cfg-2: the measured configuration, B=1 T=100 k=4 res 352, 20 tokens
+    "cfg2": dict(durations=[100], res=(352, 352), stride=4, ntok=[20], flags=[], seed=4, big=True),
+    # cfg-4 shape at one clip: --no_fast, T=200 (the longest temporal self-attention), k=2, res 352
+    "cfg4": dict(durations=[200], res=(352, 352), stride=2, ntok=[20], flags=["--no_fast"], seed=5, big=True),
+    # cfg-5: --no_tsa --no_guided_attn, T=100, res 224, k=2
+    "cfg5": dict(durations=[100], res=(224, 224), stride=2, ntok=[20], flags=["--no_tsa", "--no_guided_attn"], seed=6, big=True),
 }
+BIG_TOKEN_STEP, BIG_FRAME_STEP = 5, 7     # img_memory / pos_embed of the full-size fixtures keep [::5, ::7]
 
 
 def sample_grad(g, n=64):
@@ -138,6 +146,10 @@ def run(name, cfg, with_grad=True):
                 gs[k] = sample_grad(p.grad)
         gold["grad_norm"], gold["grad_sample"] = gn, gs
         gold["requires_grad"] = {k: p.requires_grad for k, p in model.named_parameters()}
+    if cfg.get("big"):
+        for k in ("img_memory", "pos_embed"):
+            gold[k + "_sample"] = gold.pop(k)[::BIG_TOKEN_STEP, ::BIG_FRAME_STEP]
+        gold["sample_steps"] = (BIG_TOKEN_STEP, BIG_FRAME_STEP)
     gold = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in gold.items()}
     torch.save(gold, os.path.join(HERE, name + ".pt"))
     print(name, "pred_boxes", out["pred_boxes"][0].tolist(), "loss", float(total),

@@ -23,6 +23,7 @@ def _args(cfg):
 
 
 _MODELS = {}
+GRAD_NORM_TOL, GRAD_COS_TOL = 0.08, 0.97      # per-tensor gradient norm / sampled direction vs the fp32 reference backward
 
 
 def _model(cfg):
@@ -89,7 +90,7 @@ def test_forward_matches_reference(name):
          f"pred_sted {e_sted:.4g} (absmax {g['pred_sted'].abs().max():.3f}) aux_boxes {e_aux:.4g}")
     assert out["pred_boxes"].shape == g["pred_boxes"].shape and out["pred_sted"].shape == g["pred_sted"].shape
     assert e_box <= 2e-2 and e_aux <= 2e-2
-    assert e_sted <= 2e-2 * max(1.0, g["pred_sted"].abs().max().item())
+    assert e_sted <= 2e-2                               # BASELINE.json north_star: 2e-2 absolute on the bf16 path
     assert e_mem <= 3e-2 * g["img_memory"].abs().max().item()
     if "weights" in g and name != "notsa":
         e_w, e_cw = _err(out["weights"], g["weights"]), _err(out["ca_weights"], g["ca_weights"])
@@ -138,7 +139,7 @@ def test_losses_and_gradients_match_reference(name):
     # pre-activations per layer, which removes that share of the fp32 gradient at each of the ~100 ReLUs: backbone weight
     # gradients come out 5-8 % smaller in norm with cosine >= 0.98 (tests/test_backbone_gpu.py validates the backward
     # kernels themselves to 2 % against a bf16-faithful oracle).  Hence: direction must agree, norms within 15 %.
-    bad = [w for w in worst if (w[0] > 0.15 or w[1] < 0.9) and w[4] > 1e-4]
+    bad = [w for w in worst if (w[0] > GRAD_NORM_TOL or w[1] < GRAD_COS_TOL) and w[4] > 1e-4]
     assert len(bad) <= 0.02 * checked, bad[:10]
     med = sorted(w[0] for w in worst)[len(worst) // 2]
     _log(f"{name}: grad-norm rel err median {med:.4f}, params checked {checked}")
@@ -241,7 +242,7 @@ def test_slow_frames_alias_fast_dedup(name):
     e_box, e_sted = _err(out["pred_boxes"], g["pred_boxes"]), _err(out["pred_sted"], g["pred_sted"])
     e_mem = _err(mc["img_memory"], g["img_memory"])
     _log(f"{name} (dedup): img_memory err {e_mem:.4g} pred_boxes {e_box:.4g} pred_sted {e_sted:.4g}")
-    assert e_box <= 2e-2 and e_sted <= 2e-2 * max(1.0, g["pred_sted"].abs().max().item())
+    assert e_box <= 2e-2 and e_sted <= 2e-2
     assert e_mem <= 3e-2 * g["img_memory"].abs().max().item()
     assert _err(out["pred_boxes"], res[False][0]["pred_boxes"]) <= 1e-2
     assert gr.keys() == res[False][2].keys()
@@ -249,3 +250,77 @@ def test_slow_frames_alias_fast_dedup(name):
         a, c = gr[n].float(), res[False][2][n].float()
         cos = (a * c).sum() / (a.norm() * c.norm() + 1e-20)
         assert cos > 0.99, (n, cos.item())
+
+
+# ----------------------------------------------------------------------------------------------- full-size reference fixtures
+# tests/golden/{cfg2,cfg4,cfg5}.pt come from the UNMODIFIED reference at BASELINE.json's measured sizes (make_golden.py):
+# cfg2 = configs[1] (B=1, T=100, k=4, res 352, L=20), cfg4 = the --no_fast T=200 k=2 shape of configs[3] at one clip,
+# cfg5 = configs[4] (--no_tsa --no_guided_attn, T=100, res 224, k=2).  img_memory / pos_embed are stored as [::5, ::7] samples.
+def _fullsize_outputs(name):
+    g = load_gold(name)
+    with torch.no_grad():
+        model, crit, wd, b, mc, out = _run(g["cfg"])
+    return g, model, crit, wd, b, mc, out
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg4", "cfg5"])
+def test_fullsize_forward_matches_reference(name):
+    g, model, crit, wd, b, mc, out = _fullsize_outputs(name)
+    ts, fs = g["sample_steps"]
+    for k in ("mask", "query_mask", "text_attention_mask"):
+        assert torch.equal(mc[k].cpu(), g[k]), k
+    assert _err(mc["pos_embed"][::ts, ::fs], g["pos_embed_sample"]) < 1e-4
+    assert _err(mc["query_embed"], g["query_embed"]) < 1e-4
+    e_mem = _err(mc["img_memory"][::ts, ::fs], g["img_memory_sample"])
+    e_box = _err(out["pred_boxes"], g["pred_boxes"])
+    e_sted = _err(out["pred_sted"], g["pred_sted"])
+    e_aux = _err(torch.stack([a["pred_boxes"] for a in out["aux_outputs"]]), g["aux_pred_boxes"])
+    e_auxs = _err(torch.stack([a["pred_sted"] for a in out["aux_outputs"]]), g["aux_pred_sted"])
+    _log(f"{name} (full size): img_memory err {e_mem:.4g} (absmax {g['img_memory_sample'].abs().max():.3f}) pred_boxes {e_box:.4g} "
+         f"pred_sted {e_sted:.4g} (absmax {g['pred_sted'].abs().max():.3f}) aux_boxes {e_aux:.4g} aux_sted {e_auxs:.4g}")
+    assert out["pred_boxes"].shape == g["pred_boxes"].shape and out["pred_sted"].shape == g["pred_sted"].shape
+    assert e_box <= 2e-2 and e_aux <= 2e-2 and e_sted <= 2e-2 and e_auxs <= 2e-2
+    assert e_mem <= 3e-2 * g["img_memory_sample"].abs().max().item()
+    if "weights" in g:
+        e_w, e_cw = _err(out["weights"], g["weights"]), _err(out["ca_weights"], g["ca_weights"])
+        e_aw = _err(torch.stack([a["weights"] for a in out["aux_outputs"]]), g["aux_weights"])
+        _log(f"{name} (full size): weights err {e_w:.4g} aux weights {e_aw:.4g} ca_weights err {e_cw:.4g}")
+        assert e_w <= 2e-2 and e_cw <= 2e-2 and e_aw <= 2e-2
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg5"])
+def test_fullsize_losses_and_gradients_match_reference(name):
+    g = load_gold(name)
+    model, crit, wd, b, mc, out = _run(g["cfg"])
+    keep = b["keep"].cuda()
+    o = dict(out, pred_boxes=out["pred_boxes"][keep],
+             aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in out["aux_outputs"]])
+    targets = [{"boxes": bx[None].cuda()} for bx in b["target_boxes"]]
+    losses = crit(o, targets, b["inter_idx"], b["time_mask"].cuda())
+    total = sum(losses[k] * wd[k] for k in losses if k in wd)
+    _log(f"{name} (full size): total loss {total.item():.5f} vs reference {g['loss_total'].item():.5f}")
+    assert abs(total.item() - g["loss_total"].item()) <= 2e-2 * abs(g["loss_total"].item())
+    for k, v in g["losses"].items():
+        assert abs(losses[k].item() - v.item()) <= 3e-2 * max(abs(v.item()), 0.05), (k, losses[k].item(), v.item())
+    model.zero_grad(set_to_none=True)
+    total.backward()
+    worst = []
+    for k, p in model.named_parameters():
+        if k not in g["grad_norm"]:
+            continue
+        assert p.grad is not None, k
+        ref_n, got_n = g["grad_norm"][k], p.grad.float().norm().item()
+        f = p.grad.flatten()
+        samp = f[::max(f.numel() // 64, 1)][:64].float().cpu()
+        ref_s = g["grad_sample"][k]
+        cos = torch.nn.functional.cosine_similarity(samp, ref_s, dim=0).item() if ref_s.norm() > 0 else 1.0
+        worst.append((abs(got_n - ref_n) / max(ref_n, 1e-6), cos, k, got_n, ref_n))
+    worst.sort(reverse=True)
+    for rel, cos, k, got_n, ref_n in worst[:8]:
+        _log(f"{name} (full size): grad {k}: norm {got_n:.4g} vs {ref_n:.4g} (rel {rel:.3f}) sample-cos {cos:.4f}")
+    assert len(worst) > 300
+    bad = [w for w in worst if (w[0] > GRAD_NORM_TOL or w[1] < GRAD_COS_TOL) and w[4] > 1e-4]
+    assert len(bad) <= 0.02 * len(worst), bad[:10]
+    med = sorted(w[0] for w in worst)[len(worst) // 2]
+    _log(f"{name} (full size): grad-norm rel err median {med:.4f}, params checked {len(worst)}")
+    assert med < 0.08

@@ -57,3 +57,23 @@ def test_oracle_gradients_match_reference():
     # frozen parts stay frozen (reference models/backbone.py:82-89)
     assert not g["requires_grad"]["backbone.0.body.conv1.weight"]
     assert not g["requires_grad"]["backbone.0.body.layer1.0.conv1.weight"]
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg5"])
+def test_oracle_matches_reference_at_full_size(name):
+    """the oracle against the reference at BASELINE.json's measured sizes (cfg2: B=1 T=100 k=4 res 352 L=20; cfg5: --no_tsa res 224):
+    forward only, ~20 s of CPU time each; img_memory / pos_embed fixtures are [::5, ::7] samples"""
+    g = load_gold(name)
+    ts, fs = g["sample_steps"]
+    with torch.no_grad():
+        out, cache, b = run_oracle(g["cfg"])
+    torch.testing.assert_close(cache["feat_slow"][:1], g["feat_slow0"], atol=2e-3, rtol=1e-4)
+    torch.testing.assert_close(cache["img_memory"][::ts, ::fs], g["img_memory_sample"], **TOL)
+    torch.testing.assert_close(cache["pos_embed"][::ts, ::fs], g["pos_embed_sample"], **TOL)
+    for k in ("mask", "query_mask", "text_attention_mask"):
+        assert torch.equal(cache[k], g[k]), k
+    torch.testing.assert_close(out["pred_boxes"], g["pred_boxes"], **TOL)
+    torch.testing.assert_close(out["pred_sted"], g["pred_sted"], **TOL)
+    if "weights" in g:
+        torch.testing.assert_close(out["weights"], g["weights"], **TOL)
+        torch.testing.assert_close(out["ca_weights"], g["ca_weights"], **TOL)
