@@ -54,3 +54,52 @@ def test_backbone_weight_gradients_match_oracle(N, H, W):
     # measured on B200: worst projection 0.965, worst cosine 0.992 (residual ReLU-mask flips from accumulation order)
     assert worst[0][0] < 0.05, worst[:5]
     assert min(c for _, c, _, _ in worst) > 0.985
+
+
+def test_engine_memory_is_bounded_under_varying_shapes():
+    """The reference's data pipeline changes frame count and resolution nearly every iteration (durations up to
+    video_max_len, RandomResize).  Engine buffers are ONE allocation per tag sized to the largest shape seen: after the
+    largest shape has run, further shapes allocate nothing, and results do not depend on what ran before (halo buffers are
+    re-zeroed on a shape change)."""
+    from tubedetr_b200.resnet import ResNet101Engine
+    sd = state_dict()
+    pre = "backbone.0.body."
+    eng = ResNet101Engine()
+    dsd = {k: v.cuda() for k, v in sd.items() if k.startswith(pre)}
+    g = torch.Generator().manual_seed(11)
+    shapes = [(4, 128, 160), (2, 96, 96), (3, 64, 128), (1, 128, 96), (4, 128, 160), (2, 96, 96)]
+    frames = {s: torch.randn(s[0], 3, s[1], s[2], generator=g).cuda() for s in set(shapes)}
+    with torch.no_grad():
+        Wt = eng.prepare(dsd)
+        fresh = ResNet101Engine()
+        Wf = fresh.prepare(dsd)
+        ref, _, _, _ = fresh.forward(frames[(2, 96, 96)], Wf, save=False, tag="m")
+        ref = ref.clone()
+        sizes = []
+        for s in shapes:
+            out, h, w, _ = eng.forward(frames[s], Wt, save=False, tag="m")
+            torch.cuda.synchronize()
+            sizes.append(eng.allocated_bytes())
+    assert sizes[0] == max(sizes) == sizes[-1], sizes          # the largest shape ran first: nothing grows afterwards
+    assert torch.equal(out, ref)                               # (2, 96, 96) after bigger shapes == on a fresh engine
+
+
+def test_backward_after_a_later_forward_raises():
+    """saved activations are engine-owned buffers: a second forward with the same tag before the backward must raise, not
+    return silently wrong gradients"""
+    from tubedetr_b200 import ops
+    from tubedetr_b200.resnet import ResNet101Engine
+    sd = state_dict()
+    pre = "backbone.0.body."
+    names = [pre + "layer3.5.conv2.weight", pre + "layer4.0.conv1.weight"]
+    eng = ResNet101Engine()
+    dsd = {k: v.cuda() for k, v in sd.items() if k.startswith(pre)}
+    params = [dsd[k].requires_grad_(True) for k in names]
+    Wt = eng.prepare(dsd)
+    x = torch.randn(1, 3, 64, 64, device="cuda")
+    f1 = ops.BackboneFn.apply(x, eng, Wt, names, "t", *params)
+    f2 = ops.BackboneFn.apply(x + 1, eng, Wt, names, "t", *params)
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        f1.float().sum().backward()
+    f2.float().sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in params)

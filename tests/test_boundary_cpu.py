@@ -16,7 +16,8 @@ def _args(**kw):
     d = dict(num_queries=1, aux_loss=True, video_max_len_train=200, stride=2, guided_attn=True, fast=True, fast_mode="",
              sted=True, no_tsa=False, enc_layers=6, dec_layers=6, lr_backbone=1e-5, bbox_loss_coef=5, giou_loss_coef=2,
              sted_loss_coef=10, guided_attn_loss_coef=1, sigma=1, device="cpu", hidden_dim=256, nheads=8,
-             dim_feedforward=2048, backbone="resnet101", dilation=False, position_embedding="sine")
+             dim_feedforward=2048, backbone="resnet101", dilation=False, position_embedding="sine",
+             offline_text_encoder=True)
     d.update(kw)
     return argparse.Namespace(**d)
 
@@ -166,3 +167,32 @@ def test_criterion_random_ragged_batches_match_oracle(built):
         gb = torch.autograd.grad(sum(ref.values()), leaves)
         for a, c in zip(ga, gb):
             torch.testing.assert_close(a, c, atol=1e-6, rtol=1e-4)
+
+
+def test_text_encoder_fails_loudly_without_checkpoint(monkeypatch):
+    """no silent random-init RoBERTa + hash tokenizer: without the roberta-base files (no network here) the default build raises;
+    the stand-in needs the explicit opt-in and warns"""
+    from tubedetr_b200 import build_model
+    monkeypatch.delenv("TDB_OFFLINE_TEXT_ENCODER", raising=False)
+    monkeypatch.setenv("HF_HUB_OFFLINE", "1")
+    with pytest.raises(Exception):
+        build_model(_args(offline_text_encoder=None))
+    with pytest.warns(UserWarning, match="offline text-encoder stand-in"):
+        build_model(_args(offline_text_encoder=True))
+
+
+def test_deepcopy_after_training_state_and_bounded_caches(built):
+    """EMA copies (reference main.py:370) must work at any time: transient per-step state (non-leaf trunk tensors, index cache)
+    does not follow the copy; the index cache stays bounded under varying durations"""
+    import copy
+    model = built[0]
+    x = torch.ones(3, requires_grad=True) * 2          # a non-leaf tensor: deepcopy of it raises in torch
+    model.__dict__["_trunk"] = (x, x)
+    for T in range(10, 90):
+        model._index_tensors((T,), 2, torch.device("cpu"))
+    assert len(model.__dict__["_idx_cache"]) <= 64
+    m2 = copy.deepcopy(model)
+    assert "_trunk" not in m2.__dict__ and "_idx_cache" not in m2.__dict__
+    assert m2.state_dict().keys() == model.state_dict().keys()
+    assert m2._engine is not model._engine
+    assert model.trunk_outputs()[0] is x and model.trunk_outputs() == (None, None)     # handed over once

@@ -19,7 +19,7 @@ def _build(stride, flags=()):
         fast="--no_fast" not in flags, fast_mode="", sted=True, no_tsa="--no_tsa" in flags, enc_layers=6, dec_layers=6,
         lr_backbone=1e-5, bbox_loss_coef=5, giou_loss_coef=2, sted_loss_coef=10, guided_attn_loss_coef=1, sigma=1,
         device="cuda", hidden_dim=256, nheads=8, dim_feedforward=2048, backbone="resnet101", dilation=False,
-        position_embedding="sine")
+        position_embedding="sine", offline_text_encoder=True)
     model, crit, wd = build_model(a)
     sd = state_dict()
     model.load_state_dict({k: sd[k] for k in model.state_dict()}, strict=True)

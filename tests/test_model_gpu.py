@@ -19,7 +19,7 @@ def _args(cfg):
         fast="--no_fast" not in fl, fast_mode="", sted=True, no_tsa="--no_tsa" in fl, enc_layers=6, dec_layers=6,
         lr_backbone=1e-5, bbox_loss_coef=5, giou_loss_coef=2, sted_loss_coef=10, guided_attn_loss_coef=1, sigma=1,
         device="cuda", hidden_dim=256, nheads=8, dim_feedforward=2048, backbone="resnet101", dilation=False,
-        position_embedding="sine")
+        position_embedding="sine", offline_text_encoder=True)
 
 
 _MODELS = {}
@@ -159,7 +159,11 @@ def test_train_mode_applies_dropout_and_backpropagates():
         assert (o1["pred_boxes"] - o2["pred_boxes"]).abs().max() > 1e-4            # stochastic
         assert (o1["pred_boxes"] - out_eval["pred_boxes"]).abs().max() < 0.5       # same network
         keep = b["keep"].cuda()
-        o = dict(o1, pred_boxes=o1["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in o1["aux_outputs"]])
+        # backward belongs to the LATEST forward (o2): engine-owned activations and the dropout seed are per step
+        o = dict(o2, pred_boxes=o2["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in o2["aux_outputs"]])
+        stale = (o1["pred_boxes"].float().square().sum() + o1["pred_sted"].float().square().sum())
+        with pytest.raises(RuntimeError, match="one forward per backward|overwritten by a later forward"):
+            stale.backward()                                                       # o1's saved state is gone: loud, not wrong
         losses = crit(o, [{"boxes": bx[None].cuda()} for bx in b["target_boxes"]], b["inter_idx"], b["time_mask"].cuda())
         model.zero_grad()
         sum(losses[k] * wd[k] for k in losses if k in wd).backward()

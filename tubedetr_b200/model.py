@@ -222,27 +222,37 @@ class HashTokenizer:
         return ids.to(device), am.to(device)
 
 
-def _make_text_encoder(name="roberta-base"):
+def _make_text_encoder(name="roberta-base", offline_stand_in=None):
+    """roberta-base tokenizer + encoder exactly as the reference loads them (models/transformer.py:130-135); any failure to
+    load them RAISES.  The offline stand-in (randomly initialised RobertaModel of the same architecture + HashTokenizer) exists
+    for boxes without the checkpoint (tests, bench.py, smoke) and must be asked for: `offline_stand_in=True`
+    (build(args) passes args.offline_text_encoder) or env TDB_OFFLINE_TEXT_ENCODER=1.  It warns when active: token ids then do
+    NOT match a pretrained embedding table."""
+    import os
+    import warnings
     from transformers import RobertaConfig, RobertaModel, RobertaTokenizerFast
-    try:
-        tok = RobertaTokenizerFast.from_pretrained(name, local_files_only=True)
-        enc = RobertaModel.from_pretrained(name, local_files_only=True)
-
-        def tokenize(texts, device):
-            be = tok.batch_encode_plus(texts, padding="longest", return_tensors="pt").to(device)
-            return be["input_ids"], be["attention_mask"]
-        return enc, tokenize
-    except Exception:
+    if offline_stand_in is None:
+        offline_stand_in = os.environ.get("TDB_OFFLINE_TEXT_ENCODER", "0") not in ("0", "")
+    if offline_stand_in:
+        warnings.warn("tubedetr_b200: offline text-encoder stand-in active (random-init RoBERTa architecture + hash tokenizer); "
+                      "not suitable for training or for loading pretrained checkpoints", stacklevel=2)
         cfg = RobertaConfig(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, pad_token_id=1,
                             bos_token_id=0, eos_token_id=2, layer_norm_eps=1e-5)
         return RobertaModel(cfg), HashTokenizer()
+    tok = RobertaTokenizerFast.from_pretrained(name)
+    enc = RobertaModel.from_pretrained(name)
+
+    def tokenize(texts, device):
+        be = tok.batch_encode_plus(texts, padding="longest", return_tensors="pt").to(device)
+        return be["input_ids"], be["attention_mask"]
+    return enc, tokenize
 
 
 class Transformer(nn.Module):
     """Parameter container + the video-text encoder / space-time decoder drivers."""
 
     def __init__(self, num_encoder_layers=6, num_decoder_layers=6, video_max_len=200, stride=5, no_tsa=False, fast=True,
-                 dropout=0.1):
+                 dropout=0.1, offline_text_encoder=None):
         super().__init__()
         self.dropout = dropout          # reference models/transformer.py:608-676 (attention, residual and FFN dropouts)
         self.encoder = _Stack(_EncLayer, num_encoder_layers, final_norm=False)
@@ -252,7 +262,7 @@ class Transformer(nn.Module):
         if fast:
             self.fast_encoder = _Lin(D_MODEL, D_MODEL)
             self.fast_residual = _Lin(D_MODEL, D_MODEL, zero=True)  # reference zero-inits it (transformer.py:173-174)
-        self.text_encoder, self._tokenize = _make_text_encoder()
+        self.text_encoder, self._tokenize = _make_text_encoder(offline_stand_in=offline_text_encoder)
         self.resizer = _Resizer()
         self.d_model, self.nhead, self.stride, self.no_tsa = D_MODEL, NHEAD, stride, no_tsa
         self.video_max_len = video_max_len
@@ -321,11 +331,12 @@ _TEXT_STREAMS = {}   # device -> side stream of the text encoder (module level: 
 
 class TubeDETR(nn.Module):
     def __init__(self, num_queries=1, aux_loss=True, video_max_len=200, stride=5, guided_attn=True, fast=True,
-                 fast_mode="", sted=True, no_tsa=False, enc_layers=6, dec_layers=6, train_backbone=True, dropout=0.1):
+                 fast_mode="", sted=True, no_tsa=False, enc_layers=6, dec_layers=6, train_backbone=True, dropout=0.1,
+                 offline_text_encoder=None):
         super().__init__()
         assert num_queries == 1 and fast_mode == "" and stride > 0, "only the reference default path is implemented"
         self.num_queries = num_queries
-        self.transformer = Transformer(enc_layers, dec_layers, video_max_len, stride, no_tsa, fast, dropout)
+        self.transformer = Transformer(enc_layers, dec_layers, video_max_len, stride, no_tsa, fast, dropout, offline_text_encoder)
         self.bbox_embed = _MLP(D_MODEL, D_MODEL, 4, 3)
         self.query_embed = nn.Embedding(num_queries, D_MODEL)
         self.input_proj = _Conv(2048, D_MODEL, 1, bias=True)
@@ -348,6 +359,22 @@ class TubeDETR(nn.Module):
         self.text_autocast = False  # True: RoBERTa (library call) runs its GEMMs under bf16 autocast (bench.py sets it)
 
     # ------------------------------------------------------------------ helpers
+    _TRANSIENT = ("_trunk", "_idx_cache")     # per-step state that must not follow a copy of the model
+
+    def __deepcopy__(self, memo):
+        """EMA copies (reference main.py:370 `deepcopy(model)`) may be taken at any time, also after a training forward: the
+        non-leaf trunk tensors of the last step and the device index cache stay behind."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k_, v in self.__dict__.items():
+            if k_ not in self._TRANSIENT:
+                new.__dict__[k_] = copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        return {k_: v for k_, v in self.__dict__.items() if k_ not in self._TRANSIENT}
+
     def _backbone_tensors(self):
         return {"backbone.0.body." + k: v for k, v in list(self.backbone[0].body.named_parameters()) +
                 list(self.backbone[0].body.named_buffers())}
@@ -365,6 +392,8 @@ class TubeDETR(nn.Module):
         key = (durations, k, str(dev))
         c = self.__dict__.setdefault("_idx_cache", {})
         if key not in c:
+            if len(c) >= 64:          # durations vary per batch in real training: keep the cache bounded
+                c.clear()
             B, T = len(durations), max(durations)
             n_clips = math.ceil(T / k)
             dur = torch.tensor(durations)
@@ -395,7 +424,7 @@ class TubeDETR(nn.Module):
         """(RoBERTa last_hidden_state, backbone features of the slow frames) of the latest encode call: the tensors
         `parallel.backward_overlapped` splits the backward at so the text-encoder gradients can be all-reduced while the
         backbone backward runs."""
-        return self.__dict__.get("_trunk", (None, None))
+        return self.__dict__.pop("_trunk", (None, None))     # handed over once: nothing of the step's graph stays on the module
 
     def text_stream(self, device):
         return _TEXT_STREAMS.get(device) if self.text_side_stream else None
@@ -695,7 +724,8 @@ def build(args):
     model = TubeDETR(num_queries=args.num_queries, aux_loss=args.aux_loss, video_max_len=args.video_max_len_train,
                      stride=args.stride, guided_attn=args.guided_attn, fast=args.fast, fast_mode=args.fast_mode,
                      sted=args.sted, no_tsa=args.no_tsa, enc_layers=args.enc_layers, dec_layers=args.dec_layers,
-                     train_backbone=args.lr_backbone > 0, dropout=getattr(args, "dropout", 0.1))
+                     train_backbone=args.lr_backbone > 0, dropout=getattr(args, "dropout", 0.1),
+                     offline_text_encoder=getattr(args, "offline_text_encoder", None))
     if getattr(args, "freeze_backbone", False):
         for p in model.backbone.parameters():
             p.requires_grad_(False)

@@ -96,20 +96,22 @@ def adopt_bf16_weight(w, wb):
     _WCACHE[(w.data_ptr(), tuple(w.shape))] = ((w._version,), wb, weakref.ref(_root(w)))
 
 
-_DROP = {}          # device -> [seed tensor (int64, device), host site counter]
+_DROP = {}          # device -> [seed tensor (int64, device), host site counter, generation (bumped with the seed)]
 
 
 def _drop_state(device):
     st = _DROP.get(device)
     if st is None:
         seed = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFF], dtype=torch.int64, device=device)
-        st = _DROP[device] = [seed, 0]
+        st = _DROP[device] = [seed, 0, 0]
     return st
 
 
 def advance_dropout_seed(device):
     """once per training step (TubeDETR._encode): a captured in-place add, so every CUDA-graph replay draws new masks"""
-    _drop_state(device)[0].add_(1)
+    st = _drop_state(device)
+    st[0].add_(1)
+    st[2] += 1
 
 
 def dropout_keep(shape, p, device):
@@ -412,6 +414,7 @@ class AddLayerNormFn(torch.autograd.Function):
             st = _drop_state(x.device)
             st[1] += 1
             drop = (st[0], st[1], float(drop_p))
+            ctx.drop_gen = st[2]
         K.layernorm_fwd(x, r, gamma, beta, pos, y, yb, ypb, mean, rstd, rows, D, eps, drop=drop)
         ctx.save_for_backward(x, r, gamma, mean, rstd)
         ctx.has_r = r is not None
@@ -427,6 +430,10 @@ class AddLayerNormFn(torch.autograd.Function):
         rows, D = x.shape
         if dy is None and dyb is None and dypb is None:
             return None, None, None, None, None, None, None
+        if ctx.drop is not None and _drop_state(x.device)[2] != ctx.drop_gen:
+            # the keep bits are re-hashed from the DEVICE seed, which the next training forward bumps in place
+            raise RuntimeError("tubedetr_b200: the dropout seed advanced between this forward and its backward (a second training "
+                               "forward ran first); run backward before the next forward (one forward per backward, INTEGRATION.md)")
         dy = dy.contiguous() if dy is not None else None
         dyb = dyb.contiguous() if dyb is not None else None
         dypb = dypb.contiguous() if dypb is not None else None

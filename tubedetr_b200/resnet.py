@@ -31,6 +31,7 @@ def conv_out(h, k, s, p):
 class ResNet101Engine:
     def __init__(self):
         self._bufs = {}
+        self._gen = {}        # tag -> generation, bumped by every forward that (re)writes the tag's buffers
         self._wcache = {}
         self._bn = None
         self._bn_key = None
@@ -41,12 +42,39 @@ class ResNet101Engine:
 
     # ------------------------------------------------------------------ buffers
     def buf(self, tag, shape, dtype=torch.bfloat16, zero=False, device="cuda"):
-        key = (tag, tuple(shape), dtype)
-        b = self._bufs.get(key)
-        if b is None:
-            b = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
-            self._bufs[key] = b
-        return b
+        """Scratch / activation buffer of the engine, ONE allocation per tag sized to the largest request seen: the reference's
+        data pipeline changes the frame count and the resolution nearly every iteration (durations up to video_max_len,
+        RandomResize), so keying by shape would grow without bound.  A view of the tag's storage with the requested shape is
+        returned; `zero` buffers (zero-haloed conv inputs: kernels only ever write their interior rows) are re-zeroed whenever
+        the shape changes."""
+        shape = tuple(int(x) for x in shape)
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        ent = self._bufs.get(tag)
+        if ent is None or ent[0].numel() < nbytes:
+            store = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+            ent = [store, None, None]
+            self._bufs[tag] = ent
+        if ent[1] != (shape, dtype):
+            view = ent[0][:nbytes].view(dtype).view(shape)
+            if zero:
+                view.zero_()
+            ent[1], ent[2] = (shape, dtype), view
+        return ent[2]
+
+    def allocated_bytes(self):
+        return sum(e[0].numel() for e in self._bufs.values())
+
+    def check_generation(self, ctx):
+        """Saved activations are engine-owned buffers that the next forward with the same tag overwrites in place (no autograd
+        version counter sees raw kernel writes).  One forward per backward is the contract; anything else
+        (gradient accumulation over a combined loss, checkpoint recompute, an interleaved forward) raises instead of returning
+        silently wrong gradients."""
+        if self._gen.get(ctx["tag"]) != ctx["gen"]:
+            raise RuntimeError(f"tubedetr_b200: backbone activations of tag '{ctx['tag']}' were overwritten by a later forward "
+                               "(generation %s, now %s): run backward before the next forward of the same model" % (ctx["gen"], self._gen.get(ctx["tag"])))
 
     # ------------------------------------------------------------------ weights
     def prepare(self, sd, prefix="backbone.0.body."):
@@ -103,6 +131,7 @@ class ResNet101Engine:
         many frames with per-chunk buffers that are reused by every chunk, so the intermediate activations of a chunk
         (~8 MB/frame at res 352) live in the 126 MB L2 instead of streaming through HBM; layer3/4 then run on the whole batch."""
         srcs = [f.contiguous() for f in (frames if isinstance(frames, (list, tuple)) else [frames])]
+        self._gen[tag] = self._gen.get(tag, 0) + 1
         _, _, H, Wd = srcs[0].shape
         N = sum(f.shape[0] for f in srcs)
         if l2_chunk and not save and N > l2_chunk and len(srcs) == 1:
@@ -146,7 +175,7 @@ class ResNet101Engine:
         rows into rows [n0*ho*wo, ...) of a full-batch buffer (allocated on first use) instead of a private one."""
         x, h, w = xhw
         nk = N if n_keep is None else n_keep
-        ctx = {"N": nk, "blocks": [], "tag": tag} if save else None
+        ctx = {"N": nk, "blocks": [], "tag": tag, "gen": self._gen.get(tag)} if save else None
         big = None
         for li, (width, nb, stride0) in enumerate(STAGES, start=1):
             if li < li_lo or li > li_hi:
@@ -234,6 +263,7 @@ class ResNet101Engine:
         """g_out: bf16 [N*h*w, 2048] = dL/d(pre-ReLU output of layer4.2), already masked by (feat > 0).
         grads: dict name -> fp32 tensor (torch layout) written in place for every layer2-4 conv weight."""
         from .ops import wgrad_scope
+        self.check_generation(ctx)
         N, tag = ctx["N"], ctx["tag"]
         blocks = ctx["blocks"]
         # Weight gradients run on a side stream, concurrent with the dgrad chain.  The scratch gradients are double buffered by
