@@ -105,6 +105,10 @@ int tdb_prep_weight(const float* w, void* out, void* out_scaled, const float* ro
                     int Kpad, void* stream);
 /* y(bf16) = x (+ add), n % 4 == 0 */
 int tdb_cast_add_bf16(const float* x, const float* add, void* y, int64_t n, void* stream);
+/* fp32 [rows][K] -> bf16 [rows][2K] = [hi | lo], hi = bf16(x), lo = bf16(x - hi).  The forward GEMMs of the transformer read their
+ * weights this way (tdb_gemm with ntaps = 2, a_off0 = {0, 0}, b_off0 = {0, K}: the same A tile against the hi and the lo half), which
+ * removes the weight-rounding error of the bf16 path (reference weights are fp32: models/transformer.py:608-676). K % 4 == 0 */
+int tdb_split_bf16(const float* x, void* y, int64_t rows, int K, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm with fused residual add (post-norm blocks, reference models/transformer.py:641-645, 721-750, 581;
@@ -174,20 +178,24 @@ int tdb_xattn_fused_fwd(const void* q, const void* mempb, const void* memb, cons
                         const uint8_t* kpm, const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar,
                         void* workspace, int64_t ws_bytes, int F, int S, float scale, void* stream);
 
-/* Self-attention forward with both contractions on tcgen05 (S and O accumulators in TMEM, Q/K/V by TMA, softmax on 128 threads;
- * tdb_attn_tc.cu).  Same arguments and results as tdb_mha_fwd (without pbar: the caller averages p / pdrop); needs an even H and
- * Lq, Lk <= 256.  Opt-in: tdb_mha_set_tc(1) or env TDB_MHA_TC=1 makes the Python layer route eligible shapes here
- * (level 2 also routes the backward to tdb_mha_tc_bwd). */
+/* Self-attention core with every contraction on tcgen05 (accumulators in TMEM, Q/K/V/dO by TMA, softmax on 128 threads;
+ * tdb_attn_tc.cu): the DEFAULT for the encoder's spatial attention and the decoder's temporal self-attention (reference
+ * models/transformer.py:637-640, 698-722).  Same results as tdb_mha_fwd / tdb_mha_bwd; needs an even H, 2 <= Lq <= 256, Lk <= 256
+ * (tdb_mha_tc_supported); other shapes use the CUDA-core kernels above.  The caller averages p / pdrop over heads (tdb_head_mean).
+ * Attention dropout comes from the library's counter-based stream instead of a mask tensor: drop_seed (device int64, NULL = no
+ * dropout), drop_site, drop_p select the same keep bits tdb_dropout_mask(seed, site, p) would write at the flat [B][H][Lq][Lk]
+ * index; the backward regenerates them.  p = probabilities before dropout, pdrop (optional) after.
+ * tdb_mha_set_tc(level) / env TDB_MHA_TC: 0 = CUDA-core kernels, 1 = tcgen05 forward only, 2 = forward + backward (default). */
 int tdb_mha_tc_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm,
-                   void* o, int64_t ldo, float* p, const uint8_t* keep, float* pdrop, float keep_scale, int B, int H, int Lq,
-                   int Lk, float scale, void* stream);
-/* backward on the same scheme: dPd = dO V^T, dQ = dS K, dK = dS^T Q, dV = Pd^T dO all on tcgen05 (the bf16 dS / Pd tiles in shared
- * memory serve as K-major AND MN-major A operands); same arguments as tdb_mha_bwd without the scratch buffers.  Drafted at the end of
- * round 1, NOT yet run on hardware: reachable only through tdb_mha_set_tc(2) / TDB_MHA_TC=2. */
+                   void* o, int64_t ldo, float* p, float* pdrop, const int64_t* drop_seed, int64_t drop_site, float drop_p,
+                   int B, int H, int Lq, int Lk, float scale, void* stream);
+/* backward: dPd = dO V^T, dQ = dS K, dK = dS^T Q, dV = Pd^T dO on tcgen05 (the bf16 dS / Pd tiles in shared memory serve as
+ * K-major AND MN-major A operands; dK / dV accumulate in TMEM over the query tiles).  dpbar [B][Lq][Lk] = gradient of the
+ * head-averaged post-dropout probabilities (guided-attention loss) or NULL.  No scratch buffers. */
 int tdb_mha_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout,
-                   int64_t lddo, const float* p, const uint8_t* keep, float keep_scale, const float* dpbar, void* dq,
-                   int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk, float scale,
-                   void* stream);
+                   int64_t lddo, const float* p, const int64_t* drop_seed, int64_t drop_site, float drop_p, const float* dpbar,
+                   void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk,
+                   float scale, void* stream);
 int tdb_mha_tc_supported(int H, int Lq, int Lk);
 /* pbar[b][i][j] = mean over heads of p[b][h][i][j] (the weights nn.MultiheadAttention returns) */
 int tdb_head_mean(const float* p, float* pbar, int B, int H, int Lq, int Lk, void* stream);

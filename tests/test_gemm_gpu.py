@@ -216,3 +216,34 @@ def test_gemm_2cta_wgrad_forms(splits):
     dw = torch.empty(C, C, 3, 3, dtype=torch.float32, device="cuda")
     splitk_reduce(part, s, C, 9 * C, dw, taps=9)
     _close(dw, w.grad, tol=5e-3)
+
+
+@pytest.mark.parametrize("M,N,K,relu,f32", [(3525, 512, 256, False, False), (3525, 256, 256, False, True), (3525, 2048, 256, True, False),
+                                             (3525, 256, 2048, False, True), (100, 256, 256, False, False), (100, 2048, 256, True, False),
+                                             (15125, 256, 2048, False, True), (12100, 256, 256, False, False), (20, 256, 768, False, True)])
+def test_gemm_split_precision_weights_two_taps(M, N, K, relu, f32):
+    """the transformer's forward form (ops.gemm_fwd_w): fp32 weights as bf16 [hi | lo] read through two reduction taps over the same
+    activation tile.  Against fp32 matmul with the UNROUNDED weights the error must be far below what bf16 weights give."""
+    from tubedetr_b200 import kernels as Kn
+    from tubedetr_b200.gemm import gemm
+    g = torch.Generator().manual_seed(31)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda() * 0.1
+    Ws = Kn.split_bf16(W, torch.empty(N, 2 * K, dtype=torch.bfloat16, device="cuda"))
+    assert torch.equal(Ws[:, :K], W.to(torch.bfloat16))
+    assert (Ws[:, :K].float() + Ws[:, K:].float() - W).abs().max().item() <= 2 ** -16 * W.abs().max().item()
+    out = torch.full((M, N), float("nan"), dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
+    gemm(A, Ws, out, M, N, K, ntaps=2, a_off0=(0, 0), b_off0=(0, K), bias=bias, relu=relu)
+    one = torch.empty_like(out)
+    gemm(A, Ws[:, :K], one, M, N, K, bias=bias, relu=relu)        # plain bf16 weights
+    torch.cuda.synchronize()
+    ref = A.float() @ W.t() + bias
+    if relu:
+        ref = ref.relu()
+    if f32:
+        e2, e1 = (out - ref).abs().max().item(), (one - ref).abs().max().item()
+        assert e2 <= 2e-5 * ref.abs().max().item() + 1e-5, (e2, e1)       # fp32-grade: only accumulation-order noise is left
+        assert e2 < 0.1 * e1
+    else:
+        _close(out, ref, 6e-3)                                              # bf16 output rounding only

@@ -89,6 +89,34 @@ def fwd_nograd():
 
 
 rows.append(("forward + loss under no_grad (nothing saved)", timed_graph(fwd_nograd)))
+
+
+def enc_nograd():
+    with torch.no_grad():
+        model(st.samples, [bench.T_FRAMES], st.caps, encode_and_save=True, samples_fast=st.fast)
+
+
+def encdec_nograd():
+    with torch.no_grad():
+        mc = model(st.samples, [bench.T_FRAMES], st.caps, encode_and_save=True, samples_fast=st.fast)
+        model(st.samples, [bench.T_FRAMES], st.caps, encode_and_save=False, memory_cache=mc)
+
+
+rows.append(("  encode phase only under no_grad (backbone + text + encoder + fast branch)", timed_graph(enc_nograd)))
+rows.append(("  encode + decode phases under no_grad (no criterion)", timed_graph(encdec_nograd)))
+
+
+def step_trivial_loss():
+    for p in st.fgb.params:
+        p.grad = None
+    mc = model(st.samples, [bench.T_FRAMES], st.caps, encode_and_save=True, samples_fast=st.fast)
+    out = model(st.samples, [bench.T_FRAMES], st.caps, encode_and_save=False, memory_cache=mc)
+    tot = torch.cat([out["pred_boxes"].flatten(), out["pred_sted"].flatten()] + [a["pred_boxes"].flatten() for a in out["aux_outputs"]]
+                    + [a["pred_sted"].flatten() for a in out["aux_outputs"]]).square().sum()
+    tot.backward()
+
+
+rows.append(("full step with a 3-kernel stand-in loss instead of SetCriterion (criterion fwd+bwd = bench - this)", timed_graph(step_trivial_loss)))
 W = model._engine.prepare(model._backbone_tensors())
 fr_s, fr_f = st.samples.tensors.float(), st.fast.tensors.float()
 

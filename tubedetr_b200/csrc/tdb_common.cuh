@@ -107,6 +107,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM, same lane / column mapping as tmem_ld_32x32
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ UMMA descriptors (see DESIGN.md "descriptor cheat sheet")
 // Shared-memory matrix descriptor, 128-byte swizzle.  Both operand flavours use 8-row x 128-byte swizzle atoms (1024 B):
@@ -219,6 +232,29 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ------------------------------------------------------------------ counter-based dropout stream (shared by every fused dropout)
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t keep4(unsigned long long r, uint32_t thr) {   // four 16-bit lanes -> four 0/1 bytes
+  uint32_t o = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) o |= (uint32_t)(((uint32_t)(r >> (16 * t)) & 0xFFFFu) >= thr) << (8 * t);
+  return o;
+}
+// per-element view of the same stream: element e uses 16-bit lane (e & 3) of hash number (e >> 2) -- identical to what
+// dropout_mask_kernel writes at keep[e], so a fused consumer and an explicit mask of the same (seed, site) agree bit for bit
+__device__ __forceinline__ unsigned long long drop_base(const long long* seed, unsigned long long site) {
+  return splitmix64((unsigned long long)seed[0] * 0xD1342543DE82EF95ull + site);
+}
+__device__ __forceinline__ bool drop_keep(unsigned long long base, long long e, uint32_t thr) {
+  const unsigned long long r = splitmix64(base + (unsigned long long)(e >> 2));
+  return (((uint32_t)(r >> (16 * (e & 3)))) & 0xFFFFu) >= thr;
 }
 
 }  // namespace tdb

@@ -230,26 +230,23 @@ __global__ void cast_add_bf16_kernel(const float* __restrict__ x, const float* _
   reinterpret_cast<uint2*>(y)[idx] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
-__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-__device__ __forceinline__ uint32_t keep4(unsigned long long r, uint32_t thr) {   // four 16-bit lanes -> four 0/1 bytes
-  uint32_t o = 0;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) o |= (uint32_t)(((uint32_t)(r >> (16 * t)) & 0xFFFFu) >= thr) << (8 * t);
-  return o;
-}
-// per-element view of the same stream: element e uses 16-bit lane (e & 3) of hash number (e >> 2) -- identical to what
-// dropout_mask_kernel writes at keep[e], so a fused consumer and an explicit mask of the same (seed, site) agree bit for bit
-__device__ __forceinline__ unsigned long long drop_base(const long long* seed, unsigned long long site) {
-  return splitmix64((unsigned long long)seed[0] * 0xD1342543DE82EF95ull + site);
-}
-__device__ __forceinline__ bool drop_keep(unsigned long long base, long long e, uint32_t thr) {
-  const unsigned long long r = splitmix64(base + (unsigned long long)(e >> 2));
-  return (((uint32_t)(r >> (16 * (e & 3)))) & 0xFFFFu) >= thr;
+// fp32 [rows][K] -> bf16 [rows][2K] = [hi | lo] with hi = bf16(x), lo = bf16(x - hi): hi + lo carries ~16 mantissa bits.
+// Used for the WEIGHTS of the transformer's forward GEMMs (tdb_gemm with two taps: A x hi + A x lo): weight rounding is a
+// systematic perturbation shared by every token and frame (it does not average out like activation rounding) and was measured to be
+// 3x the activation-rounding share of the bf16 path's output error.
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n4, int K4) {
+  pdl_wait();
+  pdl_trigger();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n4) return;
+  const long long r = idx / K4;
+  const int c4 = (int)(idx - r * K4);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x) + idx);
+  const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
+  const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
+  uint2* row = reinterpret_cast<uint2*>(y + r * (long long)(8 * K4));
+  row[c4] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  row[K4 + c4] = make_uint2(pack_bf16x2(v.x - h0, v.y - h1), pack_bf16x2(v.z - h2, v.w - h3));
 }
 
 // ------------------------------------------------------------------ LayerNorm over d=256 with fused residual add.  One warp per row.
@@ -604,6 +601,13 @@ extern "C" int tdb_prep_weight(const float* w, void* out, void* out_scaled, cons
 extern "C" int tdb_cast_add_bf16(const float* x, const float* add, void* y, int64_t n, void* stream_) {
   TDB_REQUIRE(x && y && n % 4 == 0, "tdb_cast_add_bf16: n must be a multiple of 4");
   TDB_CHECK_CUDA(tdb_launch(cast_add_bf16_kernel, dim3(nblocks(n / 4, 256)), dim3(256), 0, STREAM, x, add, (bf16*)y, n / 4));
+  LAUNCH_OK();
+}
+extern "C" int tdb_split_bf16(const float* x, void* y, int64_t rows, int K, void* stream_) {
+  TDB_REQUIRE(x && y && rows > 0 && K > 0 && K % 4 == 0, "tdb_split_bf16: K must be a multiple of 4");
+  TDB_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "tdb_split_bf16: buffers must be 16-byte aligned");
+  const long long n4 = rows * (K / 4);
+  TDB_CHECK_CUDA(tdb_launch(split_bf16_kernel, dim3(nblocks(n4, 256)), dim3(256), 0, STREAM, x, (bf16*)y, n4, K / 4));
   LAUNCH_OK();
 }
 extern "C" int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta, const float* pos,

@@ -43,6 +43,13 @@ def cast_add_bf16(x, add, y):
     check(lib().tdb_cast_add_bf16(ptr(x), ptr(add), ptr(y), _i64(x.numel()), stream_ptr()), "cast_add_bf16")
 
 
+def split_bf16(x, y):
+    """x fp32 [rows, K] -> y bf16 [rows, 2K] = [hi | lo]"""
+    rows, Kd = x.shape
+    check(lib().tdb_split_bf16(ptr(x), ptr(y), _i64(rows), Kd, stream_ptr()), "split_bf16")
+    return y
+
+
 def layernorm_fwd(x, r, gamma, beta, pos, y, y_bf, ypos_bf, mean, rstd, rows, D, eps, drop=None):
     """drop = (seed tensor, site, p): residual dropout on r inside the kernel (no mask tensor)"""
     seed, site, p = drop if drop is not None else (None, 0, 0.0)
@@ -69,35 +76,43 @@ def colsum_bf16(x, out, accumulate=False):
     return out
 
 
-def mha_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=None, pdrop=None, keep_scale=1.0):
-    """q,k,v: 2-D bf16 views [B*L, >=H*32] (row stride = .stride(0)); kpm uint8 [B,Lk] or None.
+def mha_uses_tc(H, Lq, Lk, level=1):
+    """tcgen05 self-attention (tdb_attn_tc.cu) is the default for every shape it supports (even H, 2 <= Lq <= 256, Lk <= 256);
+    tdb_mha_set_tc(0|1|2) / env TDB_MHA_TC select CUDA cores | tcgen05 forward | tcgen05 forward + backward (default 2)"""
+    return lib().tdb_mha_tc_enabled() >= level and bool(lib().tdb_mha_tc_supported(H, Lq, Lk))
+
+
+def mha_fwd_cuda_core(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=None, pdrop=None, keep_scale=1.0):
+    """the CUDA-core row kernel (tdb_attn.cu): one-query sequences and sequences longer than 256.
+    q,k,v: 2-D bf16 views [B*L, >=H*32] (row stride = .stride(0)); kpm uint8 [B,Lk] or None.
     keep (uint8 [B,H,Lq,Lk]) + pdrop enable attention-probability dropout."""
-    if lib().tdb_mha_tc_enabled() and lib().tdb_mha_tc_supported(H, Lq, Lk):     # opt-in tcgen05 path (tdb_attn_tc.cu)
-        return mha_tc_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pdrop, keep_scale=keep_scale)
     check(lib().tdb_mha_fwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(kpm),
                             ptr(o), _i64(o.stride(0)), ptr(p), ptr(pbar), ptr(keep), ptr(pdrop), _f(keep_scale),
                             B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_fwd")
 
 
-def mha_tc_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=None, pdrop=None, keep_scale=1.0):
-    """same contract as mha_fwd with QK^T and PV on tcgen05 (S / O accumulators in TMEM); pbar = head mean of p (or pdrop)"""
+def mha_tc_fwd(q, k, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, drop=None, pdrop=None):
+    """QK^T and PV on tcgen05 (S / O accumulators in TMEM).  drop = (seed tensor, site, p): attention dropout from the hash
+    stream inside the kernel (no mask tensor); pbar = head mean of p (of pdrop under dropout)"""
+    seed, site, dp = drop if drop is not None else (None, 0, 0.0)
     check(lib().tdb_mha_tc_fwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(kpm),
-                               ptr(o), _i64(o.stride(0)), ptr(p), ptr(keep), ptr(pdrop), _f(keep_scale),
+                               ptr(o), _i64(o.stride(0)), ptr(p), ptr(pdrop), ptr(seed), _i64(site), _f(dp),
                                B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_tc_fwd")
     if pbar is not None:
-        check(lib().tdb_head_mean(ptr(pdrop if keep is not None else p), ptr(pbar), B, H, Lq, Lk, stream_ptr()), "head_mean")
+        assert drop is None or pdrop is not None
+        check(lib().tdb_head_mean(ptr(pdrop if drop is not None else p), ptr(pbar), B, H, Lq, Lk, stream_ptr()), "head_mean")
 
 
-def mha_tc_bwd(q, k, v, dout, p, dpbar, dq, dk, dv, B, H, Lq, Lk, scale, keep=None, keep_scale=1.0):
+def mha_tc_bwd(q, k, v, dout, p, dpbar, dq, dk, dv, B, H, Lq, Lk, scale, drop=None):
+    seed, site, dp = drop if drop is not None else (None, 0, 0.0)
     check(lib().tdb_mha_tc_bwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)),
-                               ptr(dout), _i64(dout.stride(0)), ptr(p), ptr(keep), _f(keep_scale), ptr(dpbar),
+                               ptr(dout), _i64(dout.stride(0)), ptr(p), ptr(seed), _i64(site), _f(dp), ptr(dpbar),
                                ptr(dq), _i64(dq.stride(0)), ptr(dk), _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)),
                                B, H, Lq, Lk, _f(scale), stream_ptr()), "mha_tc_bwd")
 
 
-def mha_bwd(q, k, v, dout, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, keep=None, keep_scale=1.0, pd_scratch=None):
-    if lib().tdb_mha_tc_enabled() >= 2 and lib().tdb_mha_tc_supported(H, Lq, Lk):
-        return mha_tc_bwd(q, k, v, dout, p, dpbar, dq, dk, dv, B, H, Lq, Lk, scale, keep=keep, keep_scale=keep_scale)
+def mha_bwd_cuda_core(q, k, v, dout, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, keep=None, keep_scale=1.0, pd_scratch=None):
+    """ds / pd_scratch: fp32 [B,H,Lq,Lk] scratch"""
     check(lib().tdb_mha_bwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)),
                             ptr(dout), _i64(dout.stride(0)), ptr(p), ptr(keep), _f(keep_scale), ptr(pd_scratch), ptr(dpbar),
                             ptr(ds), ptr(dq), _i64(dq.stride(0)), ptr(dk), _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)),

@@ -90,6 +90,44 @@ def bf16_weight(w):
     return ent[1]
 
 
+# ---- split-precision weights for the forward GEMMs -------------------------------------------------------------------------
+# Weight rounding is the dominant error of a bf16 transformer forward against the fp32 reference: it is a fixed perturbation of
+# the network shared by every token and frame, whereas activation rounding is independent noise that averages out (measured with
+# the CPU oracle at cfg-5: bf16 weights alone -> pred_sted error 0.017, bf16 activations alone -> 0.006).  The forward GEMMs
+# therefore read W as bf16 hi + bf16 lo ([N][2K] = [hi | lo], ~16 mantissa bits) through two reduction taps over the SAME
+# activation tile: y = x W_hi^T + x W_lo^T.  Twice the tensor-core work on GEMMs that are launch- or HBM-bound anyway; backward
+# (dgrad) keeps the plain bf16 copy.  TDB_WSPLIT=0 restores one-tap bf16 weights.
+WSPLIT = _os.environ.get("TDB_WSPLIT", "1") != "0"
+_WSCACHE = {}
+
+
+def bf16_weight_split(w):
+    """[N][2K] bf16 = [hi | lo] copy of an fp32 parameter [N][K], refreshed when the parameter changes"""
+    key = (w.data_ptr(), tuple(w.shape))
+    ck = (w._version,)
+    root = _root(w)
+    ent = _WSCACHE.get(key)
+    if ent is None or ent[0] != ck or ent[2]() is not root:
+        N, Kd = w.shape
+        wb = ent[1] if (ent is not None and ent[2]() is root) else torch.empty(N, 2 * Kd, dtype=torch.bfloat16, device=w.device)
+        K.split_bf16(w.detach().contiguous(), wb)
+        ent = (ck, wb, weakref.ref(root))
+        _WSCACHE[key] = ent
+        if len(_WSCACHE) > 4096:
+            for k_ in [k_ for k_, e in _WSCACHE.items() if e[2]() is None]:
+                del _WSCACHE[k_]
+    return ent[1]
+
+
+def gemm_fwd_w(x, W, y, R, N, Kd, rows=None, **kw):
+    """y = x @ W[rows]^T (+ epilogue): forward GEMM against an fp32 parameter, split-precision weights by default"""
+    lo, hi = rows if rows is not None else (0, W.shape[0])
+    if WSPLIT and Kd % 64 == 0:
+        Ws = bf16_weight_split(W)
+        return gemm(x, Ws[lo:hi], y, R, N, Kd, ntaps=2, a_off0=(0, 0), b_off0=(0, Kd), **kw)
+    return gemm(x, bf16_weight(W)[lo:hi], y, R, N, Kd, **kw)
+
+
 def adopt_bf16_weight(w, wb):
     """register an up-to-date bf16 copy of `w` produced elsewhere (optim.FusedAdamWEMA writes it in the optimizer kernel),
     so the next forward does not launch a cast kernel for it"""
@@ -156,11 +194,10 @@ class LinearFn(torch.autograd.Function):
         # dx_scale: constant factor on dx in the same epilogue (1 / (1 - p) when x went through HiddenDropoutFn).
         ctx.mask_dx, ctx.masked_by_consumer, ctx.dx_scale = mask_dx, masked_by_consumer, float(dx_scale)
         assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
-        Wb = bf16_weight(W)
         R, Kd = x.shape
         N = W.shape[0]
         y = torch.empty(R, N, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
-        gemm(x, Wb, y, R, N, Kd, bias=b, relu=relu)
+        gemm_fwd_w(x, W, y, R, N, Kd, bias=b, relu=relu)
         ctx.relu = relu
         ctx.save_for_backward(x, W, y if relu else None)
         return y
@@ -236,11 +273,10 @@ class InProjFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, W, b, segs, *xs):
-        Wb = bf16_weight(W)
         outs = []
         for (lo, hi), x in zip(segs, xs):
             y = torch.empty(x.shape[0], hi - lo, dtype=torch.bfloat16, device=x.device)
-            gemm(x, Wb[lo:hi], y, x.shape[0], hi - lo, x.shape[1], bias=b[lo:hi])
+            gemm_fwd_w(x, W, y, x.shape[0], hi - lo, x.shape[1], rows=(lo, hi), bias=b[lo:hi])
             outs.append(y)
         ctx.segs = segs
         ctx.save_for_backward(W, *xs)
@@ -278,10 +314,19 @@ def in_proj(W, b, segs, *xs):
     return InProjFn.apply(W, b, tuple(segs), *xs)
 
 
+def _check_drop_gen(device, gen):
+    """fused dropouts re-hash their keep bits from the DEVICE seed, which the next training forward bumps in place"""
+    if _drop_state(device)[2] != gen:
+        raise RuntimeError("tubedetr_b200: the dropout seed advanced between this forward and its backward (a second training "
+                           "forward ran first); run backward before the next forward (one forward per backward, INTEGRATION.md)")
+
+
 class MHAFn(torch.autograd.Function):
     """Attention core on projected q/k/v (bf16 [B*L, 256]); returns (o bf16 [B*Lq,256], pbar fp32 [B,Lq,Lk]).
     packed: q and k are the two halves of one [R,512] tensor (self-attention).  drop_p > 0 applies torch's
-    attention-probability dropout (mask drawn with torch.rand, applied inside the kernel; pbar averages the dropped P)."""
+    attention-probability dropout inside the kernel (pbar averages the dropped P): on the tcgen05 path the keep bits come from the
+    counter-based hash stream (no mask tensor, the backward regenerates them); the CUDA-core path takes an explicit mask drawn
+    from the same stream."""
 
     @staticmethod
     def forward(ctx, q, k, v, kpm, B, H, Lq, Lk, scale, packed, drop_p, need_weights=True):
@@ -294,12 +339,22 @@ class MHAFn(torch.autograd.Function):
         # the encoder never reads its attention weights (reference transformer.py:638-640 discards them): no head-mean launch and,
         # under dropout, no second probability tensor
         pbar = torch.empty(B, Lq, Lk, dtype=torch.float32, device=q.device) if need_weights else None
-        keep = pdrop = None
+        keep = drop = None
+        tc = K.mha_uses_tc(H, Lq, Lk, 1)
         if drop_p > 0:
-            keep = dropout_keep((B, H, Lq, Lk), drop_p, q.device)
-            pdrop = torch.empty_like(p) if need_weights else None
-        K.mha_fwd(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pdrop, keep_scale=1.0 / (1.0 - drop_p))
+            st = _drop_state(q.device)
+            st[1] += 1
+            drop = (st[0], st[1], float(drop_p))
+            ctx.drop_gen = st[2]
+        pdrop = torch.empty_like(p) if (drop is not None and need_weights) else None
+        if tc:
+            K.mha_tc_fwd(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, drop=drop, pdrop=pdrop)
+        else:
+            if drop is not None:
+                keep = K.dropout_mask(torch.empty((B, H, Lq, Lk), dtype=torch.uint8, device=q.device), *drop)
+            K.mha_fwd_cuda_core(qv, kv, v, kpm, o, p, pbar, B, H, Lq, Lk, scale, keep=keep, pdrop=pdrop, keep_scale=1.0 / (1.0 - drop_p))
         ctx.cfg = (B, H, Lq, Lk, scale, packed, drop_p)
+        ctx.drop = drop
         ctx.save_for_backward(q, k if not packed else None, v, p, keep)
         if pbar is None:
             pbar = p.new_empty(0)
@@ -317,15 +372,23 @@ class MHAFn(torch.autograd.Function):
             dpbar = None
         if dpbar is not None:
             dpbar = dpbar.contiguous().float()
-        ds = torch.empty_like(p)
+        if ctx.drop is not None:
+            _check_drop_gen(q.device, ctx.drop_gen)
         dv = torch.empty_like(v)
-        kw = dict(keep=keep, keep_scale=1.0 / (1.0 - drop_p), pd_scratch=torch.empty_like(p) if keep is not None else None)
         if packed:
             dqk = torch.empty_like(q)
-            K.mha_bwd(q[:, :256], q[:, 256:], v, do, p, dpbar, ds, dqk[:, :256], dqk[:, 256:], dv, B, H, Lq, Lk, scale, **kw)
+            qv, kv, dq, dk = q[:, :256], q[:, 256:], dqk[:, :256], dqk[:, 256:]
+        else:
+            qv, kv, dq, dk = q, k, torch.empty_like(q), torch.empty_like(k)
+        if K.mha_uses_tc(H, Lq, Lk, 2):     # tcgen05 backward keeps dS / dropped P in shared memory: no fp32 scratch tensors
+            K.mha_tc_bwd(qv, kv, v, do, p, dpbar, dq, dk, dv, B, H, Lq, Lk, scale, drop=ctx.drop)
+        else:
+            if ctx.drop is not None and keep is None:       # forward ran on tcgen05 with hash dropout: materialise the same bits
+                keep = K.dropout_mask(torch.empty((B, H, Lq, Lk), dtype=torch.uint8, device=q.device), *ctx.drop)
+            K.mha_bwd_cuda_core(qv, kv, v, do, p, dpbar, torch.empty_like(p), dq, dk, dv, B, H, Lq, Lk, scale, keep=keep,
+                                keep_scale=1.0 / (1.0 - drop_p), pd_scratch=torch.empty_like(p) if keep is not None else None)
+        if packed:
             return (dqk, None, dv) + (None,) * 9
-        dq, dk = torch.empty_like(q), torch.empty_like(k)
-        K.mha_bwd(q, k, v, do, p, dpbar, ds, dq, dk, dv, B, H, Lq, Lk, scale, **kw)
         return (dq, dk, dv) + (None,) * 9
 
 
@@ -430,10 +493,8 @@ class AddLayerNormFn(torch.autograd.Function):
         rows, D = x.shape
         if dy is None and dyb is None and dypb is None:
             return None, None, None, None, None, None, None
-        if ctx.drop is not None and _drop_state(x.device)[2] != ctx.drop_gen:
-            # the keep bits are re-hashed from the DEVICE seed, which the next training forward bumps in place
-            raise RuntimeError("tubedetr_b200: the dropout seed advanced between this forward and its backward (a second training "
-                               "forward ran first); run backward before the next forward (one forward per backward, INTEGRATION.md)")
+        if ctx.drop is not None:
+            _check_drop_gen(x.device, ctx.drop_gen)
         dy = dy.contiguous() if dy is not None else None
         dyb = dyb.contiguous() if dyb is not None else None
         dypb = dypb.contiguous() if dypb is not None else None
@@ -497,6 +558,7 @@ class BackboneFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, frames, engine, W, names, tag, *params):
         feat, h, w, bctx = engine.forward(frames, W, save=True, tag=tag)
+        feat = feat[:]          # a fresh tensor object per call: the engine hands out the SAME cached buffer view every time
         ctx.engine, ctx.W, ctx.names, ctx.bctx = engine, W, names, bctx
         ctx.save_for_backward(feat, *params)
         ctx.hw = (h, w)
