@@ -163,7 +163,8 @@ def build_everything(device, seed=0):
     # RoBERTa stays the library call it is in the reference; let its fp32 GEMMs use TF32 tensor cores (bf16 autocast would
     # re-cast ~200 weight tensors every step: ~500 extra tiny kernels for a 20-token sequence)
     torch.backends.cuda.matmul.allow_tf32 = True
-    model.fast_l2_chunk = int(os.environ.get("TDB_L2_CHUNK", "0")) or None
+    model.fast_l2_chunk = int(os.environ.get("TDB_L2_CHUNK", "0")) or None     # experiment switches, defaults are the measured best
+    model.joint_backbone = os.environ.get("TDB_JOINT", "1") != "0"
     torch.backends.cudnn.allow_tf32 = True
     return model.to(device).train(), crit, wd     # a real training step: every dropout of the reference is active
 

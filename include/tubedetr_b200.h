@@ -90,7 +90,13 @@ int tdb_splitk_reduce(const float* part, int splits, int M, int N, const float* 
 /* ResNet stem (reference models/backbone.py:98 -> torchvision conv1 7x7/2/p3): fp32 NCHW frames -> bf16 im2col rows
  * [N*Ho*Wo][192] (147 real columns, order c*49+kh*7+kw); the conv itself + FrozenBN + ReLU is one tdb_gemm */
 int tdb_stem_im2col(const float* x, void* col, int N, int H, int W, void* stream);
-/* torchvision maxpool 3x3/2/p1 after the stem */
+/* The whole stem in ONE kernel (tdb_stem.cu): conv 7x7/2/p3 + FrozenBatchNorm2d + ReLU + maxpool 3x3/2/p1 (reference
+ * models/backbone.py:97-105 -> torchvision conv1 / bn1 / relu / maxpool) from fp32 NCHW frames to bf16 NHWC rows [N*H2*W2][64]:
+ * input patch and implicit-im2col A tiles in shared memory, tcgen05.mma into TMEM, pooled epilogue; only the frames and the pooled
+ * output touch HBM.  wk = conv1 weight as bf16 [64][192] in K order (c, kh, kw padded to 8), zero at kw = 7 and beyond k = 168. */
+int tdb_stem_fused(const float* x, const void* wk, const float* scale, const float* shift, void* out, int N, int H, int W,
+                   void* stream);
+/* torchvision maxpool 3x3/2/p1 after the stem (unfused path) */
 int tdb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream);
 /* stride-2 3x3 convs (first block of layer2/3/4, torchvision v1.5): explicit im2col [N*Ho*Wo][9*C] (tap major) ... */
 int tdb_im2col3x3s2(const void* x, void* col, int N, int H, int W, int C, void* stream);

@@ -42,6 +42,44 @@ def test_stem_im2col_and_maxpool():
     assert torch.equal(z.permute(0, 3, 1, 2).float(), refp)
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 96, 96), (1, 352, 352), (3, 64, 128), (1, 75, 101), (2, 224, 224), (1, 37, 33)])
+def test_stem_fused_matches_torch_and_unfused(N, H, W):
+    """conv 7x7/2 + FrozenBN + ReLU + maxpool 3x3/2 in ONE kernel (tdb_stem.cu: implicit im2col in shared memory, tcgen05, pooled
+    epilogue) vs fp32 torch on the same bf16-rounded inputs / weights, and vs the unfused im2col + GEMM + maxpool kernels"""
+    from tubedetr_b200 import kernels as K
+    from tubedetr_b200.gemm import gemm
+    x = _r((N, 3, H, W), 11, torch.float32)
+    w = _r((64, 3, 7, 7), 12, torch.float32) * 0.1
+    scale = torch.rand(64, device="cuda") + 0.5
+    shift = torch.randn(64, device="cuda") * 0.2
+    H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    H2, W2 = (H1 - 1) // 2 + 1, (W1 - 1) // 2 + 1
+    wk = torch.zeros(64, 192, dtype=torch.bfloat16, device="cuda")
+    wk[:, :168] = F.pad(w, (0, 1)).reshape(64, 168).to(torch.bfloat16)
+    out = torch.full((N * H2 * W2, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    K.stem_fused(x, wk, scale, shift, out, N, H, W)
+    torch.cuda.synchronize()
+    conv = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3)
+    act = F.relu(conv * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).bfloat16().float()      # the conv output is bf16 before the pool
+    ref = F.max_pool2d(act, 3, 2, 1)
+    got = out.view(N, H2, W2, 64).permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()
+    _close(got, ref, 1e-2)
+    assert (got - ref).abs().mean().item() <= 1e-3 * ref.abs().mean().item()
+    # unfused kernels: same math, different accumulation order -> equal up to one bf16 rounding of single elements
+    col = torch.empty(N * H1 * W1, 192, dtype=torch.bfloat16, device="cuda")
+    K.stem_im2col(x, col, N, H, W)
+    wk0 = torch.empty(64, 192, dtype=torch.bfloat16, device="cuda")
+    K.prep_weight(w, wk0, None, None, 64, 3, 49, 192)
+    y = torch.empty(N * H1 * W1, 64, dtype=torch.bfloat16, device="cuda")
+    gemm(col, wk0, y, N * H1 * W1, 64, 192, scale=scale, bias=shift, relu=True)
+    z = torch.empty(N * H2 * W2, 64, dtype=torch.bfloat16, device="cuda")
+    K.maxpool3x3s2(y, z, N, H1, W1, 64)
+    torch.cuda.synchronize()
+    _close(out, z, 1e-2)
+    assert (out.float() != z.float()).float().mean().item() < 0.02
+
+
 @pytest.mark.parametrize("H,W", [(22, 22), (11, 13)])
 def test_stride2_conv_paths(H, W):
     from tubedetr_b200 import kernels as K

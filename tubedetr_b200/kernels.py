@@ -14,6 +14,10 @@ def stem_im2col(x, col, N, H, W):
     check(lib().tdb_stem_im2col(ptr(x), ptr(col), N, H, W, stream_ptr()), "stem_im2col")
 
 
+def stem_fused(x, wk, scale, shift, out, N, H, W):
+    check(lib().tdb_stem_fused(ptr(x), ptr(wk), ptr(scale), ptr(shift), ptr(out), N, H, W, stream_ptr()), "stem_fused")
+
+
 def maxpool3x3s2(x, y, N, H, W, Cc):
     check(lib().tdb_maxpool3x3s2(ptr(x), ptr(y), N, H, W, Cc, stream_ptr()), "maxpool")
 

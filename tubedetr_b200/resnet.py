@@ -22,6 +22,10 @@ BN_EPS = 1e-5
 
 
 WGRAD_LAG = max(1, min(2, int(os.environ.get("TDB_WGRAD_LAG", "1"))))
+# experiment switch: cap the persistent grids of the backbone BACKWARD GEMMs so that the text encoder's tiny backward kernels (side
+# stream, concurrent with the backbone backward) find idle SMs instead of delaying a GEMM CTA that needs a whole SM (0 = no cap)
+BWD_MAX_CTAS = int(os.environ.get("TDB_BB_BWD_MAX_CTAS", "0"))
+STEM_FUSED = os.environ.get("TDB_STEM_FUSED", "1") != "0"    # one kernel for conv1 + FrozenBN + ReLU + maxpool (tdb_stem.cu)
 
 
 def conv_out(h, k, s, p):
@@ -115,6 +119,16 @@ class ResNet101Engine:
                 ent = (ck, wb, ws)
                 self._wcache[conv] = ent
             W[conv] = (ent[1], ent[2], self._bn[conv][0], self._bn[conv][1])
+        # fused stem: conv1 weight in K order (c, kh, kw padded to 8) -- frozen, so a handful of torch ops once per weight version
+        w1 = sd[prefix + "conv1.weight"]
+        ck = (w1.data_ptr(), w1._version)
+        ent = self._wcache.get("conv1:fused")
+        if ent is None or ent[0] != ck:
+            wk = torch.zeros(64, 192, dtype=torch.bfloat16, device=w1.device)
+            wk[:, :168] = torch.nn.functional.pad(w1.detach().float(), (0, 1)).reshape(64, 168).to(torch.bfloat16)
+            ent = (ck, wk)
+            self._wcache["conv1:fused"] = ent
+        W["conv1:fused"] = ent[1]
         return W
 
     # ------------------------------------------------------------------ forward
@@ -154,6 +168,15 @@ class ResNet101Engine:
         H1, W1 = conv_out(H, 7, 2, 3), conv_out(Wd, 7, 2, 3)
         H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
         wb, _, sc, sh = W["conv1"]
+        if STEM_FUSED:
+            x = self.buf(tag + ":pool", (N * H2 * W2, 64))
+            base = 0
+            for frames in srcs:
+                assert frames.shape[2:] == (H, Wd), "frames of one backbone batch must share their spatial size"
+                n = frames.shape[0]
+                K.stem_fused(frames, W["conv1:fused"], sc, sh, x[base * H2 * W2:(base + n) * H2 * W2], n, H, Wd)
+                base += n
+            return x, H2, W2
         stem = self.buf(tag + ":stem", (N * H1 * W1, 64))
         chunk = max(1, min(N, (1 << 28) // (H1 * W1 * 192 * 2)))
         col = self.buf(tag + ":stemcol", (chunk * H1 * W1, 192))
@@ -256,7 +279,7 @@ class ResNet101Engine:
         s = effective_splits(Kred, want)
         part = torch.empty(s, M, ntot, dtype=torch.float32, device=g.device)
         gemm(g, xin, part, M, Ncols, Kred, a_major=1, b_major=1, nz=nz, z_b_off1=z_b_off1,
-             z_out_col=[t * Ncols for t in range(9)] if nz else None, splits=want)
+             z_out_col=[t * Ncols for t in range(9)] if nz else None, splits=want, max_ctas=BWD_MAX_CTAS)
         splitk_reduce(part, s, M, ntot, out, rowscale=rowscale, taps=9 if (nz or taps == 9) else 1)
 
     def backward(self, ctx, W, g_out, grads, prefix="backbone.0.body."):
@@ -293,20 +316,20 @@ class ResNet101Engine:
                 wp = w + 2
                 taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
                 g2 = self.buf(f"{tag}:g2p{par}", (Rp, width), zero=True)
-                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=REMAP_C2P, img_hw=(h, w))
+                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=REMAP_C2P, img_hw=(h, w), max_ctas=BWD_MAX_CTAS)
                 # ---- conv2 (implicit 3x3 over the haloed grid)
                 with sc:
                     self._wgrad(g2, y1, width, width, Rp, s2, grads[prefix + name + "conv2.weight"], z_b_off1=taps)
                 g1 = self.buf(f"{tag}:g1{par}", (R, width))
                 gemm(g2, w2s, g1, Rp, width, width, b_major=1, ntaps=9, a_off1=[-t for t in taps],
-                     b_off0=[t * width for t in range(9)], mask=y1, remap=REMAP_P2C, img_hw=(h, w))
+                     b_off0=[t * width for t in range(9)], mask=y1, remap=REMAP_P2C, img_hw=(h, w), max_ctas=BWD_MAX_CTAS)
             else:
                 g2 = self.buf(f"{tag}:g2c{par}", (Ro, width))
-                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2)
+                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, max_ctas=BWD_MAX_CTAS)
                 with sc:
                     self._wgrad(g2, r["col"], width, 9 * width, Ro, s2, grads[prefix + name + "conv2.weight"], taps=9)
                 dcol = self.buf(f"{tag}:dcol{par}", (Ro, 9 * width))
-                gemm(g2, w2s, dcol, Ro, 9 * width, width, b_major=1)
+                gemm(g2, w2s, dcol, Ro, 9 * width, width, b_major=1, max_ctas=BWD_MAX_CTAS)
                 g1 = self.buf(f"{tag}:g1{par}", (R, width))
                 K.col2im3x3s2_mask(dcol, y1, g1, N, h, w, width)
             # ---- conv1
@@ -319,7 +342,7 @@ class ResNet101Engine:
                     self._wgrad(g_out, r["xs"], cout, cin, Ro, sdn, grads[prefix + name + "downsample.0.weight"])
                 if not last:
                     dxs = self.buf(f"{tag}:dxs{par}", (Ro, cin))
-                    gemm(g_out, wds, dxs, Ro, cin, cout, b_major=1)
+                    gemm(g_out, wds, dxs, Ro, cin, cout, b_major=1, max_ctas=BWD_MAX_CTAS)
                     resid = dxs
                     if r["stride"] == 2:
                         resid = self.buf(f"{tag}:dxsu{par}", (R, cin))
@@ -327,7 +350,7 @@ class ResNet101Engine:
             if last:
                 break
             gprev = self.buf(f"{tag}:gout{i % 3}", (R, cin))
-            gemm(g1, w1s, gprev, R, cin, width, b_major=1, residual=resid, mask=x)
+            gemm(g1, w1s, gprev, R, cin, width, b_major=1, residual=resid, mask=x, max_ctas=BWD_MAX_CTAS)
             g_out = gprev
             pending.append(sc.mark())
         sc.join()
