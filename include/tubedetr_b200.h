@@ -223,6 +223,17 @@ int tdb_dropout_bf16(const void* x, void* y, int64_t n, const int64_t* seed, int
  *   Outputs dq [F][256], dk, dv [F*S][256] bf16.  One streaming pass over V and one over K per frame; deterministic. */
 int tdb_xattn_bwd(const void* q, const void* k, const void* v, const void* dout, const float* p, const uint8_t* keep,
                   float keep_scale, const float* dpbar, void* dq, void* dk, void* dv, int F, int S, float scale, void* stream);
+/* The same attention core on projected keys / values with ROW STRIDES (elements): the decoder's default path projects K and V of
+ * ALL decoder layers with two tdb_gemm launches over the layer-invariant memory (reference models/transformer.py:567-579: every
+ * layer receives the same memory / pos) into [F*S][layers*256] buffers; layer l reads / writes its 256-column slice.
+ * tdb_xattn_core_fwd: o [F][256] bf16 context, p [F][8][S] fp32 probabilities (before dropout), pbar [F][S] head mean (after
+ * dropout) or NULL.  tdb_xattn_core_bwd: tdb_xattn_bwd with strides. */
+int tdb_xattn_core_fwd(const void* q, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm,
+                       const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar, int F, int S, float scale,
+                       void* stream);
+int tdb_xattn_core_bwd(const void* q, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout, const float* p,
+                       const uint8_t* keep, float keep_scale, const float* dpbar, void* dq, void* dk, int64_t lddk, void* dv,
+                       int64_t lddv, int F, int S, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimizer-side step on FLAT fp32 buffers (parameters, gradients, Adam moments, EMA copy share one element order).
@@ -246,6 +257,30 @@ int tdb_grad_sqnorm(const float* grad, int64_t n, void* workspace, int64_t ws_by
 int tdb_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_bf16,
                        int64_t n, const tdb_optim_group* groups, int ngroups, float beta1, float beta2, float eps,
                        int64_t step, const float* grad_norm, float max_norm, float ema_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SetCriterion in two launches (reference models/tubedetr.py:270-372, 437-458; util/box_ops.py:65-115):
+ * L1 + GIoU on the kept boxes, KL of the start / end distributions, guided-attention loss, for the main output and the auxiliary
+ * decoder layers at once.  All tensors fp32, contiguous, per-layer pointers (NULL = that loss family is off).
+ *   tdb_criterion_fwd  losses [4][nlayers] = {loss_bbox, loss_giou, loss_sted, loss_guided_attn} x layer
+ *   tdb_criterion_bwd  grad_losses [4][nlayers] (upstream gradient of every scalar) -> d_boxes [nlayers][K][4],
+ *                      d_sted [nlayers][B][T][2], d_weights [nlayers][B][T][T]
+ * ------------------------------------------------------------------------------------------------ */
+#define TDB_LOSS_MAX_LAYERS 8
+typedef struct tdb_loss_desc {
+  int32_t nlayers, K, B, T;
+  const float* pred_boxes[TDB_LOSS_MAX_LAYERS];  /* [K][4] cxcywh, already keep-indexed (engine.py:98-102) */
+  const float* pred_sted[TDB_LOSS_MAX_LAYERS];   /* [B][T][2] start / end logits */
+  const float* weights[TDB_LOSS_MAX_LAYERS];     /* [B][T][T] head-averaged temporal self-attention */
+  const float* tgt_boxes;                        /* [K][4] */
+  const float* num_boxes;                        /* device scalar (already clamped / averaged over ranks) */
+  const float* gauss;                            /* [B][T][2] target distributions (tubedetr.py:318-331) */
+  const uint8_t* time_mask;                      /* [B][T] 1 = valid frame */
+  const uint8_t* neg;                            /* [B][T] 1 = row excluded from the guided-attention loss (inside the moment / padding) */
+  const float* nneg;                             /* [B] number of contributing rows + 1e-6 */
+} tdb_loss_desc;
+int tdb_criterion_fwd(const tdb_loss_desc* d, float* losses, void* stream);
+int tdb_criterion_bwd(const tdb_loss_desc* d, const float* grad_losses, float* d_boxes, float* d_sted, float* d_weights, void* stream);
 
 #ifdef __cplusplus
 }

@@ -327,6 +327,53 @@ def test_xattn_bwd_streaming_kernel(F, S, drop):
     assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)
 
 
+@pytest.mark.parametrize("F,S,drop,layer", [(100, 141, 0.0, 4), (7, 59, 0.1, 0), (3, 20, 0.1, 2), (400, 141, 0.0, 5), (50, 69, 0.0, 1)])
+def test_xattn_core_strided_fwd_bwd(F, S, drop, layer):
+    """the decoder's default cross-attention core: one query per frame against the 256-column slice `layer` of [F*S, 6*256] key / value
+    buffers (row stride 1536), forward and backward (gradients written into the same slice of strided buffers) vs fp32 torch"""
+    from tubedetr_b200 import kernels as K
+    H, d, nl = 8, 256, 6
+    scale = 1 / math.sqrt(32)
+    q = _r((F, d), 160)
+    K_all, V_all = _r((F * S, nl * d), 161), _r((F * S, nl * d), 162)
+    sl = slice(layer * d, (layer + 1) * d)
+    kpm = torch.zeros(F, S, dtype=torch.uint8, device="cuda")
+    kpm[:, S - S // 5:] = 1
+    kpm[0] = 0
+    keep, ks = None, 1.0
+    if drop > 0:
+        keep = (torch.rand(F, H, 1, S, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6)) >= drop).to(torch.uint8)
+        ks = 1 / (1 - drop)
+    o = torch.full((F, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+    p = torch.full((F, H, 1, S), float("nan"), device="cuda")
+    pbar = torch.full((F, 1, S), float("nan"), device="cuda")
+    K.xattn_core_fwd(q, K_all[:, sl], V_all[:, sl], kpm, o, p, pbar, F, S, scale, keep=keep, keep_scale=ks)
+    qf = q.float().view(F, 1, d).requires_grad_(True)
+    kf = K_all[:, sl].float().reshape(F, S, d).requires_grad_(True)
+    vf = V_all[:, sl].float().reshape(F, S, d).requires_grad_(True)
+    qh = (qf * scale).view(F, 1, H, 32).transpose(1, 2)
+    kh, vh = kf.view(F, S, H, 32).transpose(1, 2), vf.view(F, S, H, 32).transpose(1, 2)
+    rp = (qh @ kh.transpose(-1, -2)).masked_fill(kpm[:, None, None, :].bool(), float("-inf")).softmax(-1)
+    rpd = rp * keep.float() * ks if keep is not None else rp
+    ro = (rpd @ vh).transpose(1, 2).reshape(F, d)
+    _close(p, rp, 1e-4)
+    _close(pbar, rpd.mean(1), 1e-4)
+    _close(o, ro, 1e-2)
+    do = _r((F, d), 163)
+    dpbar = _r((F, 1, S), 164, torch.float32)
+    (ro * do.float()).sum().add((rpd.mean(1) * dpbar).sum()).backward()
+    dq = torch.empty(F, d, dtype=torch.bfloat16, device="cuda")
+    dK_all, dV_all = torch.zeros_like(K_all), torch.zeros_like(V_all)
+    K.xattn_core_bwd(q, K_all[:, sl], V_all[:, sl], do, p, dpbar, dq, dK_all[:, sl], dV_all[:, sl], F, S, scale, keep=keep, keep_scale=ks)
+    for got, ref in ((dq, qf.grad.view(F, d)), (dK_all[:, sl].reshape(F, S, d), kf.grad), (dV_all[:, sl].reshape(F, S, d), vf.grad)):
+        _close(got, ref, 2e-2)
+        a = (got.float() * ref).sum() / (ref * ref).sum()
+        assert abs(a.item() - 1) < 5e-3, a.item()
+    other = torch.ones(nl * d, dtype=torch.bool, device="cuda")
+    other[sl] = False
+    assert (dK_all[:, other] == 0).all() and (dV_all[:, other] == 0).all()       # only the layer's slice is written
+
+
 @pytest.mark.parametrize("rows,N", [(3525, 2048), (14100, 256), (1000, 768), (20, 256), (37, 64)])
 def test_colsum_vector_path(rows, N):
     from tubedetr_b200 import kernels as K

@@ -181,6 +181,36 @@ def test_train_mode_applies_dropout_and_backpropagates():
     assert torch.equal(o3["pred_boxes"], out_eval["pred_boxes"])
 
 
+@pytest.mark.parametrize("name", ["cfg1b", "notsa"])
+def test_decoder_cross_attention_variants_agree(name):
+    """hoisted K/V projections (default) vs the per-layer fused tcgen05 kernel vs the unfused path: same outputs to bf16 noise, same
+    gradients for the cross-attention parameters and for the encoder (which receives the memory gradient of all six layers)"""
+    g = load_gold(name)
+    cfg = g["cfg"]
+    res = {}
+    model = _model(cfg)[0]
+    try:
+        for mode in ("hoist", "fused", "unfused"):
+            model.transformer.xattn_mode = mode
+            model.zero_grad(set_to_none=True)
+            _, _, _, _, mc, out = _run(cfg)
+            (out["pred_boxes"].float().square().sum() + out["pred_sted"].float().square().sum() + out["ca_weights"].square().sum()
+             if "ca_weights" in out else out["pred_boxes"].float().square().sum() + out["pred_sted"].float().square().sum()).backward()
+            res[mode] = (out["pred_boxes"].detach().clone(), out["pred_sted"].detach().clone(),
+                         {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None and "text_encoder" not in n})
+    finally:
+        model.transformer.xattn_mode = "hoist"
+    for mode in ("fused", "unfused"):
+        assert _err(res["hoist"][0], res[mode][0]) <= 5e-3 and _err(res["hoist"][1], res[mode][1]) <= 1e-2, mode
+        assert res["hoist"][2].keys() == res[mode][2].keys()
+        for n in ("transformer.decoder.layers.0.cross_attn_image.in_proj_weight", "transformer.decoder.layers.5.cross_attn_image.in_proj_bias",
+                  "transformer.decoder.layers.3.cross_attn_image.out_proj.weight", "transformer.encoder.layers.5.linear2.weight",
+                  "input_proj.weight"):
+            a, c = res["hoist"][2][n].float(), res[mode][2][n].float()
+            cos = (a * c).sum() / (a.norm() * c.norm() + 1e-20)
+            assert cos > 0.995 and abs(a.norm().item() / (c.norm().item() + 1e-20) - 1) < 0.03, (mode, n, cos.item(), a.norm().item(), c.norm().item())
+
+
 def test_l2_chunked_fast_pass_is_equivalent():
     """the L2-resident chunked schedule of stem+layer1+layer2 (no-grad pass) gives the same features as one big batch"""
     g = load_gold("cfg1")

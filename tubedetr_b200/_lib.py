@@ -31,6 +31,19 @@ class GemmDesc(C.Structure):
     ]
 
 
+LOSS_MAX_LAYERS = 8
+
+
+class LossDesc(C.Structure):
+    _fields_ = [
+        ("nlayers", C.c_int32), ("K", C.c_int32), ("B", C.c_int32), ("T", C.c_int32),
+        ("pred_boxes", C.c_void_p * LOSS_MAX_LAYERS), ("pred_sted", C.c_void_p * LOSS_MAX_LAYERS),
+        ("weights", C.c_void_p * LOSS_MAX_LAYERS),
+        ("tgt_boxes", C.c_void_p), ("num_boxes", C.c_void_p), ("gauss", C.c_void_p), ("time_mask", C.c_void_p),
+        ("neg", C.c_void_p), ("nneg", C.c_void_p),
+    ]
+
+
 _lib = None
 
 

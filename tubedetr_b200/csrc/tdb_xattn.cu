@@ -497,6 +497,7 @@ struct XattnBwdParams {
   bf16 *dq, *dk, *dv;
   int F, S;
   float scale;
+  long long ldk, ldv, lddk, lddv; // row strides (elements, multiples of 8) of k, v, dk, dv
 };
 
 __device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
@@ -536,10 +537,11 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
   unpack8(__ldg(reinterpret_cast<const uint4*>(a.dout + (long long)f * XD) + lane), dO);
   unpack8(__ldg(reinterpret_cast<const uint4*>(a.q + (long long)f * XD) + lane), qv);
   __syncthreads();
-  const uint4* vrow = reinterpret_cast<const uint4*>(a.v + (long long)f * S * XD) + lane;
-  const uint4* krow = reinterpret_cast<const uint4*>(a.k + (long long)f * S * XD) + lane;
-  uint4* dvrow = reinterpret_cast<uint4*>(a.dv + (long long)f * S * XD) + lane;
-  uint4* dkrow = reinterpret_cast<uint4*>(a.dk + (long long)f * S * XD) + lane;
+  const uint4* vrow = reinterpret_cast<const uint4*>(a.v + (long long)f * S * a.ldv) + lane;
+  const uint4* krow = reinterpret_cast<const uint4*>(a.k + (long long)f * S * a.ldk) + lane;
+  uint4* dvrow = reinterpret_cast<uint4*>(a.dv + (long long)f * S * a.lddv) + lane;
+  uint4* dkrow = reinterpret_cast<uint4*>(a.dk + (long long)f * S * a.lddk) + lane;
+  const long long sv8 = a.ldv / 8, sk8 = a.ldk / 8, sdv8 = a.lddv / 8, sdk8 = a.lddk / 8;
   const float* dpb = a.dpbar ? a.dpbar + (long long)f * S : nullptr;
   // ---- pass 1
   float rs = 0.f;
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = j0 + 8 * u;
-      raw[u] = j < S ? __ldg(vrow + (long long)j * (XD / 8)) : make_uint4(0, 0, 0, 0);
+      raw[u] = j < S ? __ldg(vrow + (long long)j * sv8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
         float o[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) o[t] = pdj * dO[t];
-        dvrow[(long long)j * (XD / 8)] = pack8(o);
+        dvrow[(long long)j * sdv8] = pack8(o);
       }
     }
   }
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = j0 + 8 * u;
-      raw[u] = j < S ? __ldg(krow + (long long)j * (XD / 8)) : make_uint4(0, 0, 0, 0);
+      raw[u] = j < S ? __ldg(krow + (long long)j * sk8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
           dqa[t] += ds * kk[t];
           o[t] = a.scale * ds * qv[t];
         }
-        dkrow[(long long)j * (XD / 8)] = pack8(o);
+        dkrow[(long long)j * sdk8] = pack8(o);
       }
     }
   }
@@ -622,31 +624,185 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Forward of the one-query-per-frame attention core on PROJECTED keys / values (the decoder's hoisted-K/V path: the K / V
+// projections of all decoder layers are two tdb_gemm launches over the layer-invariant memory, models/transformer.py:567-579,
+// 734-740).  One CTA per frame, same streaming scheme as the backward: a warp takes one 512-byte key row at a time (lane = 8
+// channels, 4 lanes = one head), scores by a 2-step butterfly, softmax by one warp per head, context by per-lane accumulation
+// over the value rows and a fixed-order cross-warp reduction.
+struct XattnCoreParams {
+  const bf16 *q, *k, *v;          // q [F][256] projected, unscaled; k, v rows [F*S] with strides ldk / ldv
+  const uint8_t* kpm;             // [F][S] nonzero = padded key, or null
+  const uint8_t* keep;            // [F][8][S] or null (attention dropout)
+  float keep_scale;
+  bf16* o;                        // [F][256]
+  float* p;                       // [F][8][S] probabilities before dropout
+  float* pbar;                    // [F][S] head mean of the post-dropout probabilities, or null
+  int F, S;
+  float scale;
+  long long ldk, ldv;
+};
+
+__global__ void __launch_bounds__(256) xattn_core_fwd_kernel(const XattnCoreParams a) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float xs[];
+  const int S = a.S;
+  float* sp = xs;                 // [8][S] scores, then P
+  float* spd = sp + 8 * S;        // [8][S] post-dropout P
+  float* so = spd + 8 * S;        // [8 warps][256]
+  const int f = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = lane >> 2;
+  float qv[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.q + (long long)f * XD) + lane), qv);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) qv[t] *= a.scale;
+  const uint4* krow = reinterpret_cast<const uint4*>(a.k + (long long)f * S * a.ldk) + lane;
+  const uint4* vrow = reinterpret_cast<const uint4*>(a.v + (long long)f * S * a.ldv) + lane;
+  const long long sk8 = a.ldk / 8, sv8 = a.ldv / 8;
+  const uint8_t* mk = a.kpm ? a.kpm + (long long)f * S : nullptr;
+  // ---- scores
+  for (int j0 = warp; j0 < S; j0 += 32) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      raw[u] = j < S ? __ldg(krow + (long long)j * sk8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      if (j < S) {
+        float kk[8];
+        unpack8(raw[u], kk);
+        float d = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) d += qv[t] * kk[t];
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        if ((lane & 3) == 0) sp[h * S + j] = (mk && mk[j]) ? -INFINITY : d;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- softmax: warp = head
+  {
+    float* row = sp + warp * S;
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) sum += (mx == -INFINITY) ? 0.f : __expf(row[j] - mx);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;          // all keys masked -> NaN, like the reference softmax
+    float* pg = a.p + ((long long)f * 8 + warp) * S;
+    const uint8_t* kg = a.keep ? a.keep + ((long long)f * 8 + warp) * S : nullptr;
+    for (int j = lane; j < S; j += 32) {
+      const float pv = ((mx == -INFINITY) ? 0.f : __expf(row[j] - mx)) * inv;
+      row[j] = pv;
+      pg[j] = pv;
+      spd[warp * S + j] = kg ? (kg[j] ? pv * a.keep_scale : 0.f) : pv;
+    }
+  }
+  __syncthreads();
+  if (a.pbar)
+    for (int j = threadIdx.x; j < S; j += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 8; ++hh) t += spd[hh * S + j];
+      a.pbar[(long long)f * S + j] = t * 0.125f;
+    }
+  // ---- context
+  float oa[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) oa[t] = 0.f;
+  for (int j0 = warp; j0 < S; j0 += 32) {
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      raw[u] = j < S ? __ldg(vrow + (long long)j * sv8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      if (j < S) {
+        float vv[8];
+        unpack8(raw[u], vv);
+        const float pdj = spd[h * S + j];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) oa[t] += pdj * vv[t];
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) so[warp * XD + lane * 8 + t] = oa[t];
+  __syncthreads();
+  {
+    const int c = threadIdx.x;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += so[w * XD + c];
+    a.o[(long long)f * XD + c] = __float2bfloat16(t);
+  }
+}
+
 }  // namespace tdb
 
 using namespace tdb;
 
-extern "C" int tdb_xattn_bwd(const void* q, const void* k, const void* v, const void* dout, const float* p, const uint8_t* keep,
-                             float keep_scale, const float* dpbar, void* dq, void* dk, void* dv, int F, int S, float scale,
-                             void* stream_) {
+extern "C" int tdb_xattn_core_fwd(const void* q, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm,
+                                  const uint8_t* keep, float keep_scale, void* o, float* p, float* pbar, int F, int S, float scale,
+                                  void* stream_) {
   int rc = tdb_init_once();
   if (rc) return rc;
-  TDB_REQUIRE(q && k && v && dout && p && dq && dk && dv && F > 0 && S > 0, "tdb_xattn_bwd: null argument");
+  TDB_REQUIRE(q && k && v && o && p && F > 0 && S > 0, "tdb_xattn_core_fwd: null argument");
+  TDB_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15) == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldk >= XD && ldv >= XD,
+              "tdb_xattn_core_fwd: bf16 buffers must be 16-byte aligned, row strides multiples of 8 and >= 256");
+  const size_t smem = sizeof(float) * ((size_t)16 * S + 8 * XD);
+  TDB_REQUIRE(smem <= 200 * 1024, "tdb_xattn_core_fwd: S=%d too long", S);
+  static bool attr = false;
+  if (!attr) {
+    TDB_CHECK_CUDA(cudaFuncSetAttribute(xattn_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  XattnCoreParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, kpm, keep, keep_scale, (bf16*)o, p, pbar, F, S, scale, (long long)ldk, (long long)ldv};
+  TDB_CHECK_CUDA(tdb_launch(xattn_core_fwd_kernel, dim3(F), dim3(256), smem, (cudaStream_t)stream_, a));
+  TDB_CHECK_CUDA(cudaGetLastError());
+  tdb_count_launch(1);
+  return TDB_OK;
+}
+
+extern "C" int tdb_xattn_core_bwd(const void* q, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout, const float* p,
+                                  const uint8_t* keep, float keep_scale, const float* dpbar, void* dq, void* dk, int64_t lddk, void* dv,
+                                  int64_t lddv, int F, int S, float scale, void* stream_) {
+  int rc = tdb_init_once();
+  if (rc) return rc;
+  TDB_REQUIRE(q && k && v && dout && p && dq && dk && dv && F > 0 && S > 0, "tdb_xattn_core_bwd: null argument");
   TDB_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) == 0,
-              "tdb_xattn_bwd: bf16 buffers must be 16-byte aligned");
+              "tdb_xattn_core_bwd: bf16 buffers must be 16-byte aligned");
+  TDB_REQUIRE(ldk % 8 == 0 && ldv % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0 && ldk >= XD && ldv >= XD && lddk >= XD && lddv >= XD,
+              "tdb_xattn_core_bwd: row strides must be multiples of 8 and >= 256");
   const size_t smem = sizeof(float) * ((size_t)24 * S + 64 + 8 * XD);
-  TDB_REQUIRE(smem <= 200 * 1024, "tdb_xattn_bwd: S=%d too long", S);
+  TDB_REQUIRE(smem <= 200 * 1024, "tdb_xattn_core_bwd: S=%d too long", S);
   static bool attr = false;
   if (!attr) {
     TDB_CHECK_CUDA(cudaFuncSetAttribute(xattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   XattnBwdParams a{(const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)dout, p, keep, keep_scale, dpbar,
-                   (bf16*)dq, (bf16*)dk, (bf16*)dv, F, S, scale};
+                   (bf16*)dq, (bf16*)dk, (bf16*)dv, F, S, scale, (long long)ldk, (long long)ldv, (long long)lddk, (long long)lddv};
   TDB_CHECK_CUDA(tdb_launch(xattn_bwd_kernel, dim3(F), dim3(256), smem, (cudaStream_t)stream_, a));
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   return TDB_OK;
+}
+
+extern "C" int tdb_xattn_bwd(const void* q, const void* k, const void* v, const void* dout, const float* p, const uint8_t* keep,
+                             float keep_scale, const float* dpbar, void* dq, void* dk, void* dv, int F, int S, float scale,
+                             void* stream_) {
+  return tdb_xattn_core_bwd(q, k, XD, v, XD, dout, p, keep, keep_scale, dpbar, dq, dk, XD, dv, XD, F, S, scale, stream_);
 }
 
 // measurement hook (tools/xattn_phase.py): when set, every fused forward launch writes 4 SM clock stamps per tile

@@ -137,6 +137,18 @@ def xattn_bwd(q, kp, vp, dout, p, dpbar, dq, dk, dv, F, S, scale, keep=None, kee
                               ptr(dv), F, S, _f(scale), stream_ptr()), "xattn_bwd")
 
 
+def xattn_core_fwd(q, k, v, kpm, o, p, pbar, F, S, scale, keep=None, keep_scale=1.0):
+    """one-query-per-frame attention on projected k, v (2-D bf16 views [F*S, 256] with any row stride); q [F,256]"""
+    check(lib().tdb_xattn_core_fwd(ptr(q), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(kpm), ptr(keep), _f(keep_scale),
+                                   ptr(o), ptr(p), ptr(pbar), F, S, _f(scale), stream_ptr()), "xattn_core_fwd")
+
+
+def xattn_core_bwd(q, k, v, dout, p, dpbar, dq, dk, dv, F, S, scale, keep=None, keep_scale=1.0):
+    check(lib().tdb_xattn_core_bwd(ptr(q), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(dout), ptr(p), ptr(keep),
+                                   _f(keep_scale), ptr(dpbar), ptr(dq), ptr(dk), _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)),
+                                   F, S, _f(scale), stream_ptr()), "xattn_core_bwd")
+
+
 def dropout_mask(keep, seed, site, p):
     check(lib().tdb_dropout_mask(ptr(keep), _i64(keep.numel()), ptr(seed), _i64(site), _f(p), stream_ptr()), "dropout_mask")
     return keep
@@ -145,3 +157,32 @@ def dropout_mask(keep, seed, site, p):
 def dropout_bf16(x, y, seed, site, p):
     check(lib().tdb_dropout_bf16(ptr(x), ptr(y), _i64(x.numel()), ptr(seed), _i64(site), _f(p), stream_ptr()), "dropout_bf16")
     return y
+
+
+def loss_desc(pbs, sts, ws, tgt_boxes, num_boxes, gauss, time_mask, neg, nneg, K_, B, T):
+    """tdb_loss_desc from per-layer tensor lists (None entries / lists = that loss family is off)"""
+    d = _lib.LossDesc()
+    nl = max(len(x) for x in (pbs or [], sts or [], ws or []))
+    d.nlayers, d.K, d.B, d.T = nl, int(K_), int(B), int(T)
+    for name, lst in (("pred_boxes", pbs), ("pred_sted", sts), ("weights", ws)):
+        arr = getattr(d, name)
+        for i in range(nl):
+            t = lst[i] if lst else None
+            if t is not None:
+                assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+            arr[i] = t.data_ptr() if t is not None else None
+    for name, t in (("tgt_boxes", tgt_boxes), ("num_boxes", num_boxes), ("gauss", gauss), ("time_mask", time_mask), ("neg", neg),
+                    ("nneg", nneg)):
+        if t is not None:
+            assert t.is_contiguous() and t.is_cuda
+            setattr(d, name, t.data_ptr())
+    return d
+
+
+def criterion_fwd(desc, losses):
+    check(lib().tdb_criterion_fwd(C.byref(desc), ptr(losses), stream_ptr()), "criterion_fwd")
+    return losses
+
+
+def criterion_bwd(desc, grad_losses, d_boxes, d_sted, d_weights):
+    check(lib().tdb_criterion_bwd(C.byref(desc), ptr(grad_losses), ptr(d_boxes), ptr(d_sted), ptr(d_weights), stream_ptr()), "criterion_bwd")

@@ -15,6 +15,7 @@ are rejected loudly in build().  In train() mode every dropout of the reference 
 attention kernel, residual / FFN / resizer / sted-head dropouts as torch ops); eval() is deterministic.
 """
 import math
+import os
 import zlib
 
 import torch
@@ -266,6 +267,10 @@ class Transformer(nn.Module):
         self.resizer = _Resizer()
         self.d_model, self.nhead, self.stride, self.no_tsa = D_MODEL, NHEAD, stride, no_tsa
         self.video_max_len = video_max_len
+        # decoder cross-attention: "hoist" (default) = K / V of ALL layers projected by two GEMMs over the layer-invariant memory,
+        # per-layer streaming attention core on their column slices; "fused" = per-layer tcgen05 kernel with the K/V projection fused
+        # in (K, V never reach HBM; S >= 43); "unfused" = per-layer projections + generic attention kernel
+        self.xattn_mode = os.environ.get("TDB_XATTN_MODE", "hoist")
         self.fused_xattn = True
 
     def _reset_temporal_parameters(self):  # called by reference main.py:545 after loading MDETR weights
@@ -299,7 +304,7 @@ class Transformer(nn.Module):
         return ops.add_layernorm(x32, f, l.norm2.weight, l.norm2.bias, drop_p=dp) + (None,)
 
     # ---- one decoder layer (reference transformer.py:684-751); rows are (b,t) batch-major
-    def _dec_layer(self, l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S):
+    def _dec_layer(self, l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S, kv=None, li=0):
         a, dp = l.self_attn, self._drop()
         if self.no_tsa:  # each time query attends to itself only (transformer.py:701-711)
             (v,) = ops.in_proj(a.in_proj_weight, a.in_proj_bias, ((512, 768),), xb)
@@ -313,7 +318,11 @@ class Transformer(nn.Module):
             att = ops.linear(o, a.out_proj.weight, a.out_proj.bias, out_fp32=True)
         x32, xb, xqb = ops.add_layernorm(x32, att, l.norm1.weight, l.norm1.bias, qp, drop_p=dp)
         c = l.cross_attn_image
-        if self.fused_xattn and S >= 43:                # K/V projection fused into the attention kernel (K, V never reach HBM)
+        if kv is not None:                              # K / V of all layers were projected once, outside the layer loop (default)
+            K_all, V_all, tok, shared, nl = kv
+            o, cw = ops.xattn_core(xqb, K_all, V_all, tok if li == 0 else None, c.in_proj_weight, c.in_proj_bias, kpm_mem, shared, li,
+                                   nl, B * T, S, 32 ** -0.5, drop_p=dp)
+        elif self.fused_xattn and S >= 43:              # K/V projection fused into the attention kernel (K, V never reach HBM)
             (q,) = ops.in_proj(c.in_proj_weight, c.in_proj_bias, ((0, 256),), xqb)
             o, cw = ops.xattn_fused(q, mempb, memb, c.in_proj_weight, c.in_proj_bias, kpm_mem, B * T, S, 32 ** -0.5, drop_p=dp)
         else:
@@ -595,8 +604,13 @@ class TubeDETR(nn.Module):
         xb, xqb = x32.to(torch.bfloat16), qp.to(torch.bfloat16)
         dn = tr.decoder.norm
         hs, ws, cws = [], [], []
-        for l in tr.decoder.layers:
-            x32, xb, xqb, w, cw = tr._dec_layer(l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S)
+        kv = None
+        if tr.xattn_mode == "hoist":
+            ca = [l.cross_attn_image for l in tr.decoder.layers]
+            kv = ops.decoder_kv(mempb, memb, [c.in_proj_weight for c in ca], [c.in_proj_bias for c in ca]) + (len(ca),)
+        tr.fused_xattn = tr.xattn_mode != "unfused"
+        for li, l in enumerate(tr.decoder.layers):
+            x32, xb, xqb, w, cw = tr._dec_layer(l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S, kv=kv, li=li)
             hs.append(ops.add_layernorm(x32, None, dn.weight, dn.bias)[0])
             ws.append(w)
             cws.append(cw)

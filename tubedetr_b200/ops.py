@@ -455,6 +455,153 @@ def xattn_fused(q, mempb, memb, W, b, kpm, F, S, scale, drop_p=0.0):
     return XAttnFusedFn.apply(q, mempb, memb, W, b, kpm, F, S, scale, float(drop_p))
 
 
+# ---- decoder cross-attention with the K / V projections of ALL layers hoisted out of the layer loop -------------------------------
+# Every decoder layer projects the SAME memory (reference models/transformer.py:567-579 passes memory / pos unchanged to each layer;
+# :734-740 key = memory + pos, value = memory), so K and V of all layers are two GEMMs [F*S, 256] x [layers*256, 256]^T instead of
+# 2 x layers launches on 111-tile grids, and they are SAVED: the backward needs no re-projection, the data gradients of the six
+# layers reach `memory` through two GEMMs with a layers*256-deep reduction (instead of 12 GEMMs + 10 accumulation passes over
+# 7 MB tensors), and each layer's attention core reads / writes its 256-column slice of the [F*S, layers*256] buffers in place.
+class DecKVShared:
+    """per-forward state shared by DecoderKVFn and the per-layer XAttnCoreFn nodes (gradient buffers written slice by slice)"""
+
+    def __init__(self):
+        self.dK = self.dV = self.dW = self.db = self.db_kv = None
+
+
+_DECKV_CACHE = {}
+
+
+def _deckv_weights(Ws, bs):
+    """split-precision [layers*256][512] copies of the key / value rows of the layers' in_proj_weight + concatenated biases"""
+    key = tuple(w.data_ptr() for w in Ws)
+    ck = tuple(w._version for w in Ws) + tuple(b._version for b in bs)
+    ent = _DECKV_CACHE.get(key)
+    if ent is None or ent[0] != ck or any(r() is not _root(w) for r, w in zip(ent[2], Ws)):
+        nl, d = len(Ws), Ws[0].shape[1]
+        if ent is not None and ent[1][0].shape[0] == nl * d:
+            Wk, Wv = ent[1][0], ent[1][1]
+        else:
+            Wk = torch.empty(nl * d, 2 * d, dtype=torch.bfloat16, device=Ws[0].device)
+            Wv = torch.empty_like(Wk)
+        for l, w in enumerate(Ws):
+            wd = w.detach()
+            K.split_bf16(wd[d:2 * d], Wk[l * d:(l + 1) * d])
+            K.split_bf16(wd[2 * d:], Wv[l * d:(l + 1) * d])
+        bk = torch.cat([b.detach()[d:2 * d] for b in bs]).contiguous()
+        bv = torch.cat([b.detach()[2 * d:] for b in bs]).contiguous()
+        ent = (ck, (Wk, Wv, bk, bv), [weakref.ref(_root(w)) for w in Ws])
+        _DECKV_CACHE.clear()
+        _DECKV_CACHE[key] = ent
+    return ent[1]
+
+
+class DecoderKVFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mempb, memb, shared, nl, *wb):
+        Ws, bs = wb[:nl], wb[nl:]
+        Wk, Wv, bk, bv = _deckv_weights(Ws, bs)
+        R, d = mempb.shape
+        K_all = torch.empty(R, nl * d, dtype=torch.bfloat16, device=mempb.device)
+        V_all = torch.empty_like(K_all)
+        gemm(mempb, Wk, K_all, R, nl * d, d, ntaps=2, a_off0=(0, 0), b_off0=(0, d), bias=bk)
+        gemm(memb, Wv, V_all, R, nl * d, d, ntaps=2, a_off0=(0, 0), b_off0=(0, d), bias=bv)
+        tok = torch.empty(1, dtype=torch.float32, device=mempb.device)     # gradient token: orders this node's backward after the layers'
+        ctx.shared, ctx.nl = shared, nl
+        ctx.wk, ctx.wv = Wk, Wv              # cache-owned bf16 copies: valid until the weights change, i.e. beyond this step's backward
+        ctx.save_for_backward(mempb, memb)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(K_all, V_all)
+        return K_all, V_all, tok
+
+    @staticmethod
+    def backward(ctx, _gk, _gv, _gtok):
+        mempb, memb = ctx.saved_tensors
+        sh, nl = ctx.shared, ctx.nl
+        if sh.dK is None:
+            return (None,) * (4 + 2 * nl)
+        Wk, Wv = ctx.wk, ctx.wv
+        R, d = mempb.shape
+        sc = wgrad_scope(mempb.device)
+        with sc:
+            for l in range(nl):
+                wgrad_into(sh.dK[:, l * d:(l + 1) * d], mempb, sh.dW[l][d:2 * d])
+                wgrad_into(sh.dV[:, l * d:(l + 1) * d], memb, sh.dW[l][2 * d:])
+            K.colsum_bf16(sh.dK, sh.db_kv[0])
+            K.colsum_bf16(sh.dV, sh.db_kv[1])
+        dmp = dmb = None
+        if ctx.needs_input_grad[0]:
+            dmp = torch.empty_like(mempb)
+            gemm(sh.dK, Wk[:, :d], dmp, R, d, nl * d, b_major=1)
+        if ctx.needs_input_grad[1]:
+            dmb = torch.empty_like(memb)
+            gemm(sh.dV, Wv[:, :d], dmb, R, d, nl * d, b_major=1)
+        sc.join()
+        for l in range(nl):                                           # tiny strided copies: bias gradients of the k / v rows
+            sh.db[l][d:2 * d].copy_(sh.db_kv[0][l * d:(l + 1) * d])
+            sh.db[l][2 * d:].copy_(sh.db_kv[1][l * d:(l + 1) * d])
+        return (dmp, dmb, None, None) + tuple(sh.dW[l] for l in range(nl)) + tuple(sh.db[l] for l in range(nl))
+
+
+def decoder_kv(mempb, memb, Ws, bs):
+    """-> (K_all, V_all [F*S, layers*256] bf16, token, shared)"""
+    shared = DecKVShared()
+    K_all, V_all, tok = DecoderKVFn.apply(mempb, memb, shared, len(Ws), *Ws, *bs)
+    return K_all, V_all, tok, shared
+
+
+class XAttnCoreFn(torch.autograd.Function):
+    """One decoder layer's time-aligned cross-attention on the hoisted K / V: q-projection (rows 0:256 of in_proj) + the one-query
+    attention core.  W / b receive their gradients from DecoderKVFn (one gradient tensor per parameter, filled by both nodes)."""
+
+    @staticmethod
+    def forward(ctx, xq, K_all, V_all, tok, W, b, kpm, shared, layer, nl, F, S, scale, drop_p):
+        d = xq.shape[1]
+        q = torch.empty(F, d, dtype=torch.bfloat16, device=xq.device)
+        gemm_fwd_w(xq, W, q, F, d, d, rows=(0, d), bias=b[:d])
+        o = torch.empty(F, d, dtype=torch.bfloat16, device=xq.device)
+        p = torch.empty(F, 8, 1, S, dtype=torch.float32, device=xq.device)
+        pbar = torch.empty(F, 1, S, dtype=torch.float32, device=xq.device)
+        keep = dropout_keep((F, 8, 1, S), drop_p, xq.device) if drop_p > 0 else None
+        Kl, Vl = K_all[:, layer * d:(layer + 1) * d], V_all[:, layer * d:(layer + 1) * d]
+        K.xattn_core_fwd(q, Kl, Vl, kpm, o, p, pbar, F, S, scale, keep=keep, keep_scale=1.0 / (1.0 - drop_p))
+        ctx.cfg = (shared, layer, nl, F, S, scale, drop_p, tok is not None)
+        ctx.save_for_backward(xq, q, K_all, V_all, W, p, keep)
+        return o, pbar
+
+    @staticmethod
+    def backward(ctx, do, dpbar):
+        xq, q, K_all, V_all, W, p, keep = ctx.saved_tensors
+        sh, layer, nl, F, S, scale, drop_p, has_tok = ctx.cfg
+        d = xq.shape[1]
+        dev = xq.device
+        if sh.dK is None:            # first layer to run its backward (the last decoder layer) allocates the shared gradient buffers
+            sh.dK, sh.dV = torch.empty_like(K_all), torch.empty_like(V_all)
+            sh.dW = torch.empty(nl, 3 * d, d, dtype=torch.float32, device=dev)
+            sh.db = torch.empty(nl, 3 * d, dtype=torch.float32, device=dev)
+            sh.db_kv = torch.empty(2, nl * d, dtype=torch.float32, device=dev)
+        if do is None:
+            do = torch.zeros(F, d, dtype=torch.bfloat16, device=dev)
+        do = _as_bf16(do).contiguous()
+        dpbar = dpbar.contiguous().float() if dpbar is not None else None
+        dq = torch.empty_like(q)
+        sl = slice(layer * d, (layer + 1) * d)
+        K.xattn_core_bwd(q, K_all[:, sl], V_all[:, sl], do, p, dpbar, dq, sh.dK[:, sl], sh.dV[:, sl], F, S, scale, keep=keep,
+                         keep_scale=1.0 / (1.0 - drop_p))
+        sc = wgrad_scope(dev)
+        with sc:
+            wgrad_into(dq, xq, sh.dW[layer][:d])
+            K.colsum_bf16(dq, sh.db[layer][:d])
+        dxq = torch.empty_like(xq)
+        gemm(dq, bf16_weight(W)[:d], dxq, F, d, d, b_major=1)
+        sc.join()
+        gtok = dq.new_empty(1, dtype=torch.float32) if has_tok else None
+        return (dxq, None, None, gtok) + (None,) * 10
+
+
+def xattn_core(xq, K_all, V_all, tok, W, b, kpm, shared, layer, nl, F, S, scale, drop_p=0.0):
+    return XAttnCoreFn.apply(xq, K_all, V_all, tok, W, b, kpm, shared, layer, nl, F, S, scale, float(drop_p))
+
+
 class AddLayerNormFn(torch.autograd.Function):
     """y = LayerNorm(x + dropout_p(r)) over d=256 (fp32 statistics).  Returns (y fp32, y bf16, (y + pos) bf16 or None).
     drop_p > 0: the residual dropout of the reference (`src + self.dropoutN(src2)`, transformer.py:641-645, 721-750) runs inside
