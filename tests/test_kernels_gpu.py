@@ -615,3 +615,50 @@ def test_mha_tc_backward_matches_fp32_autograd(B, Lq, Lk, drop):
         _close(got, ref, 2e-2)
         a = (got.float() * ref).sum() / (ref * ref).sum()      # no systematic scaling of the gradient
         assert abs(a.item() - 1) < 5e-3, a.item()
+
+
+@pytest.mark.parametrize("losses", [["boxes", "sted", "guided_attn"], ["boxes", "sted"]])
+def test_fused_criterion_matches_torch_criterion(losses):
+    """tdb_loss.cu (one forward kernel for all loss terms of all decoder layers, one backward kernel for all input gradients) vs the
+    torch expressions of SetCriterion (pinned to the reference's own loss values on CPU, tests/test_boundary_cpu.py) on random
+    ragged batches: values, and gradients under random per-term weights (a weight of exactly 0 / an unused term included)"""
+    from tubedetr_b200.model import SetCriterion
+    g = torch.Generator().manual_seed(23)
+    fused, plain = SetCriterion(losses, sigma=1), SetCriterion(losses, sigma=1)
+    fused.fused, plain.fused = True, False
+    for trial in range(3):
+        B, T = (3, 12 + trial) if trial < 2 else (1, 100)
+        durs = [T, T - 3, T - 5][:B]
+        time_mask = torch.zeros(B, T, dtype=torch.bool)
+        for b, d in enumerate(durs):
+            time_mask[b, :d] = True
+        inter = [[1, 4], [2, durs[1] - 2 if B > 1 else 3], [0, 0]][:B] if trial < 2 else [[T // 4, 3 * T // 4]]
+        keep = torch.tensor([b * T + t for b, (s, e) in enumerate(inter) for t in range(s, e + 1)]).cuda()
+        K_ = keep.numel()
+        tb = torch.cat([torch.rand(K_, 2, generator=g) * 0.5 + 0.25, torch.rand(K_, 2, generator=g) * 0.3 + 0.1], 1).cuda()
+
+        def layer():
+            w = torch.rand(B, T, T, generator=g).softmax(-1)
+            pb = torch.cat([torch.rand(B * T, 2, generator=g) * 0.5 + 0.25, torch.rand(B * T, 2, generator=g) * 0.3 + 0.1], 1)
+            return {"pred_boxes": pb.cuda().requires_grad_(True), "pred_sted": torch.randn(B, T, 2, generator=g).cuda().requires_grad_(True),
+                    "weights": w.cuda().requires_grad_(True)}
+        layers = [layer() for _ in range(6)]
+        layers[2]["pred_boxes"].data[keep[0]] = tb[0]          # an exact hit: |x|' = 0, IoU = 1
+        out = dict(layers[0], aux_outputs=layers[1:])
+        o = dict(out, pred_boxes=out["pred_boxes"][keep], aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][keep]) for a in out["aux_outputs"]])
+        tg = [{"boxes": tb[i:i + 1]} for i in range(K_)]
+        got = fused(o, tg, inter, time_mask.cuda())
+        ref = plain(o, tg, inter, time_mask.cuda())
+        assert set(got) == set(ref) and len(got) == (4 if "guided_attn" in losses else 3) * 6
+        for k_ in ref:
+            torch.testing.assert_close(got[k_], ref[k_], atol=2e-5, rtol=2e-5, msg=k_)
+        wts = {k_: float(torch.rand((), generator=g) * 3) for k_ in ref}
+        wts["loss_giou_1"] = 0.0
+        drop = "loss_sted_3"
+        leaves = [t for l in layers for n_, t in l.items() if n_ != "weights" or "guided_attn" in losses]
+        ga = torch.autograd.grad(sum(got[k_] * wts[k_] for k_ in got if k_ != drop), leaves, allow_unused=True)
+        gb = torch.autograd.grad(sum(ref[k_] * wts[k_] for k_ in ref if k_ != drop), leaves, allow_unused=True)
+        for a, c, t in zip(ga, gb, leaves):
+            a = torch.zeros_like(t) if a is None else a
+            c = torch.zeros_like(t) if c is None else c
+            torch.testing.assert_close(a, c, atol=2e-5 * (c.abs().max().item() + 1e-6) + 1e-7, rtol=1e-4)

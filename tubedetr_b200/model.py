@@ -659,6 +659,7 @@ class SetCriterion(nn.Module):
     def __init__(self, losses, sigma=1):
         super().__init__()
         self.losses, self.sigma = losses, sigma
+        self.fused = os.environ.get("TDB_FUSED_CRITERION", "1") != "0"    # CUDA inputs: two kernels instead of ~150 (tdb_loss.cu)
 
     def prepare(self, targets, inter_idx=None, time_mask=None, device=None):
         """Host-side part of the loss (target tensors, Gaussian start/end distributions, negative-frame map, the
@@ -686,6 +687,8 @@ class SetCriterion(nn.Module):
                 g = (-((tt[None] - tgt[:, None]) ** 2) / (2 * self.sigma ** 2)).exp()
                 gs.append(F.normalize(g + 1e-6, p=1, dim=1).to(dev))
             prep["gauss"] = gs
+            prep["gauss_bt2"] = torch.stack(gs, -1).contiguous()
+            prep["nneg"] = prep["nneg"].float().contiguous()
         return prep
 
     def forward(self, outputs, targets, inter_idx=None, time_mask=None):
@@ -694,8 +697,29 @@ class SetCriterion(nn.Module):
         # term is ONE batched expression (6x fewer kernels than the reference's per-layer Python loop, same values)
         layers = [outputs] + list(outputs.get("aux_outputs", []))
         names = [""] + [f"_{i}" for i in range(len(layers) - 1)]
+        if self.fused and outputs["pred_boxes"].is_cuda and len(layers) <= 8:
+            return self._fused(layers, names, prep, time_mask)
         vals = self._all(layers, prep, time_mask)
         return {k + sfx: v[i] for k, v in vals.items() for i, sfx in enumerate(names)}
+
+    def _fused(self, layers, names, prep, time_mask):
+        """all loss terms of all decoder layers in ONE kernel (tdb_loss.cu), their gradients in one more"""
+        fams = [f for f in ("boxes", "sted", "guided_attn") if f in self.losses]
+        f32 = lambda t: t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+        pbs = [f32(o["pred_boxes"]) for o in layers] if "boxes" in fams else None
+        sts = [f32(o["pred_sted"]) for o in layers] if "sted" in fams else None
+        ws = [f32(o["weights"]) for o in layers] if "guided_attn" in fams else None
+        tm = time_mask.contiguous().view(torch.uint8) if time_mask is not None else None
+        neg = prep["neg"].contiguous().view(torch.uint8) if "neg" in prep else None
+        flat = CriterionFn.apply(self, prep, tm, neg, len(layers), *(pbs or []), *(sts or []), *(ws or []))
+        nl = len(layers)
+        out = {}
+        for fi, key in enumerate(("loss_bbox", "loss_giou", "loss_sted", "loss_guided_attn")):
+            fam = ("boxes", "boxes", "sted", "guided_attn")[fi]
+            if fam in fams:
+                for i, sfx in enumerate(names):
+                    out[key + sfx] = flat[fi * nl + i]
+        return out
 
     def _all(self, layers, prep, time_mask):
         l, eps = {}, 1e-6
@@ -719,6 +743,54 @@ class SetCriterion(nn.Module):
             ga = ga.masked_fill(prep["neg"][None, :, :, None], 0)
             l["loss_guided_attn"] = (ga.sum(3) / prep["nneg"][None, :, None]).sum(2).mean(1)
         return l
+
+
+class CriterionFn(torch.autograd.Function):
+    """SetCriterion on the fused kernels: forward -> 4 * nlayers scalars (bbox, giou, sted, guided x layer) as separate 0-dim
+    outputs, backward -> gradients of every pred_boxes / pred_sted / weights tensor in one launch."""
+
+    @staticmethod
+    def forward(ctx, crit, prep, tm, neg, nl, *tensors):
+        from . import kernels as K
+        fams = [f for f in ("boxes", "sted", "guided_attn") if f in crit.losses]
+        it = iter(range(0, len(tensors), nl))
+        pbs = list(tensors[next(it):][:nl]) if "boxes" in fams else None
+        sts = list(tensors[next(it):][:nl]) if "sted" in fams else None
+        ws = list(tensors[next(it):][:nl]) if "guided_attn" in fams else None
+        B, T = (sts[0].shape[0], sts[0].shape[1]) if sts else ((ws[0].shape[0], ws[0].shape[1]) if ws else (1, 1))
+        Kb = pbs[0].shape[0] if pbs else 0
+        desc = K.loss_desc(pbs, sts, ws, prep["tgt_boxes"].float().contiguous() if pbs else None, prep["num_boxes"].reshape(1).float().contiguous(),
+                           prep.get("gauss_bt2"), tm, neg, prep.get("nneg"), Kb, B, T)
+        dev = tensors[0].device
+        losses = torch.zeros(4 * nl, dtype=torch.float32, device=dev) if len(fams) < 3 else torch.empty(4 * nl, dtype=torch.float32, device=dev)
+        K.criterion_fwd(desc, losses)
+        ctx.desc, ctx.keep = desc, (pbs, sts, ws, prep, tm, neg)      # keep = owners of the pointers in desc
+        ctx.dims = (nl, Kb, B, T)
+        return tuple(losses.unbind(0))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        from . import kernels as K
+        pbs, sts, ws, prep, tm, neg = ctx.keep
+        nl, Kb, B, T = ctx.dims
+        dev = (pbs or sts or ws)[0].device
+        zero = None
+        parts = []
+        for g in gs:
+            if g is None:
+                zero = torch.zeros((), dtype=torch.float32, device=dev) if zero is None else zero
+                g = zero
+            parts.append(g.reshape(()).float())
+        gl = torch.stack(parts)
+        d_boxes = torch.empty(nl, Kb, 4, dtype=torch.float32, device=dev) if pbs else None
+        d_sted = torch.empty(nl, B, T, 2, dtype=torch.float32, device=dev) if sts else None
+        d_w = torch.empty(nl, B, T, T, dtype=torch.float32, device=dev) if ws else None
+        K.criterion_bwd(ctx.desc, gl, d_boxes, d_sted, d_w)
+        grads = []
+        for d_, lst in ((d_boxes, pbs), (d_sted, sts), (d_w, ws)):
+            if lst:
+                grads += [d_[i] for i in range(nl)]
+        return (None, None, None, None, None) + tuple(grads)
 
 
 # ----------------------------------------------------------------------------- factory
