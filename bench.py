@@ -193,12 +193,19 @@ class Step:
         self.crit.static = self.crit.prepare(self.targets, self.inter_idx, self.time_mask)
         # flat gradient buffer: every .grad is a view into it => ONE all-reduce, static addresses for graph replay
         # (grouped text | transformer | backbone so the text slice can be reduced while the backbone backward still runs)
-        from tubedetr_b200.parallel import FlatGradBuffer, default_group_of
-        self.fgb = FlatGradBuffer(model.named_parameters(), device, groups=default_group_of)
+        from tubedetr_b200.parallel import FlatGradBuffer, default_group_of, default_subgroup_of
+        self.fgb = FlatGradBuffer(model.named_parameters(), device, groups=default_group_of, subgroups=default_subgroup_of)
         self.flat = self.fgb.flat
         # N>1: all-reduce issued inside the step (and captured with it), overlapped with the backbone backward;
         # TDB_OVERLAP=0 -> one serialised all-reduce after the replay
         self.overlap = world > 1 and os.environ.get("TDB_OVERLAP", "1") != "0"
+        self.comm_stream = self.comm_group = None
+        if self.overlap and os.environ.get("TDB_STAGED_AR", "1") != "0":
+            # second communicator + stream: the rest / backbone-stage slices are reduced as they complete, concurrently with the
+            # text slice's all-reduce on the text stream; gradients are written straight into the flat buffer
+            self.comm_group = torch.distributed.new_group()
+            self.comm_stream = torch.cuda.Stream()
+            self.fgb.bind_destinations()
         self.loss = torch.zeros((), device=device)
         self.host_loss = torch.zeros((), pin_memory=True)
         self.copy_stream = torch.cuda.Stream()
@@ -220,7 +227,8 @@ class Step:
         if self.overlap:
             from tubedetr_b200.parallel import backward_overlapped
             hid, feat = self.model.trunk_outputs()
-            backward_overlapped(total, self.fgb, hid, feat, side_stream=self.model.text_stream(self.flat.device))
+            backward_overlapped(total, self.fgb, hid, feat, side_stream=self.model.text_stream(self.flat.device),
+                                engine=self.model._engine, comm_stream=self.comm_stream, comm_group=self.comm_group)
         else:
             total.backward()
             if self.world > 1:

@@ -259,6 +259,39 @@ int tdb_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* e
                        int64_t step, const float* grad_norm, float max_norm, float ema_decay, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused data movement around the video-text encoder (tdb_glue.cu; d_model = 256; token rows frame-major; clip(b, t) = b * ceil(T/k) + t / k).
+ * ------------------------------------------------------------------------------------------------ */
+/* PositionEmbeddingSine(128, normalize=True) in one kernel (reference models/position_encoding.py:71-94): mask [N][h][w] (nonzero = pad)
+ * -> out fp32 [N][h*w][256] (channel-last: y features 0..127, x features 128..255, sin / cos interleaved) */
+int tdb_pos_sine(const uint8_t* mask, float* out, int N, int h, int w, void* stream);
+/* encoder input (reference models/transformer.py:269-331): x32 [n][HW+L][256] = [src rows | text rows of the clip's video], pe = [pos | 0],
+ * xb = bf16(x32), xpb = bf16(x32 + pe).  Backward: dsrc = g32 + gb + gpb on the image rows, dtxt = the same summed over a video's clips. */
+int tdb_enc_assemble_fwd(const float* src, const float* txt, const float* pos, float* x32, void* xb, void* xpb, float* pe, int n, int HW, int L,
+                         int n_clips, void* stream);
+int tdb_enc_assemble_bwd(const float* g32, const void* gb, const void* gpb, float* dsrc, float* dtxt, int n, int HW, int L, int n_clips,
+                         void* stream);
+/* fast branch (reference models/transformer.py:373-391): z [B*T][HW][256] bf16 = enc[clip][hw] + fm; backward: denc [n][S][256] = sum of dz over
+ * the clip's frames on the image rows, 0 on the text rows */
+int tdb_fast_mix_fwd(const float* enc, const void* fm, void* z, int B, int T, int k, int HW, int S, void* stream);
+int tdb_fast_mix_bwd(const void* dz, float* denc, int B, int T, int k, int HW, int S, void* stream);
+/* temporal replication + aggregation + decoder operands (reference models/transformer.py:393-446): mem [B*T][S][256] = enc[clip] (+ upd on the
+ * image rows, upd may be NULL), mem_pos = pe[clip], memb = bf16(mem), mempb = bf16(mem + mem_pos).  Backward: g = gmem + gmemb + gmempb (any
+ * NULL), dupd (fp32 + bf16 copy, may be NULL) = g on the image rows, denc = g summed over the clip's frames. */
+int tdb_aggregate_fwd(const float* enc, const float* pe, const float* upd, float* mem, float* mem_pos, void* memb, void* mempb, int B, int T, int k,
+                      int HW, int S, void* stream);
+int tdb_aggregate_bwd(const float* gmem, const void* gmemb, const void* gmempb, float* denc, float* dupd, void* dupd_b, int B, int T, int k, int HW,
+                      int S, void* stream);
+
+/* Last layer of a prediction head (reference models/tubedetr.py:23-42, 226-252: bbox_embed -> sigmoid, sted_embed -> dropout 0.5): x bf16
+ * [R][256] (output of the previous layer's GEMM), W fp32 [J][256], b [J], J <= 8; y fp32 [R][J] = dropout(act(x W^T + b)), act 0 none /
+ * 1 sigmoid, dropout from the hash stream (drop_seed NULL = off).  Backward: dx bf16 [R][256] (mask_dx: zero where x <= 0 and scaled by
+ * dx_scale = ReLU / hidden-dropout backward of the producing layer), dW [J][256], db [J]; dpre [R][J] scratch. */
+int tdb_head_out_fwd(const void* x, const float* W, const float* b, float* y, int R, int J, int act, const int64_t* drop_seed,
+                     int64_t drop_site, float drop_p, void* stream);
+int tdb_head_out_bwd(const float* dy, const float* y, const void* x, const float* W, float* dpre, void* dx, float* dW, float* db, int R, int J,
+                     int act, int mask_dx, float dx_scale, const int64_t* drop_seed, int64_t drop_site, float drop_p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SetCriterion in two launches (reference models/tubedetr.py:270-372, 437-458; util/box_ops.py:65-115):
  * L1 + GIoU on the kept boxes, KL of the start / end distributions, guided-attention loss, for the main output and the auxiliary
  * decoder layers at once.  All tensors fp32, contiguous, per-layer pointers (NULL = that loss family is off).

@@ -656,9 +656,80 @@ def test_fused_criterion_matches_torch_criterion(losses):
         wts["loss_giou_1"] = 0.0
         drop = "loss_sted_3"
         leaves = [t for l in layers for n_, t in l.items() if n_ != "weights" or "guided_attn" in losses]
-        ga = torch.autograd.grad(sum(got[k_] * wts[k_] for k_ in got if k_ != drop), leaves, allow_unused=True)
+        ga = torch.autograd.grad(sum(got[k_] * wts[k_] for k_ in got if k_ != drop), leaves, allow_unused=True, retain_graph=True)
         gb = torch.autograd.grad(sum(ref[k_] * wts[k_] for k_ in ref if k_ != drop), leaves, allow_unused=True)
         for a, c, t in zip(ga, gb, leaves):
             a = torch.zeros_like(t) if a is None else a
             c = torch.zeros_like(t) if c is None else c
             torch.testing.assert_close(a, c, atol=2e-5 * (c.abs().max().item() + 1e-6) + 1e-7, rtol=1e-4)
+
+
+def test_pos_sine_kernel_matches_reference_math():
+    """tdb_pos_sine (one kernel) == PositionEmbeddingSine(128, normalize=True) of reference models/position_encoding.py:71-94 (restated in
+    the oracle), with ragged padding masks"""
+    from oracle import tubedetr_oracle as O
+    from tubedetr_b200 import kernels as K
+    g = torch.Generator().manual_seed(3)
+    for N, h, w in ((5, 11, 11), (3, 7, 9), (2, 14, 5)):
+        mask = torch.zeros(N, h, w, dtype=torch.bool)
+        for n in range(1, N):
+            mask[n, int(torch.randint(2, h + 1, (1,), generator=g)):, :] = True
+            mask[n, :, int(torch.randint(2, w + 1, (1,), generator=g)):] = True
+        ref = O.pos_sine(mask).permute(0, 2, 3, 1).reshape(N, h * w, 256)
+        out = torch.empty(N, h * w, 256, device="cuda")
+        K.pos_sine(mask.cuda().view(torch.uint8), out, N, h, w)
+        assert (out.cpu() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("B,T,k,HW,L", [(1, 100, 4, 121, 20), (2, 7, 3, 25, 6), (3, 5, 5, 9, 4), (2, 8, 2, 49, 10)])
+def test_encoder_glue_kernels_match_torch(B, T, k, HW, L):
+    """enc_assemble / fast_mix / aggregate (tdb_glue.cu) vs the torch expressions they replace (gather, repeat_interleave, cat, add, casts),
+    forward values and gradients"""
+    from tubedetr_b200 import ops
+    n_clips = (T + k - 1) // k
+    n, S, D = B * n_clips, HW + L, 256
+    g = torch.Generator().manual_seed(41)
+    rnd = lambda *s: torch.randn(*s, generator=g).cuda()
+    src, txt, pos = rnd(n, HW, D).requires_grad_(True), rnd(B, L, D).requires_grad_(True), rnd(n, HW, D)
+    x32, xb, xpb, pe = ops.enc_assemble(src, txt, pos, n_clips)
+    r_x = torch.cat([src, txt.repeat_interleave(n_clips, 0)], 1).reshape(n * S, D)
+    r_pe = torch.cat([pos, torch.zeros(n, L, D, device="cuda")], 1).reshape(n * S, D)
+    assert torch.equal(x32, r_x) and torch.equal(pe, r_pe)
+    assert torch.equal(xb, r_x.bfloat16()) and torch.equal(xpb, (r_x + r_pe).bfloat16())
+    w1, w2, w3 = rnd(n * S, D), rnd(n * S, D).bfloat16(), rnd(n * S, D).bfloat16()
+    ga = torch.autograd.grad((x32 * w1).sum() + (xb.float() * w2.float()).sum() + (xpb.float() * w3.float()).sum(), [src, txt])
+    tot = (w1 + w2.float() + w3.float()).view(n, S, D)
+    torch.testing.assert_close(ga[0], tot[:, :HW], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(ga[1], tot[:, HW:].reshape(B, n_clips, L, D).sum(1), atol=1e-4, rtol=1e-5)
+    # fast mix + aggregate
+    clip = (torch.arange(B)[:, None] * n_clips + torch.arange(T)[None] // k).flatten().cuda()
+    enc = rnd(n * S, D).requires_grad_(True)
+    fm = rnd(B * T * HW, D).bfloat16().requires_grad_(True)
+    z = ops.fast_mix(enc, fm, B, T, k, HW, S)
+    r_z = (enc.view(n, S, D)[clip][:, :HW].reshape(B * T * HW, D) + fm.float()).bfloat16()
+    assert torch.equal(z, r_z)
+    wz = rnd(B * T * HW, D).bfloat16()
+    gz = torch.autograd.grad((z.float() * wz.float()).sum(), [enc, fm])
+    rz = torch.autograd.grad(((enc.view(n, S, D)[clip][:, :HW].reshape(B * T * HW, D) + fm.float()) * wz.float()).sum(), [enc, fm])
+    torch.testing.assert_close(gz[0], rz[0], atol=1e-4, rtol=1e-5)
+    torch.testing.assert_close(gz[1].float(), rz[1].float(), atol=1e-6, rtol=1e-6)
+    for has_upd in (True, False):
+        upd = rnd(B * T * HW, D).requires_grad_(True) if has_upd else None
+        mem, mem_pos, memb, mempb = ops.aggregate(enc, r_pe, upd, B, T, k, HW, S)
+        r_mem = enc.view(n, S, D)[clip]
+        if has_upd:
+            r_mem = torch.cat([r_mem[:, :HW] + upd.view(B * T, HW, D), r_mem[:, HW:]], 1)
+        r_pos = r_pe.view(n, S, D)[clip]
+        assert torch.equal(mem.view(B * T, S, D), r_mem) and torch.equal(mem_pos.view(B * T, S, D), r_pos)
+        assert torch.equal(memb.view(B * T, S, D), r_mem.bfloat16()) and torch.equal(mempb.view(B * T, S, D), (r_mem + r_pos).bfloat16())
+        v1, v2, v3 = rnd(B * T * S, D), rnd(B * T * S, D).bfloat16(), rnd(B * T * S, D).bfloat16()
+        leaves = [enc, upd] if has_upd else [enc]
+        gg = torch.autograd.grad((mem * v1).sum() + (memb.float() * v2.float()).sum() + (mempb.float() * v3.float()).sum(), leaves)
+        rr = torch.autograd.grad((r_mem.reshape(B * T * S, D) * (v1 + v2.float() + v3.float())).sum(), leaves)
+        for a_, c_ in zip(gg, rr):
+            torch.testing.assert_close(a_, c_, atol=1e-4, rtol=1e-5)
+        # only the bf16 operands carry gradient (the decoder's case): fp32 gradient slot is None inside the kernel
+        gg2 = torch.autograd.grad((memb.float() * v2.float()).sum() + (mempb.float() * v3.float()).sum(), leaves)
+        rr2 = torch.autograd.grad((r_mem.reshape(B * T * S, D) * (v2.float() + v3.float())).sum(), leaves)
+        for a_, c_ in zip(gg2, rr2):
+            torch.testing.assert_close(a_, c_, atol=1e-4, rtol=1e-5)

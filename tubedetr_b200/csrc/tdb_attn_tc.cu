@@ -90,6 +90,25 @@ __device__ __forceinline__ void warp_rows_load(float* stage, int lane, const flo
   __syncwarp();
 }
 
+// the same load in two halves, so that the global loads of the NEXT chunk are in flight while the current one is processed:
+// issue = 32 coalesced row-segment loads into registers (lane = column), commit = transpose through the staging buffer
+__device__ __forceinline__ void warp_rows_issue(int lane, const float* g, long long ld, int row0, int nrows, int col0, int ncols,
+                                                float (&raw)[32]) {
+  const int cols = ncols - col0;
+  const int rows = nrows - row0;
+  const float* base = g + (long long)row0 * ld + col0 + lane;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) raw[rr] = (rr < rows && lane < cols) ? __ldg(base + (long long)rr * ld) : 0.f;
+}
+__device__ __forceinline__ void warp_rows_commit(float* stage, int lane, const float (&raw)[32], float (&x)[32]) {
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) stage[rr * 32 + (lane ^ rr)] = raw[rr];
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < 32; ++t) x[t] = stage[lane * 32 + (t ^ lane)];
+  __syncwarp();
+}
+
 __device__ __forceinline__ void store_swizzled_row32(uint8_t* tile, int r, int c, const float (&x)[32]) {
   // columns [32c, 32c + 32) of row r of a K-major 128-byte-swizzled tile made of 64-column blocks [128 x 128 B]
   uint8_t* blk = tile + (c >> 1) * 16384 + r * 128;
@@ -454,6 +473,13 @@ mha_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const long long bh = (long long)b * a.H + h;
     const float* pmat = a.p + bh * a.Lq * a.Lk;
     const float* dpmat = a.dpbar ? a.dpbar + (long long)b * a.Lq * a.Lk : nullptr;
+    // the probabilities (and dPbar) do not depend on this kernel's MMAs: the first chunk of every query tile is requested before the
+    // wait for dPd, each further chunk while its predecessor is processed
+    float praw[32], draw[32];
+    if (wq * 32 < a.Lq) {
+      warp_rows_issue(lane, pmat, a.Lk, wq * 32, a.Lq, 0, a.Lk, praw);
+      if (dpmat) warp_rows_issue(lane, dpmat, a.Lk, wq * 32, a.Lq, 0, a.Lk, draw);
+    }
     for (int it = 0; it < iters; ++it) {
       const int mt = it;
       const uint32_t ph = (uint32_t)(it & 1);
@@ -478,14 +504,24 @@ mha_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // memory, no second hash evaluation)
         float rs = 0.f;
         for (int c = 0; c < nch; ++c) {
+          float pj[32], db[32];
+          warp_rows_commit(stage, lane, praw, pj);
+          if (dpmat) warp_rows_commit(stage, lane, draw, db);
+          {   // next chunk of this tile, or the first chunk of the next tile
+            const bool more = c + 1 < nch;
+            const int nrow0 = more ? row0 : row0 + 128, ncol0 = more ? (c + 1) * 32 : 0;
+            if ((more || it + 1 < iters) && nrow0 < a.Lq && ncol0 < a.Lk) {
+              warp_rows_issue(lane, pmat, a.Lk, nrow0, a.Lq, ncol0, a.Lk, praw);
+              if (dpmat) warp_rows_issue(lane, dpmat, a.Lk, nrow0, a.Lq, ncol0, a.Lk, draw);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) praw[t] = draw[t] = 0.f;
+            }
+          }
           uint32_t v[32];
           tmem_ld_32x32(lane_addr + c * 32, v);
           tmem_ld_wait();
-          float pj[32];
-          warp_rows_load(stage, lane, pmat, a.Lk, row0, a.Lq, c * 32, a.Lk, pj);
           if (dpmat) {
-            float db[32];
-            warp_rows_load(stage, lane, dpmat, a.Lk, row0, a.Lq, c * 32, a.Lk, db);
 #pragma unroll
             for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) + db[t] * invH);
           }

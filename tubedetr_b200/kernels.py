@@ -186,3 +186,46 @@ def criterion_fwd(desc, losses):
 
 def criterion_bwd(desc, grad_losses, d_boxes, d_sted, d_weights):
     check(lib().tdb_criterion_bwd(C.byref(desc), ptr(grad_losses), ptr(d_boxes), ptr(d_sted), ptr(d_weights), stream_ptr()), "criterion_bwd")
+
+
+def pos_sine(mask_u8, out, N, h, w):
+    check(lib().tdb_pos_sine(ptr(mask_u8), ptr(out), N, h, w, stream_ptr()), "pos_sine")
+    return out
+
+
+def enc_assemble_fwd(src, txt, pos, x32, xb, xpb, pe, n, HW, L, n_clips):
+    check(lib().tdb_enc_assemble_fwd(ptr(src), ptr(txt), ptr(pos), ptr(x32), ptr(xb), ptr(xpb), ptr(pe), n, HW, L, n_clips, stream_ptr()), "enc_assemble_fwd")
+
+
+def enc_assemble_bwd(g32, gb, gpb, dsrc, dtxt, n, HW, L, n_clips):
+    check(lib().tdb_enc_assemble_bwd(ptr(g32), ptr(gb), ptr(gpb), ptr(dsrc), ptr(dtxt), n, HW, L, n_clips, stream_ptr()), "enc_assemble_bwd")
+
+
+def fast_mix_fwd(enc, fm, z, B, T, k, HW, S):
+    check(lib().tdb_fast_mix_fwd(ptr(enc), ptr(fm), ptr(z), B, T, k, HW, S, stream_ptr()), "fast_mix_fwd")
+
+
+def fast_mix_bwd(dz, denc, B, T, k, HW, S):
+    check(lib().tdb_fast_mix_bwd(ptr(dz), ptr(denc), B, T, k, HW, S, stream_ptr()), "fast_mix_bwd")
+
+
+def aggregate_fwd(enc, pe, upd, mem, mem_pos, memb, mempb, B, T, k, HW, S):
+    check(lib().tdb_aggregate_fwd(ptr(enc), ptr(pe), ptr(upd), ptr(mem), ptr(mem_pos), ptr(memb), ptr(mempb), B, T, k, HW, S, stream_ptr()), "aggregate_fwd")
+
+
+def aggregate_bwd(gmem, gmemb, gmempb, denc, dupd, dupd_b, B, T, k, HW, S):
+    check(lib().tdb_aggregate_bwd(ptr(gmem), ptr(gmemb), ptr(gmempb), ptr(denc), ptr(dupd), ptr(dupd_b), B, T, k, HW, S, stream_ptr()), "aggregate_bwd")
+
+
+def head_out_fwd(x, W, b, y, act, drop=None):
+    seed, site, p = drop if drop is not None else (None, 0, 0.0)
+    R, J = y.shape
+    check(lib().tdb_head_out_fwd(ptr(x), ptr(W), ptr(b), ptr(y), R, J, int(act), ptr(seed), _i64(site), _f(p), stream_ptr()), "head_out_fwd")
+    return y
+
+
+def head_out_bwd(dy, y, x, W, dpre, dx, dW, db, act, mask_dx, dx_scale, drop=None):
+    seed, site, p = drop if drop is not None else (None, 0, 0.0)
+    R, J = y.shape
+    check(lib().tdb_head_out_bwd(ptr(dy), ptr(y), ptr(x), ptr(W), ptr(dpre), ptr(dx), ptr(dW), ptr(db), R, J, int(act), int(mask_dx),
+                                 _f(dx_scale), ptr(seed), _i64(site), _f(p), stream_ptr()), "head_out_bwd")

@@ -118,6 +118,15 @@ class _PosSine(nn.Module):
 
         return torch.cat((enc(y), enc(x)), dim=-1)  # (N,h,w,256) channel-last
 
+    def rows(self, mask):
+        """(N, h*w, 256) embedding rows; on CUDA one kernel (tdb_pos_sine) instead of ~15 elementwise launches"""
+        N, h, w = mask.shape
+        if not mask.is_cuda:
+            return self.forward(mask).view(N, h * w, 256)
+        from . import kernels as K
+        out = torch.empty(N, h * w, 256, dtype=torch.float32, device=mask.device)
+        return K.pos_sine(mask.contiguous().view(torch.uint8), out, N, h, w)
+
 
 class _Lin(nn.Module):
     def __init__(self, cin, cout, xavier=False, zero=False):
@@ -510,7 +519,7 @@ class TubeDETR(nn.Module):
         with torch.no_grad():
             m_s = self._resize_mask(fmask, h, w).clone()
             m_s[:, 0, 0] = False
-            pos = self.backbone[1](m_s).view(n, HW, D_MODEL)
+            pos = self.backbone[1].rows(m_s)                     # (n, HW, 256) sine embedding, one kernel
             dur, tt, valid, clip_of_t = self._index_tensors(tuple(durations), k, dev)
         Win, bin_ = self.input_proj.weight.view(D_MODEL, 2048), self.input_proj.bias
         src = ops.linear(feat, Win, bin_, out_fp32=True).view(n, HW, D_MODEL)
@@ -560,32 +569,34 @@ class TubeDETR(nn.Module):
         txt_rep = txt.repeat_interleave(n_clips, 0)                                      # (n,L,d)
 
         S = HW + L
-        x32 = torch.cat([src, txt_rep], 1).reshape(n * S, D_MODEL)
-        pe = torch.cat([pos, torch.zeros(n, L, D_MODEL, device=dev)], 1).reshape(n * S, D_MODEL)
+        # [image tokens | the video's text tokens] per clip, position rows, and the bf16 operands of the first in-projection: one kernel
+        x32, xb, xpb, pe = ops.enc_assemble(src, txt, pos, n_clips)
         kpm_enc_b = torch.cat([m_s.flatten(1), txt_kpm.repeat_interleave(n_clips, 0)], 1)
         kpm_enc = kpm_enc_b.to(torch.uint8).contiguous()
-        xb, xpb = x32.to(torch.bfloat16), (x32 + pe).to(torch.bfloat16)
         nl = len(tr.encoder.layers)
         for i, l in enumerate(tr.encoder.layers):
             x32, xb, xpb = tr._enc_layer(l, x32, xb, xpb, pe, kpm_enc, n, S, need_pos=i < nl - 1)
 
         # temporal replication: frame (b,t) <- clip (b, t//k)  (reference transformer.py:393-427)
-        enc = x32.view(n, S, D_MODEL)
-        mem = enc[clip_of_t]
-        mem_pos = pe.view(n, S, D_MODEL)[clip_of_t]
         kpm_dec = torch.cat([m_t, txt_kpm.repeat_interleave(T, 0)], 1)
         kpm_dec[:, 0] = False
-        if self.fast:
-            BT = B * T
+        BT = B * T
+        upd = None
+        if self.fast:      # fast branch: z = enc[clip(t)] + fast_encoder(fast features) -> fast_residual (reference transformer.py:373-391)
             fm = ops.linear(fsrc.reshape(BT * HW, D_MODEL), tr.fast_encoder.weight, tr.fast_encoder.bias)
-            z = (mem[:, :HW].reshape(BT * HW, D_MODEL) + fm.float()).to(torch.bfloat16)
+            z = ops.fast_mix(x32, fm, B, T, k, HW, S)
             upd = ops.linear(z, tr.fast_residual.weight, tr.fast_residual.bias, out_fp32=True)
-            mem = torch.cat([mem[:, :HW] + upd.view(BT, HW, D_MODEL), mem[:, HW:]], 1)
+        # replication over time + aggregation + the decoder's bf16 memory operands in one pass (reference transformer.py:393-446)
+        mem, mem_pos, memb, mempb = ops.aggregate(x32, pe, upd, B, T, k, HW, S)
+        mem, mem_pos = mem.view(BT, S, D_MODEL), mem_pos.view(BT, S, D_MODEL)
         return {
             "text_memory_resized": txt_rep.transpose(0, 1), "text_memory": mem[:, HW:].transpose(0, 1),
             "text_attention_mask": txt_kpm.repeat_interleave(n_clips, 0), "tokenized": {"input_ids": ids, "attention_mask": am},
             "img_memory": mem.transpose(0, 1), "mask": kpm_dec, "pos_embed": mem_pos.transpose(0, 1),
             "query_embed": qp.transpose(0, 1), "query_mask": q_kpm,
+            # private: bf16 operands of the decoder's key / value projections, produced by the same kernel as img_memory (decode
+            # recomputes them from img_memory / pos_embed when a caller passes a cache without them)
+            "_memb": memb, "_mempb": mempb,
         }
 
     def _decode(self, mc):
@@ -597,8 +608,10 @@ class TubeDETR(nn.Module):
         BT, S, _ = mem.shape
         kpm_mem = mc["mask"].to(torch.uint8).contiguous()
         kpm_q = mc["query_mask"].to(torch.uint8).contiguous()
-        memb = mem.reshape(BT * S, D_MODEL).to(torch.bfloat16)
-        mempb = (mem + mem_pos).reshape(BT * S, D_MODEL).to(torch.bfloat16)
+        memb, mempb = mc.get("_memb"), mc.get("_mempb")
+        if memb is None or mempb is None or memb.shape[0] != BT * S:
+            memb = mem.reshape(BT * S, D_MODEL).to(torch.bfloat16)
+            mempb = (mem + mem_pos).reshape(BT * S, D_MODEL).to(torch.bfloat16)
         qp = qp.reshape(B * T, D_MODEL).float().contiguous()
         x32 = torch.zeros(B * T, D_MODEL, device=mem.device)          # tgt = 0 (reference transformer.py:463-464)
         xb, xqb = x32.to(torch.bfloat16), qp.to(torch.bfloat16)

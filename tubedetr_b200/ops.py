@@ -71,6 +71,34 @@ def _root(w):
     return w._base if w._base is not None else w
 
 
+# ---- gradient destinations ----------------------------------------------------------------------------------------------------
+# Data-parallel steps keep every gradient in ONE flat buffer (parallel.FlatGradBuffer).  When the buffer's per-parameter views are
+# registered here, the backward nodes of this module write weight / bias gradients STRAIGHT into them (the split-K reduce and the
+# column sums take the view as their output), so no pack copy of these tensors is needed before the all-reduce and a slice can be
+# reduced as soon as its last producer has run.  Only used with torch.autograd.grad (parallel.backward_overlapped): with
+# .backward() AccumulateGrad would clone a tensor that is referenced elsewhere.
+_GRAD_DEST = {}
+
+
+def set_grad_dest(params, views):
+    _GRAD_DEST.clear()
+    for p, v in zip(params, views):
+        _GRAD_DEST[id(p)] = (weakref.ref(p), v)
+
+
+def grad_dest(p):
+    ent = _GRAD_DEST.get(id(p))
+    if ent is not None and ent[0]() is p:
+        return ent[1]
+    return None
+
+
+def _grad_out(p, dtype=torch.float32):
+    """output tensor for the gradient of parameter p: its flat-buffer view when registered, else a fresh tensor"""
+    v = grad_dest(p)
+    return v if v is not None else torch.empty(p.shape, dtype=dtype, device=p.device)
+
+
 def bf16_weight(w):
     """bf16 copy of an fp32 parameter, refreshed when the parameter changes (optimizer steps bump _version).
     The entry holds a weak reference to the parameter (its base tensor for views): an address can be recycled by the caching
@@ -199,6 +227,7 @@ class LinearFn(torch.autograd.Function):
         y = torch.empty(R, N, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
         gemm_fwd_w(x, W, y, R, N, Kd, bias=b, relu=relu)
         ctx.relu = relu
+        ctx.bias_ref = b if (b is not None and b.requires_grad) else None
         ctx.save_for_backward(x, W, y if relu else None)
         return y
 
@@ -216,13 +245,13 @@ class LinearFn(torch.autograd.Function):
         sc = wgrad_scope(x.device)
         with sc:                                          # weight / bias gradients: side stream, concurrent with the dgrad below
             if ctx.needs_input_grad[1]:
-                dW = wgrad_into(dyb, x, torch.empty(N, Kd, dtype=torch.float32, device=x.device))
+                dW = wgrad_into(dyb, x, _grad_out(W))
             if ctx.needs_input_grad[2]:
                 pre = getattr(dy, "_tdb_colsum", None)       # LayerNorm backward already summed this gradient over rows
                 if pre is not None and pre.numel() == N and not (ctx.relu and not ctx.masked_by_consumer):
                     db = pre
                 else:
-                    db = K.colsum_bf16(dyb, torch.empty(N, dtype=torch.float32, device=x.device))
+                    db = K.colsum_bf16(dyb, _grad_out(ctx.bias_ref) if ctx.bias_ref is not None else torch.empty(N, dtype=torch.float32, device=x.device))
         if ctx.needs_input_grad[0]:
             dx = torch.empty(R, Kd, dtype=torch.bfloat16, device=x.device)
             gemm(dyb, Wb, dx, R, Kd, N, b_major=1, mask=x if ctx.mask_dx else None,
@@ -279,6 +308,7 @@ class InProjFn(torch.autograd.Function):
             gemm_fwd_w(x, W, y, x.shape[0], hi - lo, x.shape[1], rows=(lo, hi), bias=b[lo:hi])
             outs.append(y)
         ctx.segs = segs
+        ctx.bias_ref = b if b.requires_grad else None
         ctx.save_for_backward(W, *xs)
         return tuple(outs)
 
@@ -286,8 +316,18 @@ class InProjFn(torch.autograd.Function):
     def backward(ctx, *dys):
         W, *xs = ctx.saved_tensors
         Wb = bf16_weight(W)
-        dW = torch.zeros_like(W) if ctx.needs_input_grad[0] else None
-        db = torch.zeros(W.shape[0], dtype=torch.float32, device=W.device) if ctx.needs_input_grad[1] else None
+        # gradient rows that no segment (or an unused output) covers must read zero
+        full = sum(hi - lo for (lo, hi), dy in zip(ctx.segs, dys) if dy is not None) == W.shape[0]
+        dW = db = None
+        if ctx.needs_input_grad[0]:
+            dW = _grad_out(W)
+            if not full:
+                dW.zero_()
+        if ctx.needs_input_grad[1]:
+            bref = ctx.bias_ref
+            db = _grad_out(bref) if bref is not None else torch.empty(W.shape[0], dtype=torch.float32, device=W.device)
+            if not full:
+                db.zero_()
         dxs = []
         sc = wgrad_scope(W.device)
         for i, ((lo, hi), x, dy) in enumerate(zip(ctx.segs, xs, dys)):
@@ -521,6 +561,10 @@ class DecoderKVFn(torch.autograd.Function):
             return (None,) * (4 + 2 * nl)
         Wk, Wv = ctx.wk, ctx.wv
         R, d = mempb.shape
+        for l in range(nl):            # a layer whose cross-attention received no gradient (never in the reference path): zero q rows
+            if sh.dW[l] is None:
+                sh.dW[l] = torch.zeros(3 * d, d, dtype=torch.float32, device=mempb.device)
+                sh.db[l] = torch.zeros(3 * d, dtype=torch.float32, device=mempb.device)
         sc = wgrad_scope(mempb.device)
         with sc:
             for l in range(nl):
@@ -565,6 +609,7 @@ class XAttnCoreFn(torch.autograd.Function):
         Kl, Vl = K_all[:, layer * d:(layer + 1) * d], V_all[:, layer * d:(layer + 1) * d]
         K.xattn_core_fwd(q, Kl, Vl, kpm, o, p, pbar, F, S, scale, keep=keep, keep_scale=1.0 / (1.0 - drop_p))
         ctx.cfg = (shared, layer, nl, F, S, scale, drop_p, tok is not None)
+        ctx.bias_ref = b
         ctx.save_for_backward(xq, q, K_all, V_all, W, p, keep)
         return o, pbar
 
@@ -576,9 +621,10 @@ class XAttnCoreFn(torch.autograd.Function):
         dev = xq.device
         if sh.dK is None:            # first layer to run its backward (the last decoder layer) allocates the shared gradient buffers
             sh.dK, sh.dV = torch.empty_like(K_all), torch.empty_like(V_all)
-            sh.dW = torch.empty(nl, 3 * d, d, dtype=torch.float32, device=dev)
-            sh.db = torch.empty(nl, 3 * d, dtype=torch.float32, device=dev)
+            sh.dW, sh.db = [None] * nl, [None] * nl
             sh.db_kv = torch.empty(2, nl * d, dtype=torch.float32, device=dev)
+        if sh.dW[layer] is None:
+            sh.dW[layer], sh.db[layer] = _grad_out(W), _grad_out(ctx.bias_ref)
         if do is None:
             do = torch.zeros(F, d, dtype=torch.bfloat16, device=dev)
         do = _as_bf16(do).contiguous()
@@ -694,7 +740,7 @@ class BackboneJointFn(torch.autograd.Function):
     def backward(ctx, g, _g_fast):
         feat, *params = ctx.saved_tensors
         g = (_as_bf16(g) * (feat > 0)).contiguous()
-        grads = {n: torch.empty_like(p, dtype=torch.float32) for n, p in zip(ctx.names, params)}
+        grads = {n: _grad_out(p) for n, p in zip(ctx.names, params)}
         ctx.engine.backward(ctx.bctx, ctx.W, g, grads)
         return (None, None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
 
@@ -715,6 +761,153 @@ class BackboneFn(torch.autograd.Function):
     def backward(ctx, g):
         feat, *params = ctx.saved_tensors
         g = (_as_bf16(g) * (feat > 0)).contiguous()
-        grads = {n: torch.empty_like(p, dtype=torch.float32) for n, p in zip(ctx.names, params)}
+        grads = {n: _grad_out(p) for n, p in zip(ctx.names, params)}
         ctx.engine.backward(ctx.bctx, ctx.W, g, grads)
         return (None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+# ---- fused data movement around the encoder (tdb_glue.cu) ----------------------------------------------------------------------
+def _cf32(t):
+    return t if (t is None or (t.dtype == torch.float32 and t.is_contiguous())) else t.float().contiguous()
+
+
+def _cbf(t):
+    return t if (t is None or (t.dtype == torch.bfloat16 and t.is_contiguous())) else t.to(torch.bfloat16).contiguous()
+
+
+class EncAssembleFn(torch.autograd.Function):
+    """[image tokens | per-clip repeated text tokens] -> x32 fp32, bf16(x32), bf16(x32 + pe), pe  (one kernel; reference
+    models/transformer.py:269-331 builds these with repeat / stack / cat loops)"""
+
+    @staticmethod
+    def forward(ctx, src, txt, pos, n_clips):
+        n, HW, D = src.shape
+        L = txt.shape[1]
+        S = HW + L
+        dev = src.device
+        x32 = torch.empty(n * S, D, dtype=torch.float32, device=dev)
+        pe = torch.empty_like(x32)
+        xb = torch.empty(n * S, D, dtype=torch.bfloat16, device=dev)
+        xpb = torch.empty_like(xb)
+        K.enc_assemble_fwd(_cf32(src), _cf32(txt), _cf32(pos), x32, xb, xpb, pe, n, HW, L, n_clips)
+        ctx.dims = (n, HW, L, n_clips, txt.shape[0])
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(pe)
+        return x32, xb, xpb, pe
+
+    @staticmethod
+    def backward(ctx, g32, gb, gpb, _gpe):
+        n, HW, L, n_clips, B = ctx.dims
+        ref = g32 if g32 is not None else (gb if gb is not None else gpb)
+        if ref is None:
+            return None, None, None, None
+        dsrc = torch.empty(n, HW, 256, dtype=torch.float32, device=ref.device)
+        dtxt = torch.empty(B, L, 256, dtype=torch.float32, device=ref.device)
+        K.enc_assemble_bwd(_cf32(g32), _cbf(gb), _cbf(gpb), dsrc, dtxt, n, HW, L, n_clips)
+        return dsrc, dtxt, None, None
+
+
+def enc_assemble(src, txt, pos, n_clips):
+    return EncAssembleFn.apply(src, txt, pos, int(n_clips))
+
+
+class FastMixFn(torch.autograd.Function):
+    """z = bf16(enc[clip(t)] + fm) on the image rows: the input of fast_residual (reference models/transformer.py:373-391)"""
+
+    @staticmethod
+    def forward(ctx, enc, fm, B, T, k, HW, S):
+        z = torch.empty(B * T * HW, 256, dtype=torch.bfloat16, device=enc.device)
+        K.fast_mix_fwd(_cf32(enc), _cbf(fm), z, B, T, k, HW, S)
+        ctx.dims = (B, T, k, HW, S, enc.shape)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        B, T, k, HW, S, eshape = ctx.dims
+        dz = _cbf(dz)
+        denc = torch.empty(eshape, dtype=torch.float32, device=dz.device)
+        K.fast_mix_bwd(dz, denc, B, T, k, HW, S)
+        return denc, dz.view(B * T * HW, 256), None, None, None, None, None
+
+
+def fast_mix(enc, fm, B, T, k, HW, S):
+    return FastMixFn.apply(enc, fm, B, T, k, HW, S)
+
+
+class AggregateFn(torch.autograd.Function):
+    """temporal replication + fast-branch aggregation + the decoder's bf16 memory operands in one pass (reference
+    models/transformer.py:393-446): -> mem fp32 [B*T*S, 256], mem_pos, bf16(mem), bf16(mem + mem_pos)"""
+
+    @staticmethod
+    def forward(ctx, enc, pe, upd, B, T, k, HW, S):
+        dev = enc.device
+        mem = torch.empty(B * T * S, 256, dtype=torch.float32, device=dev)
+        mem_pos = torch.empty_like(mem)
+        memb = torch.empty(B * T * S, 256, dtype=torch.bfloat16, device=dev)
+        mempb = torch.empty_like(memb)
+        K.aggregate_fwd(_cf32(enc), _cf32(pe), _cf32(upd), mem, mem_pos, memb, mempb, B, T, k, HW, S)
+        ctx.dims = (B, T, k, HW, S, enc.shape, upd is not None)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(mem_pos)
+        return mem, mem_pos, memb, mempb
+
+    @staticmethod
+    def backward(ctx, gmem, _gpos, gmemb, gmempb):
+        B, T, k, HW, S, eshape, has_upd = ctx.dims
+        ref = gmem if gmem is not None else (gmemb if gmemb is not None else gmempb)
+        if ref is None:
+            return (None,) * 8
+        dev = ref.device
+        denc = torch.empty(eshape, dtype=torch.float32, device=dev)
+        dupd = dupd_b = None
+        if has_upd and ctx.needs_input_grad[2]:
+            dupd = torch.empty(B * T * HW, 256, dtype=torch.float32, device=dev)
+            dupd_b = torch.empty(B * T * HW, 256, dtype=torch.bfloat16, device=dev)
+        K.aggregate_bwd(_cf32(gmem), _cbf(gmemb), _cbf(gmempb), denc, dupd, dupd_b, B, T, k, HW, S)
+        if dupd is not None:
+            dupd._tdb_bf16 = dupd_b
+        return denc, None, dupd, None, None, None, None, None
+
+
+def aggregate(enc, pe, upd, B, T, k, HW, S):
+    return AggregateFn.apply(enc, pe, upd, B, T, k, HW, S)
+
+
+class HeadOutFn(torch.autograd.Function):
+    """last layer of a prediction head fused with its activation / logit dropout (tdb_glue.cu); x is the bf16 output of the previous
+    layer's GEMM (post-ReLU, possibly after hidden dropout): with mask_dx its ReLU / dropout backward happens here"""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act, drop_p, mask_dx, dx_scale):
+        x = _cbf(x)
+        R = x.shape[0]
+        J = W.shape[0]
+        y = torch.empty(R, J, dtype=torch.float32, device=x.device)
+        drop = None
+        if drop_p > 0:
+            st = _drop_state(x.device)
+            st[1] += 1
+            drop = (st[0], st[1], float(drop_p))
+            ctx.drop_gen = st[2]
+        K.head_out_fwd(x, W.detach().float().contiguous(), b.detach().float().contiguous(), y, act, drop=drop)
+        ctx.cfg = (act, drop, mask_dx, float(dx_scale))
+        ctx.save_for_backward(x, W, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        act, drop, mask_dx, dx_scale = ctx.cfg
+        if drop is not None:
+            _check_drop_gen(x.device, ctx.drop_gen)
+        R, J = y.shape
+        dpre = torch.empty(R, J, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        dW = torch.empty(J, 256, dtype=torch.float32, device=x.device)
+        db = torch.empty(J, dtype=torch.float32, device=x.device)
+        K.head_out_bwd(dy.contiguous().float(), y, x, W.detach().float().contiguous(), dpre, dx, dW, db, act, mask_dx, dx_scale, drop=drop)
+        return dx, dW, db, None, None, None, None
+
+
+def head_out(x, W, b, act=0, drop_p=0.0, mask_dx=False, dx_scale=1.0):
+    return HeadOutFn.apply(x, W, b, int(act), float(drop_p), bool(mask_dx), float(dx_scale))

@@ -26,20 +26,31 @@ def default_group_of(name):
     return GROUP_REST
 
 
+def default_subgroup_of(name):
+    """order INSIDE the backbone group = the order in which the backbone backward completes its stages (layer4, layer3, layer2),
+    so that a finished stage is one contiguous slice that can be all-reduced while the earlier stages still run"""
+    if "backbone" in name:
+        for li in (4, 3, 2):
+            if f"layer{li}." in name:
+                return 4 - li
+    return 0
+
+
 class FlatGradBuffer:
     """Every trainable parameter owns a slice of ONE flat fp32 buffer, ordered group by group."""
 
-    def __init__(self, params, device=None, groups=None, align=8):
+    def __init__(self, params, device=None, groups=None, align=8, subgroups=None):
         """params: iterable of tensors (one group) or, with groups=callable(name)->int, an iterable of (name, tensor).
         Every parameter's slice starts at a multiple of `align` elements (zero padding in between: 32 B for fp32, 16 B for a
         bf16 mirror of the same layout -> vector loads and TMA tensor maps can address each slice directly)."""
         if groups is None:
-            items = [(0, p) for p in params if p.requires_grad]
+            items = [(0, 0, p) for p in params if p.requires_grad]
         else:
-            items = [(int(groups(n)), p) for n, p in params if p.requires_grad]
-        order = sorted(range(len(items)), key=lambda i: (items[i][0], i))     # stable: group-major, declaration order inside
-        self.params = [items[i][1] for i in order]
+            items = [(int(groups(n)), int(subgroups(n)) if subgroups else 0, p) for n, p in params if p.requires_grad]
+        order = sorted(range(len(items)), key=lambda i: (items[i][0], items[i][1], i))   # stable: group-major, declaration order inside
+        self.params = [items[i][2] for i in order]
         self.group_ids = [items[i][0] for i in order]
+        self.sub_ids = [items[i][1] for i in order]
         device = device or self.params[0].device
         pad = lambda n: (n + align - 1) // align * align
         self.offsets, o = [], 0
@@ -48,11 +59,28 @@ class FlatGradBuffer:
             o += pad(p.numel())
         self.flat = torch.zeros(o, dtype=torch.float32, device=device)
         self.bounds = {}                      # group -> (lo, hi) element range (hi includes the last slice's padding)
-        for g, p, off in zip(self.group_ids, self.params, self.offsets):
+        self.sub_bounds = {}                  # (group, subgroup) -> (lo, hi)
+        for g, sgp, p, off in zip(self.group_ids, self.sub_ids, self.params, self.offsets):
             lo, hi = self.bounds.get(g, (off, off))
             self.bounds[g] = (lo, off + pad(p.numel()))
+            lo, hi = self.sub_bounds.get((g, sgp), (off, off))
+            self.sub_bounds[(g, sgp)] = (lo, off + pad(p.numel()))
             p.grad = self.flat[off:off + p.numel()].view_as(p)
         self._views = None
+        self.bound = False
+
+    def bind_destinations(self):
+        """let the backward kernels write gradients straight into this buffer (ops.set_grad_dest): no pack copy for them, and a
+        slice is complete -- ready for its all-reduce -- as soon as its producers have run"""
+        from . import ops
+        if self._views is None:
+            self._views = self.views()
+        ops.set_grad_dest(self.params, self._views)
+        self.bound = True
+
+    def sub_segment(self, g, sub):
+        lo, hi = self.sub_bounds[(g, sub)]
+        return self.flat[lo:hi]
 
     def zero(self):
         self.flat.zero_()
@@ -94,14 +122,15 @@ class FlatGradBuffer:
         if dst:
             torch._foreach_copy_(dst, src)
 
-    def all_reduce(self, average=True, groups=None):
-        """sum over ranks (then / world): after this every rank holds the gradient of the mean loss over all clips."""
-        t = self.flat if groups is None else self.segment(*groups)
+    def all_reduce(self, average=True, groups=None, tensor=None, group=None):
+        """sum over ranks (then / world): after this every rank holds the gradient of the mean loss over all clips.
+        tensor: an explicit slice of the flat buffer (default: `groups`, default: everything); group: process group (communicator)."""
+        t = tensor if tensor is not None else (self.flat if groups is None else self.segment(*groups))
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and t.numel():
-            if average and dist.get_backend() == "nccl":
-                dist.all_reduce(t, op=dist.ReduceOp.AVG)          # the division rides inside the NCCL kernel
+            if average and dist.get_backend(group) == "nccl":
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)          # the division rides inside the NCCL kernel
             else:
-                dist.all_reduce(t)
+                dist.all_reduce(t, group=group)
                 if average:
                     t.div_(dist.get_world_size())
         return t
@@ -110,16 +139,21 @@ class FlatGradBuffer:
         return self.flat.numel() * 4
 
 
-def backward_overlapped(total, fgb, text_out, backbone_out, side_stream=None):
+def backward_overlapped(total, fgb, text_out, backbone_out, side_stream=None, engine=None, comm_stream=None, comm_group=None):
     """Backward of `total` with the gradient all-reduce overlapped with the backbone backward.
 
     text_out / backbone_out: the two trunk outputs the graph is cut at (RoBERTa `last_hidden_state`, backbone features;
     `TubeDETR.trunk_outputs()`), either may be None / not require grad (frozen trunk).
       phase 1  d total / d (GROUP_REST parameters, trunk outputs)                      -- decoder, encoder, heads
+               -> all-reduce(rest slice) on `comm_stream`                              -- overlaps everything below
       phase 2a text encoder backward -> pack -> all-reduce(text slice)                 -- on `side_stream`
-      phase 2b backbone backward     -> pack -> all-reduce(rest + backbone slice)      -- on the current stream
-    Everything is enqueued without host synchronisation (CUDA-graph capturable: the NCCL calls are captured with it).
-    On return the current stream has joined the side stream; fgb.flat holds the averaged gradients.
+      phase 2b backbone backward on the current stream; with `engine` (ResNet101Engine) and a buffer whose views are bound as
+               gradient destinations (fgb.bind_destinations()) every finished stage (layer4, layer3, layer2) is all-reduced on
+               `comm_stream` while the earlier stages still run, so only the last, small slice (layer2: 5 MB) is exposed;
+               otherwise the backbone slice is packed and reduced after the backward.
+    The collectives of `comm_stream` use `comm_group` (a second communicator: two NCCL streams of ONE communicator may not
+    overlap safely); the text slice uses the default group.  Everything is enqueued without host synchronisation (CUDA-graph
+    capturable).  On return the current stream has joined both helper streams; fgb.flat holds the averaged gradients.
     """
     rest = fgb.group_params(GROUP_REST)
     text = fgb.group_params(GROUP_TEXT)
@@ -131,6 +165,17 @@ def backward_overlapped(total, fgb, text_out, backbone_out, side_stream=None):
     main = torch.cuda.current_stream(fgb.flat.device) if cuda else None
     if cuda and side_stream is None:
         side_stream = torch.cuda.Stream(device=fgb.flat.device)
+    split = cuda and comm_stream is not None           # rest / backbone slices on their own stream + communicator
+
+    def on_comm(tensor):
+        """all-reduce a finished slice on the communication stream, ordered after everything enqueued on the main stream so far"""
+        comm_stream.wait_stream(main)
+        with torch.cuda.stream(comm_stream):
+            fgb.all_reduce(tensor=tensor, group=comm_group)
+
+    fgb.pack(groups=(GROUP_REST,), grads=g_rest)
+    if split:
+        on_comm(fgb.segment(GROUP_REST))
 
     # ---- 2a: text trunk on the side stream
     def text_part():
@@ -149,15 +194,32 @@ def backward_overlapped(total, fgb, text_out, backbone_out, side_stream=None):
     else:
         g_text = text_part()
 
-    # ---- 2b: backbone trunk on the main stream, then the remaining slice
+    # ---- 2b: backbone trunk on the main stream
     g_back = [None] * len(back)
     gb = g_cuts.get(id(backbone_out)) if backbone_out is not None else None
+    staged = split and engine is not None and fgb.bound and gb is not None and bool(back)
     if gb is not None and back:
-        g_back = torch.autograd.grad(backbone_out, back, gb, allow_unused=True)
-    fgb.pack(groups=(GROUP_REST, GROUP_BACKBONE), grads=g_rest + list(g_back))
-    fgb.all_reduce(groups=(GROUP_REST, GROUP_BACKBONE))
+        if staged:       # stage li of the backbone has written all its gradients (in place, into fgb.flat): reduce that slice now
+            engine.stage_callback = lambda li: on_comm(fgb.sub_segment(GROUP_BACKBONE, 4 - li))
+        try:
+            g_back = torch.autograd.grad(backbone_out, back, gb, allow_unused=True)
+        finally:
+            if staged:
+                engine.stage_callback = None
+    if staged:
+        assert all(g is not None and g.data_ptr() == v.data_ptr() for g, v in
+                   zip(g_back, [fgb._views[i] for i, gid in enumerate(fgb.group_ids) if gid == GROUP_BACKBONE])), \
+            "staged all-reduce needs every backbone gradient written in place"
+    else:
+        fgb.pack(groups=(GROUP_BACKBONE,), grads=list(g_back))
+        if split:
+            on_comm(fgb.segment(GROUP_BACKBONE))
+        else:
+            fgb.all_reduce(groups=(GROUP_REST, GROUP_BACKBONE))
     if cuda:
         main.wait_stream(side_stream)
+        if split:
+            main.wait_stream(comm_stream)
     # hand the results to the optimizer the usual way: .grad = view into the flat buffer
     for p, v in zip(fgb.params, fgb._views):
         p.grad = v

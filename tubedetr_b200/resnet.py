@@ -40,6 +40,7 @@ class ResNet101Engine:
         self._bn = None
         self._bn_key = None
         self.last_hw = None
+        self.stage_callback = None   # callable(stage index) fired by backward() when a stage's weight gradients are all enqueued
 
     def __deepcopy__(self, memo):  # EMA copies of the model (reference main.py:370) get a fresh, empty engine
         return ResNet101Engine()
@@ -349,9 +350,18 @@ class ResNet101Engine:
                         K.upsample2_zero(dxs, resid, N, h, w, cin)
             if last:
                 break
+            if r["first"] and self.stage_callback is not None:
+                # every weight gradient of this stage has been enqueued (main + wgrad side stream): join, then let the data-parallel
+                # driver all-reduce the stage's slice of the flat gradient buffer while the earlier stages still run
+                while pending:
+                    sc.wait(pending.pop(0))
+                sc.join()
+                self.stage_callback(int(name[5]))
             gprev = self.buf(f"{tag}:gout{i % 3}", (R, cin))
             gemm(g1, w1s, gprev, R, cin, width, b_major=1, residual=resid, mask=x, max_ctas=BWD_MAX_CTAS)
             g_out = gprev
             pending.append(sc.mark())
         sc.join()
+        if self.stage_callback is not None:
+            self.stage_callback(int(blocks[0]["name"][5]))
         return grads
