@@ -201,17 +201,20 @@ class Step:
         self.overlap = world > 1 and os.environ.get("TDB_OVERLAP", "1") != "0"
         self.comm_stream = self.comm_group = None
         if self.overlap and os.environ.get("TDB_STAGED_AR", "1") != "0":
-            # second communicator + stream: the rest / backbone-stage slices are reduced as they complete, concurrently with the
-            # text slice's all-reduce on the text stream; gradients are written straight into the flat buffer
-            self.comm_group = torch.distributed.new_group()
-            self.comm_stream = torch.cuda.Stream()
-            self.fgb.bind_destinations()
+            self.setup_staged()
         self.loss = torch.zeros((), device=device)
         self.host_loss = torch.zeros((), pin_memory=True)
         self.copy_stream = torch.cuda.Stream()
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = None
+
+    def setup_staged(self):
+        """second communicator + stream: the rest / backbone-stage slices are all-reduced as they complete, concurrently with the text
+        slice's all-reduce on the text stream; weight gradients are written straight into the flat buffer (no pack copy)"""
+        self.comm_group = torch.distributed.new_group()
+        self.comm_stream = torch.cuda.Stream()
+        self.fgb.bind_destinations()
 
     def body(self):
         # grads start as None so autograd ASSIGNS them (no per-parameter accumulate kernels); for N>1 they are packed into

@@ -68,7 +68,7 @@ def _batches(nsteps, stride):
     from tubedetr_b200.synthetic import make_batch, pack_clips
     out = []
     for s in range(nsteps):
-        durations = [6, 5] if s % 2 == 0 else [4, 6]
+        durations = [6, 5] if s % 2 == 0 else [3, 4]      # per batch: equal clip counts ceil(T / k) (the one layout restriction of this model)
         b = make_batch(durations, [(96, 96), (64, 96)], stride, [5, 3], seed=40 + s)
         ff, fm = pack_clips(b["clips"])
         fs, ms = pack_clips([c[:, ::stride] for c in b["clips"]])

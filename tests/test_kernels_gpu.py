@@ -724,8 +724,8 @@ def test_encoder_glue_kernels_match_torch(B, T, k, HW, L):
         assert torch.equal(memb.view(B * T, S, D), r_mem.bfloat16()) and torch.equal(mempb.view(B * T, S, D), (r_mem + r_pos).bfloat16())
         v1, v2, v3 = rnd(B * T * S, D), rnd(B * T * S, D).bfloat16(), rnd(B * T * S, D).bfloat16()
         leaves = [enc, upd] if has_upd else [enc]
-        gg = torch.autograd.grad((mem * v1).sum() + (memb.float() * v2.float()).sum() + (mempb.float() * v3.float()).sum(), leaves)
-        rr = torch.autograd.grad((r_mem.reshape(B * T * S, D) * (v1 + v2.float() + v3.float())).sum(), leaves)
+        gg = torch.autograd.grad((mem * v1).sum() + (memb.float() * v2.float()).sum() + (mempb.float() * v3.float()).sum(), leaves, retain_graph=True)
+        rr = torch.autograd.grad((r_mem.reshape(B * T * S, D) * (v1 + v2.float() + v3.float())).sum(), leaves, retain_graph=True)
         for a_, c_ in zip(gg, rr):
             torch.testing.assert_close(a_, c_, atol=1e-4, rtol=1e-5)
         # only the bf16 operands carry gradient (the decoder's case): fp32 gradient slot is None inside the kernel

@@ -37,6 +37,8 @@ def rel(a, b):
 
 r0 = rel(ref, mean)
 st.overlap = True
+if os.environ.get("TDB_STAGED_AR", "1") != "0":
+    st.setup_staged()       # per-stage all-reduce on a second communicator, gradients written in place (the bench default at N > 1)
 st.body()
 torch.cuda.synchronize()
 eager = st.flat.clone()
@@ -65,7 +67,8 @@ except Exception as e:
 if rank == 0:
     print(f"allreduce vs mean of local grads: rel {r0:.3e}")
     print(f"overlapped eager vs serialised:   rel {r1:.3e}")
-    print(f"overlapped in-graph vs serialised: rel {r2:.3e} (graph ok: {ok_graph}, graph object: {st.graph is not None}), {ms_overlap:.3f} ms/step eval mode")
+    print(f"overlapped in-graph vs serialised: rel {r2:.3e} (graph ok: {ok_graph}, graph object: {st.graph is not None}, staged: {st.comm_stream is not None}), "
+          f"{ms_overlap:.3f} ms/step eval mode")
     assert r0 < 1e-5 and r1 < 1e-4 and (not ok_graph or r2 < 1e-4), (r0, r1, r2)
     print("dp_check ok")
 sys.stdout.flush()

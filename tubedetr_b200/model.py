@@ -216,6 +216,21 @@ class _MLP(nn.Module):
                 x = F.dropout(x, self.dropout, True)
         return x
 
+    def rows(self, xb, act=0):
+        """CUDA path on bf16 rows [R, 256]: hidden layers on the tcgen05 GEMM (bias + ReLU epilogue, ReLU / dropout backward in the
+        consumer's dgrad), last layer + activation (+ logit dropout) in one small kernel (tdb_head_out).  -> fp32 [R, dout]"""
+        dp = self.dropout if (self.dropout and self.training) else 0.0
+        nl = len(self.layers)
+        first = True
+        for i, l in enumerate(self.layers[:-1]):
+            xb = ops.linear(xb, l.weight, l.bias, relu=True, masked_by_consumer=True, mask_dx=not first,
+                            dx_scale=(1.0 / (1.0 - dp)) if (dp > 0 and not first) else 1.0)
+            if dp > 0:
+                xb = ops.hidden_dropout(xb, dp)
+            first = False
+        last = self.layers[-1]
+        return ops.head_out(xb, last.weight, last.bias, act=act, drop_p=dp, mask_dx=nl > 1, dx_scale=(1.0 / (1.0 - dp)) if dp > 0 else 1.0)
+
 
 class HashTokenizer:
     """Offline stand-in when the roberta-base vocabulary is not on disk: deterministic word hashing into RoBERTa's id
@@ -624,15 +639,16 @@ class TubeDETR(nn.Module):
         tr.fused_xattn = tr.xattn_mode != "unfused"
         for li, l in enumerate(tr.decoder.layers):
             x32, xb, xqb, w, cw = tr._dec_layer(l, x32, xb, xqb, qp, memb, mempb, kpm_mem, kpm_q, B, T, S, kv=kv, li=li)
-            hs.append(ops.add_layernorm(x32, None, dn.weight, dn.bias)[0])
+            hs.append(ops.add_layernorm(x32, None, dn.weight, dn.bias)[1])      # bf16 copy of decoder.norm(output): the heads' GEMM operand
             ws.append(w)
             cws.append(cw)
-        hs = torch.stack(hs).view(len(hs), B, T, D_MODEL)
+        nlay = len(hs)
+        hsb = torch.stack(hs).view(nlay * B * T, D_MODEL)
         out = {}
-        boxes = self.bbox_embed(hs.flatten(1, 2)).sigmoid()
+        boxes = self.bbox_embed.rows(hsb, act=1).view(nlay, B * T, 4)           # sigmoid inside the head kernel
         out["pred_boxes"] = boxes[-1]
         if self.sted:
-            sted = self.sted_embed(hs)
+            sted = self.sted_embed.rows(hsb).view(nlay, B, T, 2)
             out["pred_sted"] = sted[-1]
         if self.guided_attn:
             out["weights"], out["ca_weights"] = ws[-1], cws[-1]
