@@ -118,7 +118,7 @@ int tdb_split_bf16(const float* x, void* y, int64_t rows, int K, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm with fused residual add (post-norm blocks, reference models/transformer.py:641-645, 721-750, 581;
- * FeatureResizer LN eps 1e-12 :765).  D must be 256.  z = x + r; y = LN(z).  Optional bf16 copies of y and y + pos
+ * FeatureResizer LN eps 1e-12 :765; also the text encoder's LayerNorms).  D must be 256 or 768.  z = x + r; y = LN(z).  Optional bf16 copies of y and y + pos
  * (the operand of the next projection GEMM).  Backward returns dz (gradient of both x and r) and dgamma/dbeta.
  * Residual dropout (reference transformer.py:641-645 `src + self.dropout1(src2)` etc.): with drop_seed != NULL the kernel
  * computes z = x + keep * r / (1 - p), the keep bits coming from the same counter-based hash as tdb_dropout_mask(seed, site)
@@ -290,6 +290,25 @@ int tdb_head_out_fwd(const void* x, const float* W, const float* b, float* y, in
                      int64_t drop_site, float drop_p, void* stream);
 int tdb_head_out_bwd(const float* dy, const float* y, const void* x, const float* W, float* dpre, void* dx, float* dW, float* db, int R, int J,
                      int act, int mask_dx, float dx_scale, const int64_t* drop_seed, int64_t drop_site, float drop_p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Text encoder (RoBERTa-base; reference models/transformer.py:130-135, 250-263 calls HF RobertaModel): linear layers on
+ * tdb_gemm, LayerNorm + residual (+ dropout) on tdb_layernorm_* (D = 768), and the small kernels below (tdb_text.cu).
+ * ------------------------------------------------------------------------------------------------ */
+/* erf GELU on bf16 buffers (n even); backward takes the PRE-activation x */
+int tdb_gelu_fwd(const void* x, void* y, int64_t n, void* stream);
+int tdb_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
+/* weight / bias gradient of a linear layer with few rows (R tokens): dW [N][K] = dy^T x, db [N] = column sums of dy (db may be NULL);
+ * dy bf16 [R][N] (row stride ldy), x bf16 [R][K] (row stride ldx); one launch, rows summed in order */
+int tdb_skinny_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx, float* dW, float* db, int R, int N, int K, void* stream);
+/* attention core with head_dim 64 for short sequences (L <= 128 forward, <= 100 backward): q, k, v, o bf16 rows [B*L][>= H*64] with row
+ * strides, kpm [B][L] nonzero = padded key, p [B][H][L][L] fp32 probabilities before dropout, dropout from the hash stream */
+int tdb_text_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const uint8_t* kpm, void* o,
+                      int64_t ldo, float* p, const int64_t* drop_seed, int64_t drop_site, float drop_p, int B, int H, int L, float scale,
+                      void* stream);
+int tdb_text_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout, int64_t lddo,
+                      const float* p, const int64_t* drop_seed, int64_t drop_site, float drop_p, void* dq, int64_t lddq, void* dk,
+                      int64_t lddk, void* dv, int64_t lddv, int B, int H, int L, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SetCriterion in two launches (reference models/tubedetr.py:270-372, 437-458; util/box_ops.py:65-115):

@@ -43,6 +43,15 @@ st.body()
 torch.cuda.synchronize()
 eager = st.flat.clone()
 r1 = rel(eager, ref)
+if rank == 0 and r1 >= 1e-4:        # which parameters differ
+    names = {id(p): n for n, p in model.named_parameters()}
+    worst = []
+    for p, off in zip(st.fgb.params, st.fgb.offsets):
+        a, b = eager[off:off + p.numel()], ref[off:off + p.numel()]
+        worst.append((((a - b).norm() / (b.norm() + 1e-30)).item(), names.get(id(p), "?"), b.norm().item()))
+    worst.sort(reverse=True)
+    for w in worst[:8]:
+        print(f"  mismatch {w[1]}: rel {w[0]:.3e} (ref norm {w[2]:.3e})")
 ok_graph, r2 = True, float("nan")
 try:
     st.use_graph = True
@@ -69,8 +78,8 @@ if rank == 0:
     print(f"overlapped eager vs serialised:   rel {r1:.3e}")
     print(f"overlapped in-graph vs serialised: rel {r2:.3e} (graph ok: {ok_graph}, graph object: {st.graph is not None}, staged: {st.comm_stream is not None}), "
           f"{ms_overlap:.3f} ms/step eval mode")
-    assert r0 < 1e-5 and r1 < 1e-4 and (not ok_graph or r2 < 1e-4), (r0, r1, r2)
-    print("dp_check ok")
+    good = r0 < 1e-5 and r1 < 1e-4 and (not ok_graph or r2 < 1e-4)
+    print("dp_check ok" if good else f"dp_check FAILED: {(r0, r1, r2)}")
 sys.stdout.flush()
 st.graph = None
 torch.cuda.synchronize()

@@ -300,7 +300,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 
 // backward: given dy (fp32), z recomputed from (x, r), mean, rstd: dz = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma
 // writes dz (fp32; it is the gradient of BOTH x and r) and per-block partial dgamma/dbeta [blocks][2][D] for a fixed-order reduce.
-template <int D>
+template <int D, int WPB>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ dy3,
                                      const float* __restrict__ x, const float* __restrict__ r,
                                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -311,14 +311,14 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
   pdl_trigger();
   constexpr int PER = D / 32;
   const unsigned long long dbase = drop_seed ? drop_base(drop_seed, drop_site) : 0ull;
-  __shared__ float sg[8][D];
-  __shared__ float sb[8][D];
-  __shared__ float sr[8][D];
+  __shared__ float sg[WPB][D];      // WPB warps per block: 3 x WPB x D floats must stay under the 48 KB static limit (D = 768 -> 4 warps)
+  __shared__ float sb[WPB][D];
+  __shared__ float sr[WPB][D];
   int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ag[PER], ab[PER], ar[PER];     // column sums of dy * xhat (dgamma), dy (dbeta), and the gradient of r (bias gradient of the
 #pragma unroll                       // linear layer that produced r: its separate column-sum launches disappear)
   for (int i = 0; i < PER; ++i) ag[i] = ab[i] = ar[i] = 0.f;
-  for (int row = blockIdx.x * 8 + wib; row < rows; row += gridDim.x * 8) {
+  for (int row = blockIdx.x * WPB + wib; row < rows; row += gridDim.x * WPB) {
     float m = mean[row], rs = rstd[row];
     float g[PER], xh[PER];
     float s1 = 0.f, s2 = 0.f;
@@ -368,7 +368,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const bf16* _
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float a = 0.f, b = 0.f, cc = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < WPB; ++w) {
       a += sg[w][c];
       b += sb[w][c];
       cc += sr[w][c];
@@ -613,14 +613,17 @@ extern "C" int tdb_split_bf16(const float* x, void* y, int64_t rows, int K, void
 extern "C" int tdb_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta, const float* pos,
                                  float* y, void* y_bf, void* ypos_bf, float* mean, float* rstd, int rows, int D, float eps,
                                  const int64_t* drop_seed, int64_t drop_site, float drop_p, void* stream_) {
-  TDB_REQUIRE(x && gamma && beta && y && rows > 0 && D == 256, "tdb_layernorm_fwd: only D=256 (got %d)", D);
+  TDB_REQUIRE(x && gamma && beta && y && rows > 0 && (D == 256 || D == 768), "tdb_layernorm_fwd: D must be 256 or 768 (got %d)", D);
   TDB_REQUIRE(!ypos_bf || pos, "tdb_layernorm_fwd: ypos needs pos");
   TDB_REQUIRE(!drop_seed || (r && drop_p > 0.f && drop_p < 1.f), "tdb_layernorm_fwd: residual dropout needs r and 0 < p < 1");
   const uint32_t thr = drop_seed ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
   const float dscale = drop_seed ? 1.f / (1.f - drop_p) : 1.f;
-  TDB_CHECK_CUDA(tdb_launch(layernorm_fwd_kernel<256>, dim3(nblocks((long long)rows * 32, 256)), dim3(256), 0, STREAM, x, r, gamma, beta, pos, y, (bf16*)y_bf,
-                                                                                    (bf16*)ypos_bf, mean, rstd, rows, eps,
-                                                                                    (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale));
+  if (D == 256)
+    TDB_CHECK_CUDA(tdb_launch(layernorm_fwd_kernel<256>, dim3(nblocks((long long)rows * 32, 256)), dim3(256), 0, STREAM, x, r, gamma, beta, pos, y, (bf16*)y_bf,
+                              (bf16*)ypos_bf, mean, rstd, rows, eps, (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale));
+  else       // text encoder (RoBERTa, d = 768)
+    TDB_CHECK_CUDA(tdb_launch(layernorm_fwd_kernel<768>, dim3(nblocks((long long)rows * 32, 256)), dim3(256), 0, STREAM, x, r, gamma, beta, pos, y, (bf16*)y_bf,
+                              (bf16*)ypos_bf, mean, rstd, rows, eps, (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale));
   LAUNCH_OK();
 }
 extern "C" int tdb_layernorm_bwd_blocks(int rows) {
@@ -632,13 +635,17 @@ extern "C" int tdb_layernorm_bwd(const float* dy, const void* dy2_bf, const void
                                  float* dgamma, float* dbeta, float* partial, int rows, int D, int accumulate,
                                  const int64_t* drop_seed, int64_t drop_site, float drop_p, float* dr, void* dr_bf, float* dbias,
                                  void* stream_) {
-  TDB_REQUIRE((dy || dy2_bf || dy3_bf) && x && gamma && mean && rstd && dz && partial && rows > 0 && D == 256, "tdb_layernorm_bwd: bad args");
+  TDB_REQUIRE((dy || dy2_bf || dy3_bf) && x && gamma && mean && rstd && dz && partial && rows > 0 && (D == 256 || D == 768), "tdb_layernorm_bwd: bad args");
   TDB_REQUIRE(!drop_seed || (r && drop_p > 0.f && drop_p < 1.f && (dr || dr_bf)), "tdb_layernorm_bwd: residual dropout needs r, 0 < p < 1 and a dr output");
   const uint32_t thr = drop_seed ? (uint32_t)(drop_p * 65536.0f + 0.5f) : 0u;
   const float dscale = drop_seed ? 1.f / (1.f - drop_p) : 1.f;
   int blocks = tdb_layernorm_bwd_blocks(rows);
-  TDB_CHECK_CUDA(tdb_launch(layernorm_bwd_kernel<256>, dim3(blocks), dim3(256), 0, STREAM, dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows,
-                            (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale, dr, (bf16*)dr_bf));
+  if (D == 256)
+    TDB_CHECK_CUDA(tdb_launch(layernorm_bwd_kernel<256, 8>, dim3(blocks), dim3(256), 0, STREAM, dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows,
+                              (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale, dr, (bf16*)dr_bf));
+  else
+    TDB_CHECK_CUDA(tdb_launch(layernorm_bwd_kernel<768, 4>, dim3(blocks), dim3(128), 0, STREAM, dy, (const bf16*)dy2_bf, (const bf16*)dy3_bf, x, r, gamma, mean, rstd, dz, (bf16*)dz_bf, partial, rows,
+                              (const long long*)drop_seed, (unsigned long long)drop_site, thr, dscale, dr, (bf16*)dr_bf));
   TDB_CHECK_CUDA(cudaGetLastError());
   if (dgamma && dbeta == dgamma + D) {   // [dgamma | dbeta (| dbias)] contiguous: the partial rows reduce in ONE launch
     const int cols = (dbias == dgamma + 2 * D) ? 3 * D : 2 * D;

@@ -229,3 +229,31 @@ def head_out_bwd(dy, y, x, W, dpre, dx, dW, db, act, mask_dx, dx_scale, drop=Non
     R, J = y.shape
     check(lib().tdb_head_out_bwd(ptr(dy), ptr(y), ptr(x), ptr(W), ptr(dpre), ptr(dx), ptr(dW), ptr(db), R, J, int(act), int(mask_dx),
                                  _f(dx_scale), ptr(seed), _i64(site), _f(p), stream_ptr()), "head_out_bwd")
+
+
+def gelu_fwd(x, y):
+    check(lib().tdb_gelu_fwd(ptr(x), ptr(y), _i64(x.numel()), stream_ptr()), "gelu_fwd")
+    return y
+
+
+def gelu_bwd(dy, x, dx):
+    check(lib().tdb_gelu_bwd(ptr(dy), ptr(x), ptr(dx), _i64(x.numel()), stream_ptr()), "gelu_bwd")
+    return dx
+
+
+def skinny_wgrad(dy, x, dW, db):
+    R, N = dy.shape
+    check(lib().tdb_skinny_wgrad(ptr(dy), _i64(dy.stride(0)), ptr(x), _i64(x.stride(0)), ptr(dW), ptr(db), R, N, x.shape[1], stream_ptr()), "skinny_wgrad")
+
+
+def text_attn_fwd(q, k, v, kpm, o, p, B, H, L, scale, drop=None):
+    seed, site, dp = drop if drop is not None else (None, 0, 0.0)
+    check(lib().tdb_text_attn_fwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(kpm), ptr(o),
+                                  _i64(o.stride(0)), ptr(p), ptr(seed), _i64(site), _f(dp), B, H, L, _f(scale), stream_ptr()), "text_attn_fwd")
+
+
+def text_attn_bwd(q, k, v, dout, p, dq, dk, dv, B, H, L, scale, drop=None):
+    seed, site, dp = drop if drop is not None else (None, 0, 0.0)
+    check(lib().tdb_text_attn_bwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(dout),
+                                  _i64(dout.stride(0)), ptr(p), ptr(seed), _i64(site), _f(dp), ptr(dq), _i64(dq.stride(0)), ptr(dk),
+                                  _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)), B, H, L, _f(scale), stream_ptr()), "text_attn_bwd")

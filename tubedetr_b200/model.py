@@ -24,6 +24,7 @@ from torch import nn
 
 from . import _lib
 from . import ops
+from . import text
 from .resnet import STAGES, ResNet101Engine
 
 D_MODEL, NHEAD, DFF = 256, 8, 2048
@@ -389,7 +390,11 @@ class TubeDETR(nn.Module):
         # backbone runs once per distinct frame (T instead of T + ceil(T/k) frames) and the fast branch reuses the slow
         # frames' features (detached, as the fast branch never backpropagates into the backbone).
         self.slow_frames_alias_fast = False
-        self.text_autocast = False  # True: RoBERTa (library call) runs its GEMMs under bf16 autocast (bench.py sets it)
+        self.text_autocast = False  # library path only: run HF RoBERTa's GEMMs under bf16 autocast
+        # text encoder as the HF library call it is in the reference (default), or on this library's kernels (text.py, TDB_OWN_TEXT=1):
+        # parity-tested, but measured SLOWER inside the step (20.1 vs 18.5 ms): its one-tile tcgen05 GEMMs need a whole SM's shared
+        # memory each and queue behind the backbone's persistent GEMM waves, where the library's small-footprint kernels slip in
+        self.own_text_encoder = os.environ.get("TDB_OWN_TEXT", "0") != "0"
 
     # ------------------------------------------------------------------ helpers
     _TRANSIENT = ("_trunk", "_idx_cache")     # per-step state that must not follow a copy of the model
@@ -498,8 +503,12 @@ class TubeDETR(nn.Module):
             main = torch.cuda.current_stream(dev)
             tstream.wait_stream(main)
         with torch.cuda.stream(tstream if side else torch.cuda.current_stream(dev)):
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.text_autocast):
-                hid = tr.text_encoder(input_ids=ids, attention_mask=am).last_hidden_state    # (B,L,768)
+            if self.own_text_encoder and text.supported(tr.text_encoder, ids):
+                # RoBERTa on this library's kernels (text.py): the HF module only holds the parameters
+                _, hid = text.roberta_forward(tr.text_encoder, ids, am, self.training)      # bf16 rows (B*L, 768)
+            else:
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.text_autocast):
+                    hid = tr.text_encoder(input_ids=ids, attention_mask=am).last_hidden_state    # (B,L,768)
 
         sd = self._backbone_tensors()
         W = self._engine.prepare(sd)
@@ -574,8 +583,9 @@ class TubeDETR(nn.Module):
         if side:
             main.wait_stream(tstream)
             hid.record_stream(main)
-        L = hid.shape[1]
-        r = ops.linear(hid.float().reshape(B * L, 768).to(torch.bfloat16), tr.resizer.fc.weight, tr.resizer.fc.bias, out_fp32=True)
+        L = ids.shape[1]
+        hidb = hid if hid.dtype == torch.bfloat16 else hid.float().reshape(B * L, 768).to(torch.bfloat16)
+        r = ops.linear(hidb.reshape(B * L, 768), tr.resizer.fc.weight, tr.resizer.fc.bias, out_fp32=True)
         txt, _ = ops.add_layernorm(r, None, tr.resizer.layer_norm.weight, tr.resizer.layer_norm.bias, eps=1e-12)
         if self.training:
             txt = F.dropout(txt, 0.1, True)                     # FeatureResizer dropout (reference transformer.py:141,772)

@@ -78,17 +78,27 @@ def _root(w):
 # reduced as soon as its last producer has run.  Only used with torch.autograd.grad (parallel.backward_overlapped): with
 # .backward() AccumulateGrad would clone a tensor that is referenced elsewhere.
 _GRAD_DEST = {}
+_GRAD_CLAIMED = set()
 
 
 def set_grad_dest(params, views):
     _GRAD_DEST.clear()
+    _GRAD_CLAIMED.clear()
     for p, v in zip(params, views):
         _GRAD_DEST[id(p)] = (weakref.ref(p), v)
 
 
+def begin_backward():
+    """start of a backward pass: every destination may be claimed ONCE per pass.  A parameter that feeds two backward nodes (e.g.
+    input_proj.bias: slow and fast rows) gets its in-place view from the first and a fresh tensor from the second; autograd then sums
+    the two into a new tensor, which the driver's pack() copies over the view."""
+    _GRAD_CLAIMED.clear()
+
+
 def grad_dest(p):
     ent = _GRAD_DEST.get(id(p))
-    if ent is not None and ent[0]() is p:
+    if ent is not None and ent[0]() is p and id(p) not in _GRAD_CLAIMED:
+        _GRAD_CLAIMED.add(id(p))
         return ent[1]
     return None
 

@@ -159,6 +159,9 @@ def backward_overlapped(total, fgb, text_out, backbone_out, side_stream=None, en
     text = fgb.group_params(GROUP_TEXT)
     back = fgb.group_params(GROUP_BACKBONE)
     cuts = [t for t in (text_out, backbone_out) if t is not None and t.requires_grad]
+    if fgb.bound:
+        from . import ops
+        ops.begin_backward()
     g1 = torch.autograd.grad(total, rest + cuts, allow_unused=True)
     g_rest, g_cuts = list(g1[:len(rest)]), dict(zip([id(t) for t in cuts], g1[len(rest):]))
     cuda = fgb.flat.is_cuda

@@ -75,3 +75,70 @@ def xattn_phase(F=100, S=141, pair=0, reps=24):
             "cta_lifetime_cycles_median": float(life.median()),
             "tensor_pipe_pct_of_cta_lifetime": 100.0 * XATTN_MMA_CYCLES / float(life.median()),
             "us_per_layer_fused_plus_merge": us, "globaltimer": skew, "algorithmic_bytes": alg, "algorithmic_gbs": alg / us / 1e3}
+
+
+def decoder_attn_hoisted(F=100, S=141, nl=6, reps=12, peak_tflops=None, peak_gbs=None):
+    """The decoder cross-attention as the model runs it by default (reference models/transformer.py:567-579, 724-745): (i) the K / V
+    projections of ALL `nl` layers as two tcgen05 GEMMs [F*S, 256] x [nl*256, 256]^T with split-precision weights (two reduction
+    taps: executed tensor-core work = 2 x algorithmic), (ii) per layer the streaming one-query attention core on a 256-column slice.
+    Device time from CUDA-graph replays over rotating inputs (> L2 for the GEMM operands)."""
+    from .gemm import gemm
+    d = 256
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator().manual_seed(2)
+    R = F * S
+    nb = 4
+    mems = [(torch.randn(R, d, generator=g).bfloat16().to(dev), torch.randn(R, d, generator=g).bfloat16().to(dev)) for _ in range(nb)]
+    outs = [(torch.empty(R, nl * d, dtype=torch.bfloat16, device=dev), torch.empty(R, nl * d, dtype=torch.bfloat16, device=dev)) for _ in range(nb)]
+    Wk = (torch.randn(nl * d, 2 * d, generator=g) / 16).bfloat16().to(dev)
+    Wv = (torch.randn(nl * d, 2 * d, generator=g) / 16).bfloat16().to(dev)
+    bias = torch.zeros(nl * d, device=dev)
+    q = torch.randn(F, d, generator=g).bfloat16().to(dev)
+    kpm = torch.zeros(F, S, dtype=torch.uint8, device=dev)
+    o = torch.empty(F, d, dtype=torch.bfloat16, device=dev)
+    p = torch.empty(F, 8, 1, S, device=dev)
+    pbar = torch.empty(F, 1, S, device=dev)
+
+    def proj(i):
+        m, out = mems[i % nb], outs[i % nb]
+        gemm(m[0], Wk, out[0], R, nl * d, d, ntaps=2, a_off0=(0, 0), b_off0=(0, d), bias=bias)
+        gemm(m[1], Wv, out[1], R, nl * d, d, ntaps=2, a_off0=(0, 0), b_off0=(0, d), bias=bias)
+
+    def core(i):
+        out = outs[i % nb]
+        l = i % nl
+        K.xattn_core_fwd(q, out[0][:, l * d:(l + 1) * d], out[1][:, l * d:(l + 1) * d], kpm, o, p, pbar, F, S, 1 / math.sqrt(32))
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+            for i in range(reps):
+                fn(i)
+        gr.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (5 * reps) * 1e3
+
+    us_proj = timed(proj)
+    us_core = timed(core)
+    flops = 2.0 * 2 * R * nl * d * d                      # algorithmic: K and V projections of all layers
+    bytes_proj = 2 * (R * d + nl * d * 2 * d + R * nl * d) * 2
+    bytes_core = 2 * R * d * 2 + F * d * 2 * 2 + F * 8 * S * 4
+    res = {"path": "hoisted K/V projections (2 x tdb_gemm, all layers) + per-layer xattn_core_fwd_kernel", "frames": F, "tokens": S, "layers": nl,
+           "kv_proj_us_all_layers": us_proj, "kv_proj_algorithmic_tflops": flops / us_proj / 1e6,
+           "kv_proj_executed_tflops": 2 * flops / us_proj / 1e6, "kv_proj_algorithmic_bytes": bytes_proj,
+           "kv_proj_gbs": bytes_proj / us_proj / 1e3, "core_us_per_layer": us_core, "core_algorithmic_bytes": bytes_core,
+           "core_gbs": bytes_core / us_core / 1e3, "us_all_layers": us_proj + nl * us_core}
+    if peak_tflops:
+        res["kv_proj_executed_frac_of_tensor_peak"] = res["kv_proj_executed_tflops"] / peak_tflops
+    if peak_gbs:
+        res["kv_proj_frac_of_hbm_peak"] = res["kv_proj_gbs"] / peak_gbs
+        res["core_frac_of_hbm_peak"] = res["core_gbs"] / peak_gbs
+    return res
