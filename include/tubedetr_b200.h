@@ -203,6 +203,9 @@ int tdb_mha_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const
                    void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int Lq, int Lk,
                    float scale, void* stream);
 int tdb_mha_tc_supported(int H, int Lq, int Lk);
+/* measurement hook: buf = device int64 [16] (NULL = off); CTA 0 of subsequent tdb_mha_tc_bwd launches stores SM clock stamps at its phase
+ * boundaries (kernel entry; per query tile: dPd ready, pass A done, pass B done, MMA2 done, epilogues done) */
+int tdb_mha_tc_set_timing_buffer(void* buf);
 /* pbar[b][i][j] = mean over heads of p[b][h][i][j] (the weights nn.MultiheadAttention returns) */
 int tdb_head_mean(const float* p, float* pbar, int B, int H, int Lq, int Lk, void* stream);
 int tdb_mha_set_tc(int on);

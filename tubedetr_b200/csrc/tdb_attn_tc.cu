@@ -366,6 +366,7 @@ struct TcBwdParams {
   long long lddq, lddk, lddv;
   int B, H, Lq, Lk, LKP, MT, KT, nblk, v_reload;
   float scale;
+  long long* stamps;    // measurement hook (null = off): CTA 0 stores SM clock stamps at its phase boundaries, [16] int64
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -487,8 +488,11 @@ mha_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int row0 = mt * 128 + wq * 32;
       const bool valid = i < a.Lq;
       const long long prow = (bh * a.Lq + i) * a.Lk;
+      const bool stamp = a.stamps && blockIdx.x == 0 && r == 0;
+      if (stamp && it == 0) a.stamps[0] = clock64();
       mbar_wait(&sh.s_full, ph, 56);
       tc_fence_after();
+      if (stamp) a.stamps[1 + 6 * it] = clock64();          // dPd ready (loads + MMA1)
       if (row0 >= a.Lq) {
         // no row of this warp is inside the sequence: its dS / Pd rows must be ZERO (they are summed over by the dK / dV MMAs)
         float z[32];
@@ -540,6 +544,7 @@ mha_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           store_swizzled_row32(sDS, r, c, pj);
         }
         tmem_st_wait();
+        if (stamp) a.stamps[2 + 6 * it] = clock64();        // pass A done
         // pass B: dS = scale P (d - rs) as bf16 over the parked probabilities (zero rows / columns outside the sequence: P = 0)
         for (int c = 0; c < nch; ++c) {
           uint32_t v[32];
@@ -562,12 +567,14 @@ mha_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
       }
+      if (stamp) a.stamps[3 + 6 * it] = clock64();          // pass B done
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&sh.p_full);
       // ---- dQ epilogue
       mbar_wait(&sh.mma2_done, ph, 57);
       tc_fence_after();
+      if (stamp) a.stamps[4 + 6 * it] = clock64();          // MMA2 (dQ, dK, dV) done
       {
         uint32_t v[32];
         tmem_ld_32x32(lane_addr + e * 32, v);
@@ -587,6 +594,7 @@ mha_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (j < a.Lk) store_row32_bf16(a.dv + ((long long)b * a.Lk + j) * a.lddv + h * 32, v);
         }
       }
+      if (stamp) a.stamps[5 + 6 * it] = clock64();          // epilogues done
       tc_fence_before();
       mbar_arrive(&sh.dq_free);
     }
@@ -604,6 +612,11 @@ mha_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 using namespace tdb;
 
+static long long* g_mha_tc_stamps = nullptr;
+extern "C" int tdb_mha_tc_set_timing_buffer(void* buf) {      // measurement hook: device int64 [16] (NULL = off), see TcBwdParams::stamps
+  g_mha_tc_stamps = (long long*)buf;
+  return TDB_OK;
+}
 static int g_mha_tc = -1;
 extern "C" int tdb_mha_set_tc(int level) {      // 0 = CUDA-core kernels, 1 = tcgen05 forward, 2 = tcgen05 forward + backward
   g_mha_tc = level < 0 ? 0 : (level > 2 ? 2 : level);
@@ -700,6 +713,7 @@ extern "C" int tdb_mha_tc_bwd(const void* q, int64_t ldq, const void* k, int64_t
   a.KT = (a.LKP + 127) / 128;
   a.nblk = (a.LKP + 63) / 64;
   a.scale = scale;
+  a.stamps = g_mha_tc_stamps;
   CUtensorMap tmQ, tmK, tmV, tmdO;
   if ((rc = tdb_make_tmap_bf16(&tmQ, q, (int64_t)B * Lq, (int64_t)H * 32, ldq, 128))) return rc;
   if ((rc = tdb_make_tmap_bf16(&tmdO, dout, (int64_t)B * Lq, (int64_t)H * 32, lddo, 128))) return rc;
