@@ -165,6 +165,7 @@ def build_everything(device, seed=0):
     torch.backends.cuda.matmul.allow_tf32 = True
     model.fast_l2_chunk = int(os.environ.get("TDB_L2_CHUNK", "0")) or None     # experiment switches, defaults are the measured best
     model.joint_backbone = os.environ.get("TDB_JOINT", "1") != "0"
+    model.text_side_stream = os.environ.get("TDB_TEXT_SIDE", "1") != "0"
     torch.backends.cudnn.allow_tf32 = True
     return model.to(device).train(), crit, wd     # a real training step: every dropout of the reference is active
 

@@ -294,6 +294,12 @@ int tdb_head_out_fwd(const void* x, const float* W, const float* b, float* y, in
 int tdb_head_out_bwd(const float* dy, const float* y, const void* x, const float* W, float* dpre, void* dx, float* dW, float* db, int R, int J,
                      int act, int mask_dx, float dx_scale, const int64_t* drop_seed, int64_t drop_site, float drop_p, void* stream);
 
+/* Input pipeline on the GPU (reference datasets/vidstg.py:104-116, datasets/video_transforms.py, util/misc.py:142-172):
+ * decoded rgb24 frames src [T][H0][W0][3] uint8 -> bilinear resize to H x W (half-pixel centres), / 255, (x - mean) / std, written as fp32
+ * [T][3][Hp][Wp] into a padded batch slot (zeros outside H x W); mask [T][Hp][Wp] (1 = padding) may be NULL.  mean3 / std3: HOST floats. */
+int tdb_frames_preprocess(const uint8_t* src, float* dst, uint8_t* mask, int T, int H0, int W0, int H, int W, int Hp, int Wp,
+                          const float* mean3, const float* std3, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Text encoder (RoBERTa-base; reference models/transformer.py:130-135, 250-263 calls HF RobertaModel): linear layers on
  * tdb_gemm, LayerNorm + residual (+ dropout) on tdb_layernorm_* (D = 768), and the small kernels below (tdb_text.cu).

@@ -733,3 +733,28 @@ def test_encoder_glue_kernels_match_torch(B, T, k, HW, L):
         rr2 = torch.autograd.grad((r_mem.reshape(B * T * S, D) * (v2.float() + v3.float())).sum(), leaves)
         for a_, c_ in zip(gg2, rr2):
             torch.testing.assert_close(a_, c_, atol=1e-4, rtol=1e-5)
+
+
+def test_frames_preprocess_matches_torch_pipeline():
+    """GPU input pipeline (tubedetr_b200/preprocess.py: resize + /255 + normalise + pad-and-pack in one kernel per clip) vs the same steps
+    in torch (bilinear, half-pixel centres), ragged clips, stride-2 slow frames"""
+    from tubedetr_b200 import preprocess as P
+    g = torch.Generator().manual_seed(9)
+    clips = [torch.randint(0, 256, (5, 72, 128, 3), generator=g, dtype=torch.uint8), torch.randint(0, 256, (4, 90, 60, 3), generator=g, dtype=torch.uint8)]
+    fast, slow = P.clips_to_nested(clips, size=48, max_size=96, stride=2)
+    sizes = [P.target_size(c.shape[1], c.shape[2], 48, 96) for c in clips]
+    assert sizes == [(48, 85), (72, 48)]
+    Hp, Wp = 72, 85
+    assert fast.tensors.shape == (9, 3, Hp, Wp) and slow.tensors.shape == (5, 3, Hp, Wp)
+    mean, std = torch.tensor(P.MEAN).view(1, 3, 1, 1), torch.tensor(P.STD).view(1, 3, 1, 1)
+    o = 0
+    for c, (h, w) in zip(clips, sizes):
+        x = c.permute(0, 3, 1, 2).float()
+        ref = (F.interpolate(x, size=(h, w), mode="bilinear", align_corners=False) / 255.0 - mean) / std
+        got = fast.tensors[o:o + c.shape[0]].cpu()
+        assert (got[:, :, :h, :w] - ref).abs().max().item() < 2e-4
+        assert (got[:, :, h:, :] == 0).all() and (got[:, :, :, w:] == 0).all()
+        m = fast.mask[o:o + c.shape[0]].cpu()
+        assert not m[:, :h, :w].any() and m[:, h:, :].all() and m[:, :, w:].all()
+        o += c.shape[0]
+    assert torch.equal(slow.tensors[:3], fast.tensors[0:5:2]) and torch.equal(slow.tensors[3:], fast.tensors[5:9:2])

@@ -395,3 +395,49 @@ extern "C" int tdb_head_out_bwd(const float* dy, const float* y, const void* x, 
   tdb_count_launch(2);
   return TDB_OK;
 }
+
+// ------------------------------------------------------------------ input pipeline: decoded frames -> model input
+// Reference datasets/vidstg.py:104-116 + datasets/video_transforms.py (resize -> ToTensor (/255) -> Normalize(mean, std)) + util/misc.py:
+// 142-172 (pad-and-pack into a NestedTensor) run on the CPU per frame.  Here ONE kernel takes the decoder's packed rgb24 frames
+// [T][H0][W0][3] uint8 and writes the resized (bilinear, half-pixel centres = cv2.INTER_LINEAR / F.interpolate(align_corners=False)),
+// scaled and normalised fp32 frames straight into their slot [T][3][Hp][Wp] of the padded batch tensor, zero padding and pad mask included.
+namespace tdb {
+__global__ void __launch_bounds__(256) frames_preprocess_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, uint8_t* __restrict__ mask,
+                                                                int T, int H0, int W0, int H, int W, int Hp, int Wp, float m0, float m1, float m2,
+                                                                float is0, float is1, float is2) {
+  pdl_wait();
+  pdl_trigger();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * Hp * Wp) return;
+  const int x = (int)(idx % Wp), y = (int)((idx / Wp) % Hp), t = (int)(idx / ((long long)Wp * Hp));
+  float o[3] = {0.f, 0.f, 0.f};
+  const bool inside = y < H && x < W;
+  if (inside) {
+    const float sy = ((float)y + 0.5f) * ((float)H0 / (float)H) - 0.5f, sx = ((float)x + 0.5f) * ((float)W0 / (float)W) - 0.5f;
+    const float fy = fmaxf(sy, 0.f), fx = fmaxf(sx, 0.f);
+    const int y0 = min((int)fy, H0 - 1), x0 = min((int)fx, W0 - 1);
+    const int y1 = min(y0 + 1, H0 - 1), x1 = min(x0 + 1, W0 - 1);
+    const float wy = fy - (float)y0, wx = fx - (float)x0;
+    const uint8_t* f = src + (long long)t * H0 * W0 * 3;
+    const float mean[3] = {m0, m1, m2}, istd[3] = {is0, is1, is2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float a = f[((long long)y0 * W0 + x0) * 3 + c], b = f[((long long)y0 * W0 + x1) * 3 + c];
+      const float cc = f[((long long)y1 * W0 + x0) * 3 + c], d = f[((long long)y1 * W0 + x1) * 3 + c];
+      const float v = (a * (1.f - wx) + b * wx) * (1.f - wy) + (cc * (1.f - wx) + d * wx) * wy;
+      o[c] = (v * (1.f / 255.f) - mean[c]) * istd[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dst[(((long long)t * 3 + c) * Hp + y) * Wp + x] = o[c];
+  if (mask) mask[idx] = inside ? 0 : 1;
+}
+}  // namespace tdb
+
+extern "C" int tdb_frames_preprocess(const uint8_t* src, float* dst, uint8_t* mask, int T, int H0, int W0, int H, int W, int Hp, int Wp,
+                                     const float* mean3, const float* std3, void* stream_) {
+  TDB_REQUIRE(src && dst && T > 0 && H0 > 0 && W0 > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W && mean3 && std3, "tdb_frames_preprocess: bad args");
+  TDB_CHECK_CUDA(tdb_launch(tdb::frames_preprocess_kernel, dim3(gblocks((long long)T * Hp * Wp)), dim3(256), 0, GSTREAM, src, dst, mask, T, H0, W0, H, W,
+                            Hp, Wp, mean3[0], mean3[1], mean3[2], 1.f / std3[0], 1.f / std3[1], 1.f / std3[2]));
+  GLAUNCH_OK();
+}

@@ -257,3 +257,9 @@ def text_attn_bwd(q, k, v, dout, p, dq, dk, dv, B, H, L, scale, drop=None):
     check(lib().tdb_text_attn_bwd(ptr(q), _i64(q.stride(0)), ptr(k), _i64(k.stride(0)), ptr(v), _i64(v.stride(0)), ptr(dout),
                                   _i64(dout.stride(0)), ptr(p), ptr(seed), _i64(site), _f(dp), ptr(dq), _i64(dq.stride(0)), ptr(dk),
                                   _i64(dk.stride(0)), ptr(dv), _i64(dv.stride(0)), B, H, L, _f(scale), stream_ptr()), "text_attn_bwd")
+
+
+def frames_preprocess(src_u8, dst, mask, T, H0, W0, H, W, Hp, Wp, mean, std):
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    sd = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib().tdb_frames_preprocess(ptr(src_u8), ptr(dst), ptr(mask), T, H0, W0, H, W, Hp, Wp, m, sd, stream_ptr()), "frames_preprocess")
