@@ -352,10 +352,15 @@ def kernel_probe(device, pk):
     flops = 2.0 * N * h * w * C * 9 * C           # algorithmic (un-haloed) conv FLOPs per launch
     ach = flops / (ms * 1e-3) / 1e12
     traffic, tsrc = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_gemm2_traffic.json")   # dram read+write bytes of this launch from ncu --set full
-    if os.path.exists(tp):
-        t = json.load(open(tp))
-        traffic, tsrc = t["dram_bytes_per_launch"], t["source"]
+    # dram read + write bytes of this launch from ncu --set full (captured under profiles/, tagged with the commit of the capture: the
+    # kernel source has not changed since; a run under a profiler cannot be the timed run)
+    for tp in ("r02_ncu_gemm2_traffic.json", "r01_ncu_gemm2_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tp):
+            t = json.load(open(tp))
+            traffic = t["dram_bytes_per_launch"]
+            tsrc = t["source"] + (f" @ {t['captured_at_commit']}" if "captured_at_commit" in t else " (round 1 capture)")
+            break
     return {"bound": "tensor", "kernel": f"tdb_gemm2_kernel (layer3 3x3 conv as implicit GEMM, cta_group::2 + halo tile, {N} frames)",
             "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic,
             "traffic_source": tsrc, "peak_source": pk["src"] + " cuBLAS bf16 burst", "ms_per_launch": ms,

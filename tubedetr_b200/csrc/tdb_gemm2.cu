@@ -481,7 +481,9 @@ int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
   // worthwhile only for deep reductions (the feed-bound regime) with enough tiles to fill the pairs, and when the
   // 256-row pair tile does not waste more than a quarter of its rows
   const long long kdepth = (splits > 1 ? (long long)kb_per_split * 64 : (long long)d->K * d->ntaps);
-  if (!forced && (kdepth < 512 || total < pairs / 2 || (long long)m_tiles * 256 * 3 > (long long)d->M * 4)) return 0;
+  static int min_k = -1;      // experiment switch: reduction depth from which the pair kernel is taken (default 512)
+  if (min_k < 0) { const char* e = getenv("TDB_GEMM2_MIN_K"); min_k = e ? atoi(e) : 512; }
+  if (!forced && (kdepth < min_k || total < pairs / 2 || (long long)m_tiles * 256 * 3 > (long long)d->M * 4)) return 0;
   static bool attr = false;
   if (!attr) {
     TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));

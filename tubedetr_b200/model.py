@@ -499,7 +499,8 @@ class TubeDETR(nn.Module):
         if side:
             tstream = _TEXT_STREAMS.get(dev)
             if tstream is None:
-                tstream = _TEXT_STREAMS[dev] = torch.cuda.Stream(device=dev, priority=-1)   # high: its tiny kernels slip in at GEMM boundaries
+                # high priority (default): its tiny kernels slip in at GEMM boundaries; TDB_TEXT_PRIO=0 = same priority as the main stream
+                tstream = _TEXT_STREAMS[dev] = torch.cuda.Stream(device=dev, priority=int(os.environ.get("TDB_TEXT_PRIO", "-1")))
             main = torch.cuda.current_stream(dev)
             tstream.wait_stream(main)
         with torch.cuda.stream(tstream if side else torch.cuda.current_stream(dev)):
