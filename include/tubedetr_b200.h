@@ -40,6 +40,7 @@ int64_t tdb_launch_count(void);
  *                                                wgrad: dY [pixels(K)][Cout(M)], X [pixels(K)][Cin(N)])
  * ------------------------------------------------------------------------------------------------ */
 #define TDB_MAX_TAPS 9
+#define TDB_GEMM_FLAG_DYNAMIC_TILES (1 << 11)
 enum { TDB_OUT_BF16 = 0, TDB_OUT_F32 = 1 };
 enum { TDB_REMAP_NONE = 0, TDB_REMAP_COMPACT_TO_PADDED = 1, TDB_REMAP_PADDED_TO_COMPACT = 2 };
 
@@ -72,7 +73,10 @@ typedef struct tdb_gemm_desc {
   /* tuning: 0 = auto */
   int32_t block_n; int32_t max_ctas;
   /* bring-up only: bit0 swaps LBO/SBO of MN-major operand descriptors; bits1-3 epilogue variant + 1; bit4 no stores;
-     bit6 force the 2-CTA kernel; bit7 disable its halo mode; bit8 set a descriptor base offset in halo mode (wrong on purpose) */
+     bit6 force the 2-CTA kernel; bit7 disable its halo mode; bit8 set a descriptor base offset in halo mode (wrong on purpose);
+     bit9 row-per-thread epilogue instead of the shared-memory-box epilogue of the 2-CTA kernel; bit10 never schedule dynamically.
+     Scheduling hint (not bring-up): TDB_GEMM_FLAG_DYNAMIC_TILES -- this launch runs next to other streams' kernels (collectives,
+     the text encoder): hand out tiles by cluster launch control (work stealing) instead of the static persistent schedule */
   int32_t debug_flags;
 } tdb_gemm_desc;
 
@@ -342,6 +346,10 @@ typedef struct tdb_loss_desc {
 } tdb_loss_desc;
 int tdb_criterion_fwd(const tdb_loss_desc* d, float* losses, void* stream);
 int tdb_criterion_bwd(const tdb_loss_desc* d, const float* grad_losses, float* d_boxes, float* d_sted, float* d_weights, void* stream);
+
+/* Measurement aid (no reference counterpart): a kernel of `ctas` CTAs with `smem_bytes` of dynamic shared memory each that spins for
+ * `cycles` SM clocks -- stands in for a foreign kernel (NCCL all-reduce, text encoder) holding SMs while a GEMM runs (tools/clc_hog.py). */
+int tdb_debug_spin(int ctas, int smem_bytes, long long cycles, void* stream);
 
 #ifdef __cplusplus
 }

@@ -153,20 +153,62 @@ def test_gemm_epilogue_variants(mode, M, N, K):
 TWO_CTA = 64  # debug flag: force the cta_group::2 kernel
 
 
+NO_TMA_EPI = 512  # debug flag: row-per-thread global epilogue instead of the TMA boxes (tdb_gemm2_kernel<0>)
+
+
+@pytest.mark.parametrize("flags", [TWO_CTA, TWO_CTA | NO_TMA_EPI])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 256, 512), (4096, 512, 1024), (300, 768, 256)])
-def test_gemm_2cta_plain_and_epilogue(M, N, K):
+def test_gemm_2cta_plain_and_epilogue(M, N, K, flags):
     from tubedetr_b200.gemm import gemm
     A, B, R, Mk = _rand((M, K), 31), _rand((N, K), 32), _rand((M, N), 33), _rand((M, N), 34)
     out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
-    gemm(A, B, out, M, N, K, debug_flags=TWO_CTA)
+    gemm(A, B, out, M, N, K, debug_flags=flags)
     torch.cuda.synchronize()
     _close(out, A.float() @ B.float().t())
     scale = torch.rand(N, device="cuda") + 0.5
     bias = torch.randn(N, device="cuda")
     ref = torch.relu((A.float() @ B.float().t()) * scale + bias + R.float()) * (Mk.float() > 0)
-    gemm(A, B, out, M, N, K, scale=scale, bias=bias, residual=R, relu=True, mask=Mk, debug_flags=TWO_CTA)
+    gemm(A, B, out, M, N, K, scale=scale, bias=bias, residual=R, relu=True, mask=Mk, debug_flags=flags)
     torch.cuda.synchronize()
     _close(out, ref)
+
+
+@pytest.mark.parametrize("M,N,K,res,relu,mask", [(60500, 1024, 256, True, True, False), (30001, 512, 128, True, True, False),
+                                                  (40000, 256, 64, True, True, False), (14100, 1536, 256, False, False, False),
+                                                  (12100, 1024, 256, True, False, True), (9999, 256, 1024, False, True, False),
+                                                  (2500, 2048, 256, False, True, False)])
+def test_gemm_2cta_tma_epilogue_is_bit_identical_to_the_row_epilogue(M, N, K, res, relu, mask):
+    """the TMA-box epilogue of the pair kernel (the backbone's 1x1 conv + FrozenBN + residual + ReLU shapes, the decoder's K/V projection,
+    the dgrad with residual + ReLU mask): many tiles per CTA pair (box recycling), ragged last tile, output written into a column
+    slice of a wider matrix, residual read from one; compared with fp32 torch and, bit for bit, with the row-per-thread epilogue"""
+    from tubedetr_b200.gemm import gemm
+    A, B = _rand((M, K), 51), _rand((N, K), 52)
+    Rw = _rand((M, N + 64), 53)
+    R = Rw[:, 64:] if res else None
+    Mk = _rand((M, N), 54) if mask else None
+    scale = torch.rand(N, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    wide = torch.full((M + 3, 2 * N), 7.0, dtype=torch.bfloat16, device="cuda")
+    out = wide[:M, N:]
+    out2 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    gemm(A, B, out, M, N, K, scale=scale, bias=bias, residual=R, relu=relu, mask=Mk, debug_flags=TWO_CTA)
+    gemm(A, B, out2, M, N, K, scale=scale, bias=bias, residual=R, relu=relu, mask=Mk, debug_flags=TWO_CTA | NO_TMA_EPI)
+    torch.cuda.synchronize()
+    ref = (A.float() @ B.float().t()) * scale + bias
+    if res:
+        ref = ref + R.float()
+    if relu:
+        ref = torch.relu(ref)
+    if mask:
+        ref = ref * (Mk.float() > 0)
+    _close(out, ref)
+    assert torch.equal(out, out2)
+    assert bool((wide[:M, :N] == 7.0).all()) and bool((wide[M:] == 7.0).all()), "the TMA store wrote outside its column slice / row range"
+    # the default routing (no debug flag) must agree as well, whichever kernel it picks
+    out3 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    gemm(A, B, out3, M, N, K, scale=scale, bias=bias, residual=R, relu=relu, mask=Mk)
+    torch.cuda.synchronize()
+    _close(out3, ref)
 
 
 def test_gemm_2cta_dgrad_and_implicit_conv():
@@ -247,3 +289,107 @@ def test_gemm_split_precision_weights_two_taps(M, N, K, relu, f32):
         assert e2 < 0.1 * e1
     else:
         _close(out, ref, 6e-3)                                              # bf16 output rounding only
+
+
+@pytest.mark.parametrize("frames,H,W,C,N,bmaj,mask", [(20, 22, 22, 1024, 256, 0, False), (9, 11, 11, 2048, 512, 0, False),
+                                                      (7, 22, 22, 1024, 256, 1, True)])
+def test_gemm_2cta_copy_out_compact_to_padded(frames, H, W, C, N, bmaj, mask):
+    """1x1 conv (or its dgrad with ReLU mask) whose rows go into the zero-haloed pixel grid of the following 3x3 conv: the pair
+    kernel's shared-memory-box epilogue with the coalesced copy-out == the row-per-thread epilogue, halo rows untouched"""
+    from tubedetr_b200.gemm import REMAP_C2P, gemm
+    M = frames * H * W
+    A = _rand((M, C), 61)
+    B = (_rand((C, N), 62) if bmaj else _rand((N, C), 62)) * 0.05
+    Mk = _rand((M, N), 63) if mask else None
+    scale = torch.rand(N, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    Rp = frames * (H + 2) * (W + 2)
+    outs = []
+    for fl in (TWO_CTA, TWO_CTA | NO_TMA_EPI, 0):
+        o = torch.zeros(Rp, N, dtype=torch.bfloat16, device="cuda")
+        gemm(A, B, o, M, N, C, b_major=bmaj, scale=scale, bias=bias, relu=not mask, mask=Mk, remap=REMAP_C2P, img_hw=(H, W), debug_flags=fl)
+        outs.append(o)
+    torch.cuda.synchronize()
+    ref = (A.float() @ (B.float() if bmaj else B.float().t())) * scale + bias
+    ref = ref * (Mk.float() > 0) if mask else torch.relu(ref)
+    got = outs[0].view(frames, H + 2, W + 2, N)
+    _close(got[:, 1:-1, 1:-1].reshape(M, N), ref)
+    halo = got.clone()
+    halo[:, 1:-1, 1:-1] = 0
+    assert not bool(halo.any()), "halo rows of the padded grid were written"
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("frames,H,W,C,bmaj,mask", [(12, 22, 22, 256, 0, False), (10, 11, 11, 512, 0, False), (5, 22, 22, 256, 1, True)])
+def test_gemm_2cta_copy_out_implicit_conv_padded_to_compact(frames, H, W, C, bmaj, mask):
+    """3x3 conv over the zero-haloed grid (halo A tile, 9 taps) -> compact rows, fprop and dgrad form, box epilogue == row epilogue"""
+    from tubedetr_b200.gemm import REMAP_P2C, gemm
+    x = _rand((frames, H, W, C), 71)
+    xp = _pad_rows(x)
+    Rp = xp.shape[0]
+    Bm = _rand((C, 9 * C), 72) * 0.05
+    Mk = _rand((Rp, C), 73) if mask else None
+    taps = [(kh - 1) * (W + 2) + (kw - 1) for kh in range(3) for kw in range(3)]
+    outs = []
+    for fl in (TWO_CTA, TWO_CTA | NO_TMA_EPI, 0):
+        o = torch.full((frames * H * W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+        gemm(xp, Bm, o, Rp, C, C, b_major=bmaj, ntaps=9, a_off1=taps, b_off0=[t * C for t in range(9)], relu=not mask, mask=Mk,
+             remap=REMAP_P2C, img_hw=(H, W), debug_flags=fl)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    _close(outs[2], outs[0])          # the default route may be the 1-CTA kernel (other tap order in the fp32 sum): close, not equal
+    assert bool(torch.isfinite(outs[0].float()).all())
+    if not bmaj and not mask:
+        w = Bm.view(C, 3, 3, C).permute(0, 3, 1, 2).float()
+        ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w, padding=1)).permute(0, 2, 3, 1).reshape(-1, C)
+        _close(outs[0], ref)
+
+
+DYNAMIC_TILES = 2048  # TDB_GEMM_FLAG_DYNAMIC_TILES: cluster launch control (work stealing) instead of the static schedule (tile += grid)
+
+
+@pytest.mark.parametrize("M,N,K,res,f32,flags", [(20000, 64, 64, False, False, 0), (60500, 1024, 256, True, False, 0), (60500, 256, 1024, False, False, 0),
+                                                   (3525, 256, 2048, False, True, 0), (9000, 512, 512, True, False, TWO_CTA), (300, 128, 192, False, False, 0),
+                                                   (129, 64, 64, False, False, 0)])
+def test_gemm_work_stealing_schedule_equals_static_schedule(M, N, K, res, f32, flags):
+    """cluster launch control (one CTA / cluster per tile, resident ones steal the rest) must produce exactly what the static
+    persistent schedule produces: every tile computed once, by whichever CTA"""
+    from tubedetr_b200.gemm import gemm
+    A, B = _rand((M, K), 81), _rand((N, K), 82)
+    R = _rand((M, N), 83) if res else None
+    scale = torch.rand(N, device="cuda") + 0.5
+    bias = torch.randn(N, device="cuda")
+    dt = torch.float32 if f32 else torch.bfloat16
+    o1 = torch.full((M, N), float("nan"), dtype=dt, device="cuda")
+    o2 = torch.full((M, N), float("nan"), dtype=dt, device="cuda")
+    for _ in range(3):      # several launches back to back: the response ring / barriers of one launch must not leak into the next
+        gemm(A, B, o1, M, N, K, scale=scale, bias=bias, residual=R, relu=True, debug_flags=flags | DYNAMIC_TILES)
+    gemm(A, B, o2, M, N, K, scale=scale, bias=bias, residual=R, relu=True, debug_flags=flags)
+    torch.cuda.synchronize()
+    ref = (A.float() @ B.float().t()) * scale + bias
+    if res:
+        ref = ref + R.float()
+    _close(o1, torch.relu(ref), tol=2e-2 if not f32 else 2e-3)
+    assert torch.equal(o1, o2)
+
+
+def test_gemm_work_stealing_with_a_foreign_kernel_holding_sms():
+    """a spin kernel occupies 24 SMs on another stream while the GEMM runs: results unchanged (CTAs that start late take what is left)"""
+    import ctypes as C
+    from tubedetr_b200 import _lib
+    from tubedetr_b200.gemm import gemm
+    M, N, K = 60500, 256, 1024
+    A, B = _rand((M, K), 91), _rand((N, K), 92)
+    o1 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    o2 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    gemm(A, B, o2, M, N, K)
+    torch.cuda.synchronize()
+    lib = _lib.lib()
+    lib.tdb_debug_spin.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_void_p]
+    side = torch.cuda.Stream()
+    _lib.check(lib.tdb_debug_spin(24, 200 * 1024, 1_000_000, C.c_void_p(side.cuda_stream)), "spin")
+    for _ in range(4):
+        gemm(A, B, o1, M, N, K, debug_flags=DYNAMIC_TILES)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)

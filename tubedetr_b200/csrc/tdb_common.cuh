@@ -214,6 +214,101 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------ cluster launch control: hardware work stealing (sm_100)
+// A grid is launched with ONE cluster per tile.  A resident cluster finishes its own tile, then asks the launch hardware to CANCEL a
+// cluster that has not started yet and takes over that cluster's tile (its ctaid comes back in a 16-byte response, delivered through
+// the async proxy with mbarrier complete_tx -- with .multicast::cluster::all to the same shared-memory offset of every CTA of the
+// cluster).  The first failed request means no work is left.  Unlike a static `tile += gridDim` schedule, SMs that are busy with
+// another stream's kernels (NCCL, the text encoder) when the GEMM starts simply take fewer tiles instead of starting late and
+// running their full share after everybody else has finished.
+__device__ __forceinline__ void clc_try_cancel(void* resp, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(smem_u32(resp)),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void clc_try_cancel_mc(void* resp, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];" ::"r"(
+          smem_u32(resp)),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+// -> ctaid.x of the cancelled cluster's first CTA, or -1 when the request failed (nothing left to steal)
+__device__ __forceinline__ int clc_query(const void* resp) {
+  uint32_t valid, cx, cy, cz;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%4];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %3, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n\t}"
+      : "=r"(cx), "=r"(cy), "=r"(cz), "=r"(valid)
+      : "r"(smem_u32(resp))
+      : "memory");
+  (void)cy;
+  (void)cz;
+  return valid ? (int)cx : -1;
+}
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+constexpr int kClcStages = 8;
+struct ClcShared {                 // 256 bytes, 16-byte aligned
+  uint4 resp[kClcStages];
+  uint64_t full[kClcStages];       // response landed (every CTA of the cluster has its own)
+  uint64_t empty[kClcStages];      // response read by every consumer warp of the cluster (the leader CTA's copy is the one used)
+};
+// Per-warp cursor over the tile sequence of its cluster.  Static mode: tile += stride.  CLC mode: the next tile is whatever the
+// scheduler warp's cancellation request returned; every consumer warp of the cluster walks the same response ring.
+struct TileCursor {
+  ClcShared* q;
+  int clc, stride, id_shift, s, unit, j, total;     // unit = tiles per claimed cluster id (consecutive tile indices)
+  uint32_t ph, leader_empty0;      // cluster address of the leader CTA's empty[0]
+  __device__ __forceinline__ void init(ClcShared* q_, int clc_, int stride_, int shift, int unit_, int total_) {
+    q = q_; clc = clc_; stride = stride_; id_shift = shift; unit = unit_; total = total_; s = 0; ph = 0; j = 0;
+    uint32_t a = smem_u32(&q_->empty[0]), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(0u));
+    leader_empty0 = r;
+  }
+  // first tile of this CTA / cluster (id = blockIdx.x >> id_shift)
+  __device__ __forceinline__ int first(int id) const { return clc ? id * unit : id; }
+  // Leader CTA's producer warp only, at the top of every tile: at the first tile of a unit, claim ONE unit ahead (the response is
+  // read by next() when this unit is exhausted), so that a cluster never hoards more than the unit its producer will prefetch next.
+  // A unit is sized (host side) to outlast the ~2 us round trip of the request.  The ring is deeper (kClcStages) only because the
+  // slower consumer warps (epilogue) read their copy of a response several tiles after the producer did.  Never called again
+  // after a failed request (the tile loop ends on it).
+  __device__ __forceinline__ void request(int cluster_size) {
+    if (!clc || j != 0) return;
+    mbar_wait(&q->empty[s], ph ^ 1, 41);
+    const uint32_t lane = threadIdx.x & 31;
+    if ((int)lane < cluster_size) {
+      uint32_t a = smem_u32(&q->full[s]), r;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(lane));
+      mbar_expect_tx_remote(r, 16);
+    }
+    __syncwarp();
+    if (elect_one()) {
+      if (cluster_size > 1) clc_try_cancel_mc(&q->resp[s], &q->full[s]);
+      else clc_try_cancel(&q->resp[s], &q->full[s]);
+    }
+    __syncwarp();
+  }
+  // warp-collective (all 32 lanes call it); returns the next tile or INT_MAX
+  __device__ __forceinline__ int next(int w) {
+    if (!clc) return w + stride;
+    if (++j < unit && w + 1 < total) return w + 1;
+    j = 0;
+    mbar_wait(&q->full[s], ph, 40);
+    const int x = clc_query(&q->resp[s]);
+    fence_proxy_async();           // my generic-proxy read of the response is ordered before the async-proxy write that recycles it
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_empty0 + (uint32_t)s * 8u) : "memory");
+    if (++s == kClcStages) { s = 0; ph ^= 1; }
+    return x < 0 ? 0x7fffffff : (x >> id_shift) * unit;
+  }
+};
+
 // ------------------------------------------------------------------ small numeric helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

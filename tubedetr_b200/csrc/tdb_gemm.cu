@@ -48,6 +48,7 @@ struct GemmKParams {
   long long ldo;
   int remap, img_h, img_w;
   int debug_flags;
+  int clc, clc_unit;     // 1: one CTA per `clc_unit` tiles + cluster launch control (work stealing, tdb_common.cuh) instead of the static persistent schedule
   int epi_mode;
   // halo mode (see tdb_gemm2.cu): one row-haloed A tile per k-block serves all taps; B either streams through a ring of
   // BN x 64 stages or, when every (tap, k-block) slice fits next to the A tiles, is loaded once and stays resident
@@ -64,7 +65,7 @@ struct GemmCfg {
   static constexpr int kOperandSlots = (EPI == 4) ? 2 : (EPI == 5 ? 3 : 0);
   static constexpr int kOperandBytes = kOperandSlots * BM * BN * 2;
   static constexpr int kStagingBytes = (EPI == 5) ? 1024 : 4 * 32 * 64 * 4;  // per epilogue warp 32 x 64 fp32 (mode 5: shared scale/bias)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOperandBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kStagingBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOperandBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kStagingBytes + 256 /*ClcShared*/;
 };
 
 struct WorkItem {
@@ -114,6 +115,7 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* afull_bar = oempty_bar + 3;             // [4] halo mode: row-haloed A tile landed
   uint64_t* aempty_bar = afull_bar + 4;             // [4] ... and consumed by all taps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
+  ClcShared* clcq = reinterpret_cast<ClcShared*>(after + 512 + Cfg::kStagingBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -139,6 +141,10 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&afull_bar[s], 1);
       mbar_init(&aempty_bar[s], 1);
     }
+    for (int s = 0; s < kClcStages; ++s) {     // consumers: producer + MMA + 4 epilogue warps
+      mbar_init(&clcq->full[s], 1);
+      mbar_init(&clcq->empty[s], 6);
+    }
     if (EPI == 5) tma_prefetch_desc(&tmO);
     fence_barrier_init();
   }
@@ -152,6 +158,8 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // everything above overlapped the previous kernel's tail; from here on we read what it wrote
   pdl_trigger();
+  TileCursor cur;
+  cur.init(clcq, p.clc, (int)gridDim.x, 0, p.clc_unit, p.total_work);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -162,13 +170,14 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int oslot = 0;
       uint32_t ophase = 0;
-      if (EPI == 3 && p.halo) {
+      if ((EPI == 3 || EPI == 1) && p.halo) {
         uint8_t* bring = smem + p.na_stages * p.a_tile_bytes;
         constexpr int kBStage = BN * 128;
         int sa = 0;
         uint32_t pa = 0;
         bool first = true;
-        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        for (int w = cur.first((int)blockIdx.x); w < p.total_work; w = cur.next(w)) {
+          cur.request(1);
           const WorkItem wi = decode_work(p, w, BN);
           if (p.b_resident && first) {       // all (k-block, tap) weight slices once; they stay for every tile of this CTA
             first = false;
@@ -227,7 +236,8 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       } else
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      for (int w = cur.first((int)blockIdx.x); w < p.total_work; w = cur.next(w)) {
+        cur.request(1);
         const WorkItem wi = decode_work(p, w, BN);
         if constexpr (EPI == 5) {
           if (p.residual != nullptr) {      // residual tile, two tiles ahead of the epilogue (3 slots)
@@ -312,13 +322,13 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (EPI == 3 && p.halo) {
+      if ((EPI == 3 || EPI == 1) && p.halo) {
         const uint32_t bring = smem_base + p.na_stages * p.a_tile_bytes;
         constexpr uint32_t kBStage = BN * 128;
         int sa = 0;
         uint32_t pa = 0;
         bool first = true;
-        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        for (int w = cur.first((int)blockIdx.x); w < p.total_work; w = cur.next(w)) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
           const uint32_t d_tmem = tmem_base + acc * BN;
           if (p.b_resident && first) {
@@ -366,7 +376,7 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
       } else
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      for (int w = cur.first((int)blockIdx.x); w < p.total_work; w = cur.next(w)) {
         const WorkItem wi = decode_work(p, w, BN);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
@@ -406,7 +416,7 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     const int Hp = p.img_h + 2, Wp = p.img_w + 2;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    for (int w = cur.first((int)blockIdx.x); w < p.total_work; w = cur.next(w)) {
       const WorkItem wi = decode_work(p, w, BN);
       const int row_t = wi.m0 + wq * 32 + lane;
       bool valid = row_t < p.M;
@@ -1236,6 +1246,23 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   p.remap = d->remap; p.img_h = d->img_h; p.img_w = d->img_w;
   p.debug_flags = d->debug_flags;
   p.epi_mode = epi_mode;
+  {
+    // cluster launch control (see tdb_gemm2.cu for the policy): units of tiles sized to outlast the request's round trip
+    static int clc_on = -1;
+    if (clc_on < 0) { const char* e = getenv("TDB_CLC"); clc_on = e ? atoi(e) : 1; }
+    const bool want_clc = clc_on == 2 || (clc_on == 1 && ((d->debug_flags >> 11) & 1));
+    p.clc = 0;
+    p.clc_unit = 1;
+    if (want_clc && !((d->debug_flags >> 10) & 1) && total > g_num_sms) {
+      const double tile_us = (bn == 256 ? 0.27 : (bn == 128 ? 0.14 : 0.09)) * (double)(splits > 1 ? kb_per_split : kb * d->ntaps) + (bn >= 128 ? 1.5 : 1.0);
+      int unit = (int)(6.0 / tile_us + 0.999);
+      const int cap = (int)(total / (4 * g_num_sms));
+      if (unit > cap) unit = cap;
+      if (unit < 1) unit = 1;
+      p.clc = 1;
+      p.clc_unit = unit;
+    }
+  }
   TDB_REQUIRE(p.ldo % 8 == 0 && (!p.residual || p.ldr % 8 == 0) && (!p.mask || p.ldmask % 8 == 0), "tdb_gemm: leading dims must be multiples of 8");
   {
     int r2 = tdb_gemm2_try(d, stream_);   // 2-CTA (cta_group::2) path for the feed-bound deep-K shapes
@@ -1248,7 +1275,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   {
     static int halo_ok = -1;
     if (halo_ok < 0) { const char* e = getenv("TDB_GEMM_HALO"); halo_ok = e ? atoi(e) : 1; }
-    if (halo_ok && !((d->debug_flags >> 7) & 1) && p.epi_mode == 3 && p.a_major == 0 && d->ntaps > 1 && splits == 1 && nz == 1) {
+    if (halo_ok && !((d->debug_flags >> 7) & 1) && (p.epi_mode == 3 || p.epi_mode == 1) && p.a_major == 0 && d->ntaps > 1 && splits == 1 && nz == 1) {
       int lo = d->a_off1[0], hi = d->a_off1[0];
       bool same_cols = true;
       for (int i = 1; i < d->ntaps; ++i) {
@@ -1317,6 +1344,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   auto launch = [&](int bn_, const CUtensorMap& tmB_, const GemmKParams& q) -> int {
     int grid = q.total_work < g_num_sms ? q.total_work : g_num_sms;
     if (d->max_ctas > 0 && grid > d->max_ctas) grid = d->max_ctas;
+    if (q.clc) grid = (q.total_work + q.clc_unit - 1) / q.clc_unit;    // one CTA per unit; resident CTAs steal the units of CTAs that have not started
 #define TDB_LAUNCH(BN_, EPI_) TDB_CHECK_CUDA(tdb_launch(tdb_gemm_kernel<BN_, EPI_>, dim3(grid), dim3(kGemmThreads), GemmCfg<BN_, EPI_>::kSmemBytes, stream, tmA, tmB_, tmR, tmO, q))
     if (q.epi_mode == 0) {
       switch (bn_) {

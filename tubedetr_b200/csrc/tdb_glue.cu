@@ -441,3 +441,23 @@ extern "C" int tdb_frames_preprocess(const uint8_t* src, float* dst, uint8_t* ma
                             Hp, Wp, mean3[0], mean3[1], mean3[2], 1.f / std3[0], 1.f / std3[1], 1.f / std3[2]));
   GLAUNCH_OK();
 }
+
+// ------------------------------------------------------------------ measurement aid: occupy `ctas` SMs for `cycles` SM clocks
+// (tools/clc_hog.py: how a GEMM behaves while another stream's kernel -- an NCCL all-reduce, the text encoder -- holds some SMs)
+namespace tdb {
+__global__ void __launch_bounds__(256) debug_spin_kernel(long long cycles, int* sink) {
+  extern __shared__ uint8_t spin_smem[];
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+  if (sink && cycles < 0) sink[0] = spin_smem[threadIdx.x];
+}
+}  // namespace tdb
+
+extern "C" int tdb_debug_spin(int ctas, int smem_bytes, long long cycles, void* stream_) {
+  TDB_REQUIRE(ctas > 0 && smem_bytes >= 0 && smem_bytes <= 200 * 1024 && cycles >= 0 && cycles < 4000000000ll, "tdb_debug_spin: bad args");
+  TDB_CHECK_CUDA(cudaFuncSetAttribute(tdb::debug_spin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  tdb::debug_spin_kernel<<<ctas, 256, smem_bytes, (cudaStream_t)stream_>>>(cycles, nullptr);
+  TDB_CHECK_CUDA(cudaGetLastError());
+  return TDB_OK;
+}

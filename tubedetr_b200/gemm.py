@@ -7,6 +7,9 @@ from . import _lib
 from ._lib import GemmDesc, OUT_BF16, OUT_F32, REMAP_C2P, REMAP_NONE, REMAP_P2C  # noqa: F401
 
 
+DYNAMIC_TILES = 1 << 11     # TDB_GEMM_FLAG_DYNAMIC_TILES (include/tubedetr_b200.h)
+
+
 def _mat(t):
     assert t.dim() == 2 and t.dtype == torch.bfloat16 and t.is_cuda and t.stride(1) == 1, (t.shape, t.dtype, t.stride())
     return t.data_ptr(), t.shape[0], t.shape[1], t.stride(0)

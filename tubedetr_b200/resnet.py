@@ -15,7 +15,7 @@ import os
 import torch
 
 from . import kernels as K
-from .gemm import REMAP_C2P, REMAP_P2C, effective_splits, gemm, splitk_reduce
+from .gemm import DYNAMIC_TILES, REMAP_C2P, REMAP_P2C, effective_splits, gemm, splitk_reduce
 
 STAGES = ((64, 3, 1), (128, 4, 2), (256, 23, 2), (512, 3, 2))  # width, blocks, stride of first block
 BN_EPS = 1e-5
@@ -26,6 +26,21 @@ WGRAD_LAG = max(1, min(2, int(os.environ.get("TDB_WGRAD_LAG", "1"))))
 # stream, concurrent with the backbone backward) find idle SMs instead of delaying a GEMM CTA that needs a whole SM (0 = no cap)
 BWD_MAX_CTAS = int(os.environ.get("TDB_BB_BWD_MAX_CTAS", "0"))
 STEM_FUSED = os.environ.get("TDB_STEM_FUSED", "1") != "0"    # one kernel for conv1 + FrozenBN + ReLU + maxpool (tdb_stem.cu)
+
+
+def _dyn(env, auto):
+    """scheduling hint for the GEMMs of one pass: TDB_GEMM_FLAG_DYNAMIC_TILES (tiles handed out by cluster launch control, i.e. work
+    stealing) when that pass shares the GPU with other streams' kernels.  Measured on B200 (tools/clc_hog.py): +5 % on an idle GPU,
+    -25..45 % when 8-32 SMs are held by a foreign kernel, because a static persistent schedule makes the CTAs that start late run
+    their full share after everybody else has finished.  env: 0 / 1 / unset = `auto`."""
+    v = os.environ.get(env)
+    on = auto if v is None else v != "0"
+    return DYNAMIC_TILES if on else 0
+
+
+def _multi_rank():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
 def conv_out(h, k, s, p):
@@ -41,6 +56,7 @@ class ResNet101Engine:
         self._bn_key = None
         self.last_hw = None
         self.stage_callback = None   # callable(stage index) fired by backward() when a stage's weight gradients are all enqueued
+        self._bf = 0                 # scheduling hint of the current backward pass (see _dyn)
 
     def __deepcopy__(self, memo):  # EMA copies of the model (reference main.py:370) get a fresh, empty engine
         return ResNet101Engine()
@@ -198,6 +214,7 @@ class ResNet101Engine:
         """bottleneck stages li_lo..li_hi on pixel rows x [N*h*w, C].  out_into=(big, n0, Ntot): the last block writes its
         rows into rows [n0*ho*wo, ...) of a full-batch buffer (allocated on first use) instead of a private one."""
         x, h, w = xhw
+        ff = _dyn("TDB_CLC_FWD", False)        # the text encoder's forward runs beside this pass (side stream)
         nk = N if n_keep is None else n_keep
         ctx = {"N": nk, "blocks": [], "tag": tag, "gen": self._gen.get(tag)} if save else None
         big = None
@@ -221,19 +238,19 @@ class ResNet101Engine:
                 if stride == 1:
                     Rp = N * (h + 2) * (w + 2)
                     y1 = self.buf(btag + "y1p", (Rp, width), zero=True)
-                    gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, remap=REMAP_C2P, img_hw=(h, w))
+                    gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, remap=REMAP_C2P, img_hw=(h, w), debug_flags=ff)
                     y2 = self.buf(btag + "y2", (R, width))
                     wp = w + 2
                     taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
                     gemm(y1, w2, y2, Rp, width, width, ntaps=9, a_off1=taps, b_off0=[t * width for t in range(9)],
-                         scale=s2, bias=b2, relu=True, remap=REMAP_P2C, img_hw=(h, w))
+                         scale=s2, bias=b2, relu=True, remap=REMAP_P2C, img_hw=(h, w), debug_flags=ff)
                 else:
                     y1 = self.buf(btag + "y1", (R, width))
-                    gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True)
+                    gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, debug_flags=ff)
                     colb = self.buf(btag + "col", (Ro, 9 * width))
                     K.im2col3x3s2(y1, colb, N, h, w, width)
                     y2 = self.buf(btag + "y2", (Ro, width))
-                    gemm(colb, w2, y2, Ro, width, 9 * width, scale=s2, bias=b2, relu=True)
+                    gemm(colb, w2, y2, Ro, width, 9 * width, scale=s2, bias=b2, relu=True, debug_flags=ff)
                     rec["col"] = colb
                 if bi == 0:
                     wd, _, sd_, bd = W[name + "downsample.0"]
@@ -242,7 +259,7 @@ class ResNet101Engine:
                         xs = self.buf(btag + "xs", (Ro, cin))
                         K.subsample2(x, xs, N, h, w, cin)
                     idt = self.buf(btag + "idt", (Ro, cout))
-                    gemm(xs, wd, idt, Ro, cout, cin, scale=sd_, bias=bd)
+                    gemm(xs, wd, idt, Ro, cout, cin, scale=sd_, bias=bd, debug_flags=ff)
                     rec["xs"] = xs
                 else:
                     idt = x
@@ -255,7 +272,7 @@ class ResNet101Engine:
                 else:
                     # ping-pong the block output so the no-grad pass needs two buffers per stage
                     out = self.buf(f"{btag}out{0 if keep else bi % 2}", (Ro, cout))
-                gemm(y2, w3, out, Ro, cout, width, scale=s3, bias=b3, residual=idt, relu=True)
+                gemm(y2, w3, out, Ro, cout, width, scale=s3, bias=b3, residual=idt, relu=True, debug_flags=ff)
                 rec.update(y1=y1, y2=y2, out=out)
                 if keep:
                     if nk != N:      # differentiate the first nk frames only: row-prefix views of every saved activation
@@ -280,7 +297,7 @@ class ResNet101Engine:
         s = effective_splits(Kred, want)
         part = torch.empty(s, M, ntot, dtype=torch.float32, device=g.device)
         gemm(g, xin, part, M, Ncols, Kred, a_major=1, b_major=1, nz=nz, z_b_off1=z_b_off1,
-             z_out_col=[t * Ncols for t in range(9)] if nz else None, splits=want, max_ctas=BWD_MAX_CTAS)
+             z_out_col=[t * Ncols for t in range(9)] if nz else None, splits=want, max_ctas=BWD_MAX_CTAS, debug_flags=self._bf)
         splitk_reduce(part, s, M, ntot, out, rowscale=rowscale, taps=9 if (nz or taps == 9) else 1)
 
     def backward(self, ctx, W, g_out, grads, prefix="backbone.0.body."):
@@ -288,6 +305,7 @@ class ResNet101Engine:
         grads: dict name -> fp32 tensor (torch layout) written in place for every layer2-4 conv weight."""
         from .ops import wgrad_scope
         self.check_generation(ctx)
+        bf = self._bf = _dyn("TDB_CLC_BWD", _multi_rank())   # gradient all-reduces (and the text encoder's backward) run beside this pass
         N, tag = ctx["N"], ctx["tag"]
         blocks = ctx["blocks"]
         # Weight gradients run on a side stream, concurrent with the dgrad chain.  The scratch gradients are double buffered by
@@ -317,20 +335,20 @@ class ResNet101Engine:
                 wp = w + 2
                 taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
                 g2 = self.buf(f"{tag}:g2p{par}", (Rp, width), zero=True)
-                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=REMAP_C2P, img_hw=(h, w), max_ctas=BWD_MAX_CTAS)
+                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=REMAP_C2P, img_hw=(h, w), max_ctas=BWD_MAX_CTAS, debug_flags=bf)
                 # ---- conv2 (implicit 3x3 over the haloed grid)
                 with sc:
                     self._wgrad(g2, y1, width, width, Rp, s2, grads[prefix + name + "conv2.weight"], z_b_off1=taps)
                 g1 = self.buf(f"{tag}:g1{par}", (R, width))
                 gemm(g2, w2s, g1, Rp, width, width, b_major=1, ntaps=9, a_off1=[-t for t in taps],
-                     b_off0=[t * width for t in range(9)], mask=y1, remap=REMAP_P2C, img_hw=(h, w), max_ctas=BWD_MAX_CTAS)
+                     b_off0=[t * width for t in range(9)], mask=y1, remap=REMAP_P2C, img_hw=(h, w), max_ctas=BWD_MAX_CTAS, debug_flags=bf)
             else:
                 g2 = self.buf(f"{tag}:g2c{par}", (Ro, width))
-                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, max_ctas=BWD_MAX_CTAS)
+                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, max_ctas=BWD_MAX_CTAS, debug_flags=bf)
                 with sc:
                     self._wgrad(g2, r["col"], width, 9 * width, Ro, s2, grads[prefix + name + "conv2.weight"], taps=9)
                 dcol = self.buf(f"{tag}:dcol{par}", (Ro, 9 * width))
-                gemm(g2, w2s, dcol, Ro, 9 * width, width, b_major=1, max_ctas=BWD_MAX_CTAS)
+                gemm(g2, w2s, dcol, Ro, 9 * width, width, b_major=1, max_ctas=BWD_MAX_CTAS, debug_flags=bf)
                 g1 = self.buf(f"{tag}:g1{par}", (R, width))
                 K.col2im3x3s2_mask(dcol, y1, g1, N, h, w, width)
             # ---- conv1
@@ -343,7 +361,7 @@ class ResNet101Engine:
                     self._wgrad(g_out, r["xs"], cout, cin, Ro, sdn, grads[prefix + name + "downsample.0.weight"])
                 if not last:
                     dxs = self.buf(f"{tag}:dxs{par}", (Ro, cin))
-                    gemm(g_out, wds, dxs, Ro, cin, cout, b_major=1, max_ctas=BWD_MAX_CTAS)
+                    gemm(g_out, wds, dxs, Ro, cin, cout, b_major=1, max_ctas=BWD_MAX_CTAS, debug_flags=bf)
                     resid = dxs
                     if r["stride"] == 2:
                         resid = self.buf(f"{tag}:dxsu{par}", (R, cin))
@@ -358,7 +376,7 @@ class ResNet101Engine:
                 sc.join()
                 self.stage_callback(int(name[5]))
             gprev = self.buf(f"{tag}:gout{i % 3}", (R, cin))
-            gemm(g1, w1s, gprev, R, cin, width, b_major=1, residual=resid, mask=x, max_ctas=BWD_MAX_CTAS)
+            gemm(g1, w1s, gprev, R, cin, width, b_major=1, residual=resid, mask=x, max_ctas=BWD_MAX_CTAS, debug_flags=bf)
             g_out = gprev
             pending.append(sc.mark())
         sc.join()
