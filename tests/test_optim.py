@@ -123,3 +123,40 @@ def test_grad_norm_is_deterministic_and_accurate_gpu():
     assert out[0].item() == out[1].item()
     ref = g.double().norm().item()
     assert abs(out[0].item() - ref) / ref < 1e-6
+
+
+@pytest.mark.gpu
+def test_state_dict_round_trip_and_layout_check_gpu():
+    """moments + step survive a state_dict round trip into a fresh optimizer of the same model; a checkpoint whose flat-buffer
+    layout (names / offsets / sizes) differs is refused instead of being copied into the wrong parameters' moments"""
+    from tubedetr_b200.optim import FusedAdamWEMA
+    gen = torch.Generator().manual_seed(5)
+    shapes = [("transformer.decoder.w", (33, 2)), ("transformer.decoder.b", (5,)), ("backbone.0.body.w", (4, 1, 3, 3)),
+              ("transformer.text_encoder.w", (77,))]
+    init = [torch.randn(s, generator=gen) for _, s in shapes]
+    a = _Holder(shapes, init).cuda()
+    oa = FusedAdamWEMA(a, lr=3e-3, lr_backbone=1e-3, text_encoder_lr=2e-3, weight_decay=1e-2, max_norm=0.1)
+    for _ in range(2):
+        oa.zero_grad(set_to_none=True)
+        for p in a.ps:
+            p.grad = torch.randn(p.shape, generator=gen).cuda()
+        oa.step()
+    sd = oa.state_dict()
+    b = _Holder(shapes, [p.detach().cpu().clone() for p in a.ps]).cuda()
+    ob = FusedAdamWEMA(b, lr=3e-3, lr_backbone=1e-3, text_encoder_lr=2e-3, weight_decay=1e-2, max_norm=0.1)
+    ob.load_state_dict(sd)
+    assert ob.step_count == 2 and torch.equal(ob.exp_avg, oa.exp_avg) and torch.equal(ob.exp_avg_sq, oa.exp_avg_sq)
+    g = [torch.randn(p.shape, generator=gen).cuda() for p in a.ps]
+    for o, mdl in ((oa, a), (ob, b)):
+        o.zero_grad(set_to_none=True)
+        for p, gr in zip(mdl.ps, g):
+            p.grad = gr.clone()
+        o.step()
+    for pa, pb in zip(a.ps, b.ps):
+        assert torch.equal(pa, pb)
+    other = [("transformer.decoder.w", (33, 2)), ("transformer.decoder.b", (6,)), ("backbone.0.body.w", (4, 1, 3, 3)),
+             ("transformer.text_encoder.w", (76,))]
+    c = _Holder(other, [torch.randn(s, generator=gen) for _, s in other]).cuda()
+    oc = FusedAdamWEMA(c, max_norm=0.1)
+    with pytest.raises(ValueError, match="layout"):
+        oc.load_state_dict(sd)

@@ -17,6 +17,7 @@
 // and single-thread MMA issuer.  Persistent grid (one CTA per SM, 195 KB of shared memory).
 #include "../../include/tubedetr_b200.h"
 #include "tdb_common.cuh"
+#include <type_traits>
 
 void tdb_count_launch(int n);
 int tdb_init_once();
@@ -109,6 +110,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fused_kernel(const __grid_
   } else {
     const int p = tid & 127, half = tid >> 7;            // conv pixel row of the MMA tile, which half of the work of that row
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
+    // FrozenBN scale / shift of this thread's 32 channels stay in registers for the whole kernel (64 shared-memory loads per
+    // epilogue otherwise: the kernel is instruction-issue bound, profiles/r02_ncu_kernels.txt)
+    float rsc[32], rsh[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      rsc[i] = sScale[half * 32 + i];
+      rsh[i] = sShift[half * 32 + i];
+    }
     int g = 0;
     for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x) {
       const int n = tile / (a.tiles_x * a.tiles_y);
@@ -160,9 +169,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fused_kernel(const __grid_
           uint32_t w[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int ch = half * 32 + q4 * 8 + 2 * u;
-            float f0 = fmaxf(__uint_as_float(v[q4 * 8 + 2 * u]) * sScale[ch] + sShift[ch], 0.f);
-            float f1 = fmaxf(__uint_as_float(v[q4 * 8 + 2 * u + 1]) * sScale[ch + 1] + sShift[ch + 1], 0.f);
+            const int ch = q4 * 8 + 2 * u;
+            float f0 = fmaxf(fmaf(__uint_as_float(v[ch]), rsc[ch], rsh[ch]), 0.f);
+            float f1 = fmaxf(fmaf(__uint_as_float(v[ch + 1]), rsc[ch + 1], rsh[ch + 1]), 0.f);
             w[u] = ok ? pack_bf16x2(f0, f1) : 0u;
           }
           *reinterpret_cast<uint4*>(rowp + (((half * 4 + q4) ^ (cp & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -174,13 +183,26 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fused_kernel(const __grid_
         const int cp = m * 128 + p;
         if (cp < ST_NCP) {
           const int ry = cp / ST_CC, rx = cp - ry * ST_CC;
-          const int j0 = half * 11, j1 = half ? 21 : 11;
-          for (int j = j0; j < j1; ++j) {
-            const int c = j / 7, kh = j - c * 7;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(sPatch + (c * ST_IR + 2 * ry + kh) * ST_IP + 2 * rx);
-            const uint4 w = make_uint4(src[0], src[1], src[2], src[3]);
-            *reinterpret_cast<uint4*>(sA + (j >> 3) * 16384 + p * 128 + (((j & 7) ^ (p & 7)) * 16)) = w;
-          }
+          // fully unrolled over the chunk index (two instantiations, one per half): (c, kh), the k-block and the chunk slot are
+          // compile-time constants, so a chunk costs 4 LDS + 1 STS + the XOR with the row's swizzle phase
+          const uint32_t* src0 = reinterpret_cast<const uint32_t*>(sPatch + (2 * ry) * ST_IP + 2 * rx);
+          uint8_t* dst0 = sA + p * 128;
+          const int p7 = p & 7;
+          auto build = [&](auto H) {
+            constexpr int HALF = decltype(H)::value;
+#pragma unroll
+            for (int jj = 0; jj < (HALF ? 10 : 11); ++jj) {
+              constexpr int dummy = 0;
+              (void)dummy;
+              const int j = HALF * 11 + jj;
+              const int c = j / 7, kh = j - c * 7;
+              const uint32_t* src = src0 + ((c * ST_IR + kh) * ST_IP) / 2;
+              const uint4 w = make_uint4(src[0], src[1], src[2], src[3]);
+              *reinterpret_cast<uint4*>(dst0 + (j >> 3) * 16384 + (((j & 7) ^ p7) * 16)) = w;
+            }
+          };
+          if (half) build(std::integral_constant<int, 1>{});
+          else build(std::integral_constant<int, 0>{});
         }
         fence_proxy_async();
         tc_fence_before();

@@ -79,11 +79,21 @@ class FusedAdamWEMA:
             for p, v in zip(self.fgb.params, self.fgb.views()):
                 p.grad = v
 
+    def _layout(self):
+        """names / offsets / sizes of the flat moment buffers: the layout follows FlatGradBuffer's ordering and padding, so a
+        checkpoint is only valid for the same layout"""
+        return [(n, int(o), int(p.numel())) for n, o, p in zip(self.names, self.fgb.offsets, self.fgb.params)]
+
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "layout": self._layout(),
                 "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, sd):
+        if "layout" in sd and [tuple(x) for x in sd["layout"]] != self._layout():
+            raise ValueError("FusedAdamWEMA.load_state_dict: the checkpoint's flat-buffer layout (parameter names / offsets / sizes) "
+                             "differs from this optimizer's; it was saved for another model configuration or buffer ordering")
+        if sd["exp_avg"].numel() != self.exp_avg.numel():
+            raise ValueError("FusedAdamWEMA.load_state_dict: moment buffers of %d elements, expected %d" % (sd["exp_avg"].numel(), self.exp_avg.numel()))
         self.step_count = int(sd["step"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
