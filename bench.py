@@ -224,8 +224,10 @@ class Step:
             p.grad = None
         mc = self.model(self.samples, [T_FRAMES], self.caps, encode_and_save=True, samples_fast=self.fast)
         out = self.model(self.samples, [T_FRAMES], self.caps, encode_and_save=False, memory_cache=mc)
-        out = dict(out, pred_boxes=out["pred_boxes"][self.keep],
-                   aux_outputs=[dict(a, pred_boxes=a["pred_boxes"][self.keep]) for a in out["aux_outputs"]])
+        # engine.py:98-102 keeps the annotated frames with `pred_boxes[keep]`; index_select is the same gather, but its backward is one
+        # index_add_ instead of the sort-based index_put_ path (~10 launches per output, 6 outputs, at the very start of the backward)
+        out = dict(out, pred_boxes=out["pred_boxes"].index_select(0, self.keep),
+                   aux_outputs=[dict(a, pred_boxes=a["pred_boxes"].index_select(0, self.keep)) for a in out["aux_outputs"]])
         losses = self.crit(out, self.targets, self.inter_idx, self.time_mask)
         total = sum(losses[k] * self.wd[k] for k in losses if k in self.wd)
         if self.overlap:
