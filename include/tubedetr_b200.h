@@ -42,7 +42,12 @@ int64_t tdb_launch_count(void);
 #define TDB_MAX_TAPS 9
 #define TDB_GEMM_FLAG_DYNAMIC_TILES (1 << 11)
 enum { TDB_OUT_BF16 = 0, TDB_OUT_F32 = 1 };
-enum { TDB_REMAP_NONE = 0, TDB_REMAP_COMPACT_TO_PADDED = 1, TDB_REMAP_PADDED_TO_COMPACT = 2 };
+enum { TDB_REMAP_NONE = 0, TDB_REMAP_COMPACT_TO_PADDED = 1, TDB_REMAP_PADDED_TO_COMPACT = 2,
+       /* stride-2 3x3 convolution without an im2col matrix: the producing 1x1 conv writes its NHWC rows (img_h x img_w) space-to-depth,
+        * out[(n, h/2 + 1, w/2 + 1)][plane(h&1, w&1) * N + c] with a one-pixel zero halo on the top / left of every parity plane
+        * (grid (ceil(H/2) + 1) x (ceil(W/2) + 1), ldo = 4 N); the 9 taps of the convolution are then constant (row shift, plane)
+        * offsets into that matrix.  S2D_TO_COMPACT drops the halo positions of such a grid (img_h x img_w = OUTPUT size). */
+       TDB_REMAP_COMPACT_TO_S2D = 3, TDB_REMAP_S2D_TO_COMPACT = 4 };
 
 typedef struct tdb_gemm_desc {
   /* operands */

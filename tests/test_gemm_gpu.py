@@ -393,3 +393,43 @@ def test_gemm_work_stealing_with_a_foreign_kernel_holding_sms():
         gemm(A, B, o1, M, N, K, debug_flags=DYNAMIC_TILES)
     torch.cuda.synchronize()
     assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("frames,H,W,Cin,C", [(6, 44, 44, 512, 256), (5, 22, 22, 256, 128), (3, 11, 9, 128, 128), (40, 22, 22, 1024, 512),
+                                              (2, 7, 12, 64, 64)])
+def test_stride2_conv_as_implicit_gemm_over_space_to_depth(frames, H, W, Cin, C):
+    """1x1 conv + ReLU written space-to-depth (TDB_REMAP_COMPACT_TO_S2D), then the 3x3 / stride 2 / pad 1 conv as ONE 9-tap implicit
+    GEMM over that matrix (TDB_REMAP_S2D_TO_COMPACT) == torch conv2d of the bf16-rounded intermediate; even and odd image sizes,
+    1-CTA and pair kernels; equal to the im2col route bit for bit (same tap-major reduction order)"""
+    from tubedetr_b200 import kernels as K
+    from tubedetr_b200.gemm import REMAP_C2S, REMAP_S2C, gemm
+    x = _rand((frames * H * W, Cin), 101)
+    w1 = _rand((C, Cin), 102) * 0.05
+    w2 = _rand((C, C, 3, 3), 103) * 0.05
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    ohp, owp = Ho + 1, Wo + 1
+    y1s = torch.zeros(frames * ohp * owp, 4 * C, dtype=torch.bfloat16, device="cuda")
+    gemm(x, w1, y1s, frames * H * W, C, Cin, relu=True, remap=REMAP_C2S, img_hw=(H, W))
+    wk = w2.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous()
+    a0 = [(((kh - 1) & 1) * 2 + ((kw - 1) & 1)) * C for kh in range(3) for kw in range(3)]
+    a1 = [(-1 if kh == 0 else 0) * owp + (-1 if kw == 0 else 0) for kh in range(3) for kw in range(3)]
+    y2 = torch.full((frames * Ho * Wo, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    gemm(y1s, wk, y2, frames * ohp * owp, C, C, ntaps=9, a_off0=a0, a_off1=a1, b_off0=[t * C for t in range(9)], relu=True,
+         remap=REMAP_S2C, img_hw=(Ho, Wo))
+    # the im2col route on the same operands
+    y1 = torch.empty(frames * H * W, C, dtype=torch.bfloat16, device="cuda")
+    gemm(x, w1, y1, frames * H * W, C, Cin, relu=True)
+    col = torch.empty(frames * Ho * Wo, 9 * C, dtype=torch.bfloat16, device="cuda")
+    K.im2col3x3s2(y1, col, frames, H, W, C)
+    y2b = torch.empty(frames * Ho * Wo, C, dtype=torch.bfloat16, device="cuda")
+    gemm(col, wk, y2b, frames * Ho * Wo, C, 9 * C, relu=True)
+    torch.cuda.synchronize()
+    ref = torch.relu(torch.nn.functional.conv2d(y1.float().view(frames, H, W, C).permute(0, 3, 1, 2), w2.float(), stride=2, padding=1))
+    _close(y2, ref.permute(0, 2, 3, 1).reshape(-1, C))
+    _close(y2, y2b, tol=1e-2)
+    # the space-to-depth matrix holds exactly the compact conv1 output, halo positions zero
+    s = y1s.view(frames, ohp, owp, 2, 2, C)
+    assert not bool(s[:, 0].any()) and not bool(s[:, :, 0].any())
+    full = torch.zeros(frames, 2 * Ho, 2 * Wo, C, dtype=torch.bfloat16, device="cuda")
+    full[:, :H, :W] = y1.view(frames, H, W, C)
+    assert torch.equal(s[:, 1:, 1:].permute(0, 1, 3, 2, 4, 5).reshape(frames, 2 * Ho, 2 * Wo, C), full)

@@ -421,6 +421,7 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row_t = wi.m0 + wq * 32 + lane;
       bool valid = row_t < p.M;
       long long out_row = row_t;
+      int s2d_col = 0;               // per-row column offset of the space-to-depth remap (parity plane)
       if (p.remap == TDB_REMAP_COMPACT_TO_PADDED) {
         int hw = p.img_h * p.img_w;
         int n = row_t / hw;
@@ -436,8 +437,20 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int x = rem - h * Wp;
         valid = valid && h >= 1 && h <= p.img_h && x >= 1 && x <= p.img_w;
         out_row = ((long long)n * p.img_h + (h - 1)) * p.img_w + (x - 1);
+      } else if (p.remap == TDB_REMAP_COMPACT_TO_S2D) {
+        const int hw = p.img_h * p.img_w, ohp = ((p.img_h + 1) >> 1) + 1, owp = ((p.img_w + 1) >> 1) + 1;
+        const int n = row_t / hw, rem = row_t - n * hw;
+        const int h = rem / p.img_w, x = rem - h * p.img_w;
+        out_row = ((long long)n * ohp + (h >> 1) + 1) * owp + (x >> 1) + 1;
+        s2d_col = ((h & 1) * 2 + (x & 1)) * p.N;
+      } else if (p.remap == TDB_REMAP_S2D_TO_COMPACT) {
+        const int ohp = p.img_h + 1, owp = p.img_w + 1;
+        const int n = row_t / (ohp * owp), rem = row_t - n * (ohp * owp);
+        const int i = rem / owp, j = rem - i * owp;
+        valid = valid && i >= 1 && j >= 1;
+        out_row = ((long long)n * p.img_h + (i - 1)) * p.img_w + (j - 1);
       }
-      int out_col0 = wi.n0 + p.z_out_col[wi.z];
+      int out_col0 = wi.n0 + p.z_out_col[wi.z] + s2d_col;
       if (p.splits > 1) out_row += (long long)wi.split * p.M;
 
       // mode 2: software-pipelined register prefetch of the row-wise epilogue operands (residual, ReLU mask).  The first
@@ -1223,6 +1236,7 @@ extern "C" int tdb_gemm(const tdb_gemm_desc* d, void* stream_) {
   const int bn = (epi_mode == 4 || epi_mode == 5) ? 128 : pick_block_n(d->N, (long long)m_tiles * nz * splits, d->block_n);
   TDB_REQUIRE(bn != 0, "tdb_gemm: no tile width for N=%d (block_n=%d)", d->N, d->block_n);
   if (d->remap != TDB_REMAP_NONE) TDB_REQUIRE(d->img_h > 0 && d->img_w > 0, "tdb_gemm: remap needs img_h/img_w");
+  TDB_REQUIRE(d->remap < TDB_REMAP_COMPACT_TO_S2D || (epi_mode != 1 && splits == 1 && !d->residual), "tdb_gemm: space-to-depth remaps: no residual / split / epilogue mode 1");
 
   GemmKParams p;
   memset(&p, 0, sizeof(p));

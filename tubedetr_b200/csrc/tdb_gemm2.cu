@@ -538,10 +538,11 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int w = cur.first(pair); w < p.total_work; w = cur.next(w)) {
       const Work2 wi = decode2(p, w);
       const int n0 = wi.nt * G2_BN;
-      const int out_col0 = n0 + p.z_out_col[wi.z];
+      int out_col0 = n0 + p.z_out_col[wi.z];
       const int row_t = wi.mt * 256 + (int)rank * 128 + wq * 32 + lane;
       bool valid = row_t < p.M;
       long long out_row = row_t;
+      int s2d_col = 0;               // per-row column offset of the space-to-depth remap (parity plane)
       if (p.remap == TDB_REMAP_COMPACT_TO_PADDED) {
         int hw = p.img_h * p.img_w;
         int n = row_t / hw;
@@ -557,7 +558,20 @@ tdb_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int x = rem - h * Wp;
         valid = valid && h >= 1 && h <= p.img_h && x >= 1 && x <= p.img_w;
         out_row = ((long long)n * p.img_h + (h - 1)) * p.img_w + (x - 1);
+      } else if (p.remap == TDB_REMAP_COMPACT_TO_S2D) {
+        const int hw = p.img_h * p.img_w, ohp = ((p.img_h + 1) >> 1) + 1, owp = ((p.img_w + 1) >> 1) + 1;
+        const int n = row_t / hw, rem = row_t - n * hw;
+        const int h = rem / p.img_w, x = rem - h * p.img_w;
+        out_row = ((long long)n * ohp + (h >> 1) + 1) * owp + (x >> 1) + 1;
+        s2d_col = ((h & 1) * 2 + (x & 1)) * p.N;
+      } else if (p.remap == TDB_REMAP_S2D_TO_COMPACT) {
+        const int ohp = p.img_h + 1, owp = p.img_w + 1;
+        const int n = row_t / (ohp * owp), rem = row_t - n * (ohp * owp);
+        const int i = rem / owp, j = rem - i * owp;
+        valid = valid && i >= 1 && j >= 1;
+        out_row = ((long long)n * p.img_h + (i - 1)) * p.img_w + (j - 1);
       }
+      out_col0 += s2d_col;
       if (p.splits > 1) out_row += (long long)wi.split * p.M;
       for (int i = lane; i < G2_BN; i += 32) {
         ssc[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
@@ -721,7 +735,7 @@ int tdb_gemm2_try(const tdb_gemm_desc* d, void* stream_) {
   const bool box_fmt = !((d->debug_flags >> 9) & 1) && d->out_dtype == TDB_OUT_BF16 && splits == 1 && nz == 1 && d->ldo % 8 == 0 &&
                        (forced || d->M >= tepi_min_m);
   const bool tma_ok = box_fmt && tepi_on && d->remap == TDB_REMAP_NONE && (!d->residual || d->ldr % 8 == 0);
-  const bool copy_ok = box_fmt && copy_on && d->remap != TDB_REMAP_NONE && !d->residual && d->img_h > 0 && d->img_w > 0 &&
+  const bool copy_ok = box_fmt && copy_on && d->remap != TDB_REMAP_NONE && d->remap <= TDB_REMAP_PADDED_TO_COMPACT && !d->residual && d->img_h > 0 && d->img_w > 0 &&
                        (long long)d->M * 2 < (1ll << 31);
   bool tepi = tma_ok || copy_ok;
   if (!forced && (kdepth < (tma_ok ? tepi_min_k : min_k) || total < pairs / 2 || (long long)m_tiles * 256 * 3 > (long long)d->M * 4)) return 0;

@@ -15,7 +15,7 @@ import os
 import torch
 
 from . import kernels as K
-from .gemm import DYNAMIC_TILES, REMAP_C2P, REMAP_P2C, effective_splits, gemm, splitk_reduce
+from .gemm import DYNAMIC_TILES, REMAP_C2P, REMAP_C2S, REMAP_P2C, REMAP_S2C, effective_splits, gemm, splitk_reduce
 
 STAGES = ((64, 3, 1), (128, 4, 2), (256, 23, 2), (512, 3, 2))  # width, blocks, stride of first block
 BN_EPS = 1e-5
@@ -26,6 +26,7 @@ WGRAD_LAG = max(1, min(2, int(os.environ.get("TDB_WGRAD_LAG", "1"))))
 # stream, concurrent with the backbone backward) find idle SMs instead of delaying a GEMM CTA that needs a whole SM (0 = no cap)
 BWD_MAX_CTAS = int(os.environ.get("TDB_BB_BWD_MAX_CTAS", "0"))
 STEM_FUSED = os.environ.get("TDB_STEM_FUSED", "1") != "0"    # one kernel for conv1 + FrozenBN + ReLU + maxpool (tdb_stem.cu)
+S2_IMPLICIT = os.environ.get("TDB_S2_IMPLICIT", "1") != "0"  # stride-2 3x3 convs as implicit GEMMs over a space-to-depth layout (no im2col matrix)
 
 
 def _dyn(env, auto):
@@ -244,6 +245,31 @@ class ResNet101Engine:
                     taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
                     gemm(y1, w2, y2, Rp, width, width, ntaps=9, a_off1=taps, b_off0=[t * width for t in range(9)],
                          scale=s2, bias=b2, relu=True, remap=REMAP_P2C, img_hw=(h, w), debug_flags=ff)
+                elif S2_IMPLICIT and not (keep and nk == N):
+                    # stride-2 3x3 conv WITHOUT an im2col matrix: conv1 writes its rows space-to-depth (4 parity planes side by side,
+                    # one-pixel zero halo on the top / left of every plane); tap (kh, kw) of the convolution then is the plane
+                    # ((kh - 1) & 1, (kw - 1) & 1) shifted by (-1 if k == 0 else 0) rows / columns: 9 constant (row, column) offsets
+                    # of ONE implicit GEMM (same tap-major K order as the im2col matrix, so the result is unchanged).
+                    ohp, owp = ho + 1, wo + 1
+                    y1s = self.buf(f"{tag}:L{li}y1s", (N * ohp * owp, 4 * width), zero=True)
+                    gemm(x, w1, y1s, R, width, cin, scale=s1, bias=b1, relu=True, remap=REMAP_C2S, img_hw=(h, w), debug_flags=ff)
+                    a0, a1 = [], []
+                    for kh in range(3):
+                        for kw in range(3):
+                            a0.append((((kh - 1) & 1) * 2 + ((kw - 1) & 1)) * width)
+                            a1.append((-1 if kh == 0 else 0) * owp + (-1 if kw == 0 else 0))
+                    y2 = self.buf(btag + "y2", (Ro, width))
+                    gemm(y1s, w2, y2, N * ohp * owp, width, width, ntaps=9, a_off0=a0, a_off1=a1, b_off0=[t * width for t in range(9)],
+                         scale=s2, bias=b2, relu=True, remap=REMAP_S2C, img_hw=(ho, wo), debug_flags=ff)
+                    y1 = None
+                    if keep:
+                        # the differentiated frames (a row prefix) also get the compact conv1 output and the im2col matrix their
+                        # backward reads (ReLU mask, weight gradient): 1/5 of the old cost at 25 of 125 frames
+                        y1 = self.buf(btag + "y1", (nk * h * w, width))
+                        gemm(x[:nk * h * w], w1, y1, nk * h * w, width, cin, scale=s1, bias=b1, relu=True, debug_flags=ff)
+                        colb = self.buf(btag + "col", (nk * ho * wo, 9 * width))
+                        K.im2col3x3s2(y1, colb, nk, h, w, width)
+                        rec["col"] = colb
                 else:
                     y1 = self.buf(btag + "y1", (R, width))
                     gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, debug_flags=ff)
