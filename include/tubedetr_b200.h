@@ -105,6 +105,9 @@ int tdb_stem_im2col(const float* x, void* col, int N, int H, int W, void* stream
  * output touch HBM.  wk = conv1 weight as bf16 [64][192] in K order (c, kh, kw padded to 8), zero at kw = 7 and beyond k = 168. */
 int tdb_stem_fused(const float* x, const void* wk, const float* scale, const float* shift, void* out, int N, int H, int W,
                    void* stream);
+/* same, pooled rows ldo elements apart (>= 64) */
+int tdb_stem_fused_ld(const float* x, const void* wk, const float* scale, const float* shift, void* out, int64_t ldo, int N, int H,
+                      int W, void* stream);
 /* torchvision maxpool 3x3/2/p1 after the stem (unfused path) */
 int tdb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, void* stream);
 /* stride-2 3x3 convs (first block of layer2/3/4, torchvision v1.5): explicit im2col [N*Ho*Wo][9*C] (tap major) ... */
@@ -113,6 +116,8 @@ int tdb_im2col3x3s2(const void* x, void* col, int N, int H, int W, int C, void* 
 int tdb_col2im3x3s2_mask(const void* dcol, const void* ymask, void* dx, int N, int H, int W, int C, void* stream);
 /* stride-2 1x1 `downsample` conv input (pixel subsample) and its transpose (zero upsample) */
 int tdb_subsample2(const void* x, void* y, int N, int H, int W, int C, void* stream);
+/* same, output rows ldy elements apart (the gathered pixels land in a column slice of a wider matrix) */
+int tdb_subsample2_ld(const void* x, void* y, int64_t ldy, int N, int H, int W, int C, void* stream);
 int tdb_upsample2_zero(const void* y, void* x, int N, int H, int W, int C, void* stream);
 /* fp32 torch conv weight [Cout][Cin][kh][kw] -> bf16 GEMM layout [Cout][Kpad] (tap major; taps==49 keeps torch order),
  * optional second copy scaled per output channel (FrozenBN scale folded for dgrad, reference models/backbone.py:60-70) */

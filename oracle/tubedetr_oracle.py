@@ -43,8 +43,14 @@ def resnet101_layer4(x, sd, p="backbone.0.body.", emulate_bf16=False):
     emulate_bf16=True rounds weights and every stored activation to bf16 exactly where the CUDA path does (bf16
     operands, fp32 accumulate + FrozenBN/residual/ReLU epilogue, bf16 store).  Used only to validate the backward pass:
     ReLU masks then agree with the CUDA forward, which a comparison against the pure-fp32 network cannot guarantee.
+    In the first block of every stage the CUDA path computes conv3 and the downsample branch as ONE GEMM over [y2 | x] with the
+    FrozenBN scales folded into the bf16 weights and no bf16 store of the identity branch; the emulation rounds there too.
     """
     e = emulate_bf16
+
+    def bn_affine(q):
+        scale = sd[q + ".weight"] * torch.rsqrt(sd[q + ".running_var"] + 1e-5)
+        return scale, sd[q + ".bias"] - sd[q + ".running_mean"] * scale
 
     def conv(t, w, **kw):
         return F.conv2d(t, _q(w, e), **kw)
@@ -59,6 +65,14 @@ def resnet101_layer4(x, sd, p="backbone.0.body.", emulate_bf16=False):
             idt = x
             y = _q(F.relu(frozen_bn(conv(x, sd[q + "conv1.weight"]), sd, q + "bn1")), e)
             y = _q(F.relu(frozen_bn(conv(y, sd[q + "conv2.weight"], stride=stride, padding=1), sd, q + "bn2")), e)
+            if bi == 0 and e:
+                s3, b3 = bn_affine(q + "bn3")
+                sdn, bdn = bn_affine(q + "downsample.1")
+                y = (F.conv2d(y, _q(sd[q + "conv3.weight"] * s3.view(-1, 1, 1, 1), e))
+                     + F.conv2d(x, _q(sd[q + "downsample.0.weight"] * sdn.view(-1, 1, 1, 1), e), stride=stride)
+                     + (b3 + bdn).view(1, -1, 1, 1))
+                x = _q(F.relu(y), e)
+                continue
             y = frozen_bn(conv(y, sd[q + "conv3.weight"]), sd, q + "bn3")
             if bi == 0:
                 idt = _q(frozen_bn(conv(x, sd[q + "downsample.0.weight"], stride=stride), sd, q + "downsample.1"), e)

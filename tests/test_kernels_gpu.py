@@ -78,6 +78,11 @@ def test_stem_fused_matches_torch_and_unfused(N, H, W):
     torch.cuda.synchronize()
     _close(out, z, 1e-2)
     assert (out.float() != z.float()).float().mean().item() < 0.02
+    # the pooled rows written into a column slice of a wider matrix (layer1.0's [conv2 output | block input] operand): same values
+    wide = torch.full((N * H2 * W2, 128), 3.0, dtype=torch.bfloat16, device="cuda")
+    K.stem_fused(x, wk, scale, shift, wide[:, 64:], N, H, W)
+    torch.cuda.synchronize()
+    assert torch.equal(wide[:, 64:], out) and bool((wide[:, :64] == 3).all())
 
 
 @pytest.mark.parametrize("H,W", [(22, 22), (11, 13)])
@@ -109,6 +114,9 @@ def test_stride2_conv_paths(H, W):
     xs = torch.empty(N, Ho, Wo, C, dtype=torch.bfloat16, device="cuda")
     K.subsample2(x, xs, N, H, W, C)
     assert torch.equal(xs, x[:, ::2, ::2].contiguous())
+    wide = torch.full((N * Ho * Wo, 3 * C), 5.0, dtype=torch.bfloat16, device="cuda")    # ... into a column slice of a wider matrix
+    K.subsample2(x, wide[:, C:2 * C], N, H, W, C)
+    assert torch.equal(wide[:, C:2 * C], xs.view(-1, C)) and bool((wide[:, :C] == 5).all()) and bool((wide[:, 2 * C:] == 5).all())
     up = torch.empty(N, H, W, C, dtype=torch.bfloat16, device="cuda")
     K.upsample2_zero(xs, up, N, H, W, C)
     refu = torch.zeros_like(x)

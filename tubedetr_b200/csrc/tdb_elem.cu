@@ -156,7 +156,7 @@ __global__ void col2im3x3s2_mask_kernel(const bf16* __restrict__ dcol, const bf1
 }
 
 // ------------------------------------------------------------------ stride-2 pixel subsample (1x1 stride-2 downsample conv input) and its transpose
-__global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int Ho, int Wo) {
+__global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long ldy, int N, int H, int W, int C, int Ho, int Wo) {
   pdl_wait();
   pdl_trigger();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,7 +169,7 @@ __global__ void subsample2_kernel(const bf16* __restrict__ x, bf16* __restrict__
   t /= Wo;
   int ho = (int)(t % Ho);
   int n = (int)(t / Ho);
-  *reinterpret_cast<uint4*>(y + (((long long)n * Ho + ho) * Wo + wo) * C + c8 * 8) =
+  *reinterpret_cast<uint4*>(y + (((long long)n * Ho + ho) * Wo + wo) * ldy + c8 * 8) =
       __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + c8 * 8));
 }
 __global__ void upsample2_zero_kernel(const bf16* __restrict__ y, bf16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo) {
@@ -576,12 +576,15 @@ extern "C" int tdb_col2im3x3s2_mask(const void* dcol, const void* ymask, void* d
   TDB_CHECK_CUDA(tdb_launch(col2im3x3s2_mask_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, (const bf16*)dcol, (const bf16*)ymask, (bf16*)dx, N, H, W, C, Ho, Wo));
   LAUNCH_OK();
 }
-extern "C" int tdb_subsample2(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
-  TDB_REQUIRE(x && y && C % 8 == 0, "tdb_subsample2: bad args");
+extern "C" int tdb_subsample2_ld(const void* x, void* y, int64_t ldy, int N, int H, int W, int C, void* stream_) {
+  TDB_REQUIRE(x && y && C % 8 == 0 && ldy >= C && ldy % 8 == 0, "tdb_subsample2: bad args");
   int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   long long total = (long long)N * Ho * Wo * (C / 8);
-  TDB_CHECK_CUDA(tdb_launch(subsample2_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, (const bf16*)x, (bf16*)y, N, H, W, C, Ho, Wo));
+  TDB_CHECK_CUDA(tdb_launch(subsample2_kernel, dim3(nblocks(total, 256)), dim3(256), 0, STREAM, (const bf16*)x, (bf16*)y, (long long)ldy, N, H, W, C, Ho, Wo));
   LAUNCH_OK();
+}
+extern "C" int tdb_subsample2(const void* x, void* y, int N, int H, int W, int C, void* stream_) {
+  return tdb_subsample2_ld(x, y, C, N, H, W, C, stream_);
 }
 extern "C" int tdb_upsample2_zero(const void* y, void* x, int N, int H, int W, int C, void* stream_) {
   TDB_REQUIRE(x && y && C % 8 == 0, "tdb_upsample2_zero: bad args");

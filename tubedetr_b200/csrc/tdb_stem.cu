@@ -40,7 +40,8 @@ struct StemParams {
   const bf16* wk;        // [64][192] bf16, K order (c, kh, kw8), zero beyond the 7 real kw and beyond k = 168
   const float* scale;    // [64] FrozenBN scale, shift
   const float* shift;
-  bf16* out;             // [N * H2 * W2][64]
+  bf16* out;             // [N * H2 * W2][64], row pitch ldo elements
+  long long ldo;
   int N, H, W, H1, W1, H2, W2, tiles_x, tiles_y, total;
 };
 
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fused_kernel(const __grid_
         o.y = *reinterpret_cast<uint32_t*>(&mx[1]);
         o.z = *reinterpret_cast<uint32_t*>(&mx[2]);
         o.w = *reinterpret_cast<uint32_t*>(&mx[3]);
-        *reinterpret_cast<uint4*>(a.out + (((long long)n * a.H2 + oy) * a.W2 + ox) * 64 + ch8 * 8) = o;
+        *reinterpret_cast<uint4*>(a.out + (((long long)n * a.H2 + oy) * a.W2 + ox) * a.ldo + ch8 * 8) = o;
       }
       // the next tile's patch load only touches sPatch (last read by the A builds above); its epilogues write sConv after the
       // bar.sync that follows the patch load, i.e. after every thread has left this pool loop
@@ -261,11 +262,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fused_kernel(const __grid_
 
 using namespace tdb;
 
-extern "C" int tdb_stem_fused(const float* x, const void* wk, const float* scale, const float* shift, void* out, int N, int H, int W,
-                              void* stream_) {
+extern "C" int tdb_stem_fused_ld(const float* x, const void* wk, const float* scale, const float* shift, void* out, int64_t ldo, int N, int H,
+                                 int W, void* stream_) {
   int rc = tdb_init_once();
   if (rc) return rc;
-  TDB_REQUIRE(x && wk && scale && shift && out && N > 0 && H >= 7 && W >= 7, "tdb_stem_fused: bad args");
+  TDB_REQUIRE(x && wk && scale && shift && out && N > 0 && H >= 7 && W >= 7 && ldo >= 64 && ldo % 8 == 0, "tdb_stem_fused: bad args");
   TDB_REQUIRE((((uintptr_t)wk | (uintptr_t)out) & 15) == 0, "tdb_stem_fused: wk / out must be 16-byte aligned");
   StemParams a;
   a.x = x;
@@ -273,6 +274,7 @@ extern "C" int tdb_stem_fused(const float* x, const void* wk, const float* scale
   a.scale = scale;
   a.shift = shift;
   a.out = (bf16*)out;
+  a.ldo = ldo;
   a.N = N;
   a.H = H;
   a.W = W;
@@ -296,4 +298,9 @@ extern "C" int tdb_stem_fused(const float* x, const void* wk, const float* scale
   TDB_CHECK_CUDA(cudaGetLastError());
   tdb_count_launch(1);
   return TDB_OK;
+}
+
+extern "C" int tdb_stem_fused(const float* x, const void* wk, const float* scale, const float* shift, void* out, int N, int H, int W,
+                              void* stream_) {
+  return tdb_stem_fused_ld(x, wk, scale, shift, out, 64, N, H, W, stream_);
 }

@@ -15,7 +15,9 @@ def stem_im2col(x, col, N, H, W):
 
 
 def stem_fused(x, wk, scale, shift, out, N, H, W):
-    check(lib().tdb_stem_fused(ptr(x), ptr(wk), ptr(scale), ptr(shift), ptr(out), N, H, W, stream_ptr()), "stem_fused")
+    """out: [N * H2 * W2, 64] bf16 rows, possibly a column slice of a wider matrix (row stride = out.stride(0))"""
+    assert out.stride(-1) == 1
+    check(lib().tdb_stem_fused_ld(ptr(x), ptr(wk), ptr(scale), ptr(shift), ptr(out), C.c_int64(out.stride(-2)), N, H, W, stream_ptr()), "stem_fused")
 
 
 def maxpool3x3s2(x, y, N, H, W, Cc):
@@ -31,7 +33,9 @@ def col2im3x3s2_mask(dcol, ymask, dx, N, H, W, Cc):
 
 
 def subsample2(x, y, N, H, W, Cc):
-    check(lib().tdb_subsample2(ptr(x), ptr(y), N, H, W, Cc, stream_ptr()), "subsample2")
+    """y: [N * Ho * Wo, Cc] rows, possibly a column slice of a wider matrix (row stride = y.stride(0))"""
+    assert y.stride(-1) == 1 and x.is_contiguous()
+    check(lib().tdb_subsample2_ld(ptr(x), ptr(y), C.c_int64(y.stride(-2)), N, H, W, Cc, stream_ptr()), "subsample2")
 
 
 def upsample2_zero(y, x, N, H, W, Cc):

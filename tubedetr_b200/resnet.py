@@ -27,6 +27,11 @@ WGRAD_LAG = max(1, min(2, int(os.environ.get("TDB_WGRAD_LAG", "1"))))
 BWD_MAX_CTAS = int(os.environ.get("TDB_BB_BWD_MAX_CTAS", "0"))
 STEM_FUSED = os.environ.get("TDB_STEM_FUSED", "1") != "0"    # one kernel for conv1 + FrozenBN + ReLU + maxpool (tdb_stem.cu)
 S2_IMPLICIT = os.environ.get("TDB_S2_IMPLICIT", "1") != "0"  # stride-2 3x3 convs as implicit GEMMs over a space-to-depth layout (no im2col matrix)
+# first block of a stage: out = relu(bn3(conv3(y2)) + bnd(convd(xs))) as ONE GEMM over K = width + cin: y2 and the (subsampled) block
+# input sit side by side in one matrix [rows, width + cin], the FrozenBN scales are folded into the concatenated weights (the
+# `ws` copies the backward already uses), the shifts are summed.  Removes the downsample GEMM and the write + re-read of its
+# [rows, 4 * width] output as a residual (layer1.0 at 125 frames: 0.99 GB of HBM traffic)
+DS_JOINT = os.environ.get("TDB_DS_JOINT", "1") != "0"
 
 
 def _dyn(env, auto):
@@ -137,6 +142,16 @@ class ResNet101Engine:
                 ent = (ck, wb, ws)
                 self._wcache[conv] = ent
             W[conv] = (ent[1], ent[2], self._bn[conv][0], self._bn[conv][1])
+        for li, (width, _, _) in enumerate(STAGES, start=1):
+            p = f"layer{li}.0."
+            e3, ed = self._wcache[p + "conv3"], self._wcache[p + "downsample.0"]
+            ck = (e3[0], ed[0])
+            ent = self._wcache.get("j:" + p)
+            if ent is None or ent[0] != ck:
+                wj = torch.cat([e3[2], ed[2]], 1).contiguous()                      # [cout, width + cin], FrozenBN scales folded in
+                ent = (ck, wj, (self._bn[p + "conv3"][1] + self._bn[p + "downsample.0"][1]).contiguous())
+                self._wcache["j:" + p] = ent
+            W["j:" + p] = (ent[1], ent[2])
         # fused stem: conv1 weight in K order (c, kh, kw padded to 8) -- frozen, so a handful of torch ops once per weight version
         w1 = sd[prefix + "conv1.weight"]
         ck = (w1.data_ptr(), w1._version)
@@ -187,7 +202,12 @@ class ResNet101Engine:
         H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
         wb, _, sc, sh = W["conv1"]
         if STEM_FUSED:
-            x = self.buf(tag + ":pool", (N * H2 * W2, 64))
+            if DS_JOINT:      # the pooled rows land in the right half of layer1.0's [rows, conv2 output | block input] matrix
+                self._l1j = self.buf(tag + ":L1J", (N * H2 * W2, 128))
+                x = self._l1j[:, 64:]
+            else:
+                self._l1j = None
+                x = self.buf(tag + ":pool", (N * H2 * W2, 64))
             base = 0
             for frames in srcs:
                 assert frames.shape[2:] == (H, Wd), "frames of one backbone batch must share their spatial size"
@@ -195,6 +215,7 @@ class ResNet101Engine:
                 K.stem_fused(frames, W["conv1:fused"], sc, sh, x[base * H2 * W2:(base + n) * H2 * W2], n, H, Wd)
                 base += n
             return x, H2, W2
+        self._l1j = None
         stem = self.buf(tag + ":stem", (N * H1 * W1, 64))
         chunk = max(1, min(N, (1 << 28) // (H1 * W1 * 192 * 2)))
         col = self.buf(tag + ":stemcol", (chunk * H1 * W1, 192))
@@ -236,11 +257,18 @@ class ResNet101Engine:
                 w3, _, s3, b3 = W[name + "conv3"]
                 rec = {"name": name, "x": x, "h": h, "w": w, "ho": ho, "wo": wo, "stride": stride, "width": width,
                        "cin": cin, "cout": cout, "first": bi == 0}
+                J = None
+                if DS_JOINT and bi == 0:
+                    if stride == 2:
+                        J = self.buf(btag + "J", (Ro, width + cin))
+                    elif getattr(self, "_l1j", None) is not None and x.data_ptr() == self._l1j.data_ptr() + 2 * width:
+                        J = self._l1j                                            # layer1.0: the stem wrote x into J[:, width:]
+                y2buf = (lambda: J[:, :width]) if J is not None else (lambda: self.buf(btag + "y2", (Ro, width)))
                 if stride == 1:
                     Rp = N * (h + 2) * (w + 2)
                     y1 = self.buf(btag + "y1p", (Rp, width), zero=True)
                     gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, remap=REMAP_C2P, img_hw=(h, w), debug_flags=ff)
-                    y2 = self.buf(btag + "y2", (R, width))
+                    y2 = y2buf()
                     wp = w + 2
                     taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
                     gemm(y1, w2, y2, Rp, width, width, ntaps=9, a_off1=taps, b_off0=[t * width for t in range(9)],
@@ -258,7 +286,7 @@ class ResNet101Engine:
                         for kw in range(3):
                             a0.append((((kh - 1) & 1) * 2 + ((kw - 1) & 1)) * width)
                             a1.append((-1 if kh == 0 else 0) * owp + (-1 if kw == 0 else 0))
-                    y2 = self.buf(btag + "y2", (Ro, width))
+                    y2 = y2buf()
                     gemm(y1s, w2, y2, N * ohp * owp, width, width, ntaps=9, a_off0=a0, a_off1=a1, b_off0=[t * width for t in range(9)],
                          scale=s2, bias=b2, relu=True, remap=REMAP_S2C, img_hw=(ho, wo), debug_flags=ff)
                     y1 = None
@@ -275,10 +303,17 @@ class ResNet101Engine:
                     gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, debug_flags=ff)
                     colb = self.buf(btag + "col", (Ro, 9 * width))
                     K.im2col3x3s2(y1, colb, N, h, w, width)
-                    y2 = self.buf(btag + "y2", (Ro, width))
+                    y2 = y2buf()
                     gemm(colb, w2, y2, Ro, width, 9 * width, scale=s2, bias=b2, relu=True, debug_flags=ff)
                     rec["col"] = colb
-                if bi == 0:
+                if bi == 0 and J is not None:
+                    xs = x
+                    if stride == 2:
+                        xs = J[:, width:]
+                        K.subsample2(x, xs, N, h, w, cin)
+                    rec["xs"] = xs
+                    idt = None
+                elif bi == 0:
                     wd, _, sd_, bd = W[name + "downsample.0"]
                     xs = x
                     if stride == 2:
@@ -298,7 +333,11 @@ class ResNet101Engine:
                 else:
                     # ping-pong the block output so the no-grad pass needs two buffers per stage
                     out = self.buf(f"{btag}out{0 if keep else bi % 2}", (Ro, cout))
-                gemm(y2, w3, out, Ro, cout, width, scale=s3, bias=b3, residual=idt, relu=True, debug_flags=ff)
+                if J is not None:
+                    wj, bj = W["j:" + name]
+                    gemm(J, wj, out, Ro, cout, width + cin, bias=bj, relu=True, debug_flags=ff)
+                else:
+                    gemm(y2, w3, out, Ro, cout, width, scale=s3, bias=b3, residual=idt, relu=True, debug_flags=ff)
                 rec.update(y1=y1, y2=y2, out=out)
                 if keep:
                     if nk != N:      # differentiate the first nk frames only: row-prefix views of every saved activation
