@@ -47,7 +47,12 @@ enum { TDB_REMAP_NONE = 0, TDB_REMAP_COMPACT_TO_PADDED = 1, TDB_REMAP_PADDED_TO_
         * out[(n, h/2 + 1, w/2 + 1)][plane(h&1, w&1) * N + c] with a one-pixel zero halo on the top / left of every parity plane
         * (grid (ceil(H/2) + 1) x (ceil(W/2) + 1), ldo = 4 N); the 9 taps of the convolution are then constant (row shift, plane)
         * offsets into that matrix.  S2D_TO_COMPACT drops the halo positions of such a grid (img_h x img_w = OUTPUT size). */
-       TDB_REMAP_COMPACT_TO_S2D = 3, TDB_REMAP_S2D_TO_COMPACT = 4 };
+       TDB_REMAP_COMPACT_TO_S2D = 3, TDB_REMAP_S2D_TO_COMPACT = 4,
+       /* zero-haloed grid with ONE shared halo row / column: (img_h + 1) x (img_w + 1) positions per image, data at (h + 1, w + 1).
+        * The cell right of the last column is the next row's halo column, the row below the last row is the next image's halo row
+        * (beyond the matrix: TMA zero fill), so a 3x3 / pad 1 convolution sees the same zeros as in the (H + 2) x (W + 2) grid of
+        * COMPACT_TO_PADDED with 8 % (22 x 22) to 15 % (11 x 11) fewer rows.  The way back is S2D_TO_COMPACT (same formula). */
+       TDB_REMAP_COMPACT_TO_PADDED1 = 5 };
 
 typedef struct tdb_gemm_desc {
   /* operands */

@@ -433,3 +433,38 @@ def test_stride2_conv_as_implicit_gemm_over_space_to_depth(frames, H, W, Cin, C)
     full = torch.zeros(frames, 2 * Ho, 2 * Wo, C, dtype=torch.bfloat16, device="cuda")
     full[:, :H, :W] = y1.view(frames, H, W, C)
     assert torch.equal(s[:, 1:, 1:].permute(0, 1, 3, 2, 4, 5).reshape(frames, 2 * Ho, 2 * Wo, C), full)
+
+
+@pytest.mark.parametrize("frames,H,W,Cin,C", [(12, 22, 22, 1024, 256), (9, 11, 11, 2048, 512), (3, 44, 44, 512, 128), (2, 9, 13, 256, 64)])
+def test_conv3x3_over_the_shared_halo_grid(frames, H, W, Cin, C):
+    """1x1 conv + ReLU written into the (H + 1) x (W + 1) grid with ONE shared zero halo row / column per image
+    (TDB_REMAP_COMPACT_TO_PADDED1), then the 3x3 / pad 1 conv as a 9-tap implicit GEMM over it (way back = TDB_REMAP_S2D_TO_COMPACT)
+    == torch conv2d; also the last image's bottom halo, which lies beyond the matrix (TMA zero fill)"""
+    from tubedetr_b200.gemm import REMAP_C2P1, REMAP_S2C, gemm
+    x = _rand((frames * H * W, Cin), 111)
+    w1 = _rand((C, Cin), 112) * 0.05
+    w2 = _rand((C, C, 3, 3), 113) * 0.05
+    Rp = frames * (H + 1) * (W + 1)
+    y1p = torch.zeros(Rp, C, dtype=torch.bfloat16, device="cuda")
+    gemm(x, w1, y1p, frames * H * W, C, Cin, relu=True, remap=REMAP_C2P1, img_hw=(H, W))
+    wk = w2.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous()
+    taps = [(kh - 1) * (W + 1) + (kw - 1) for kh in range(3) for kw in range(3)]
+    y2 = torch.full((frames * H * W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    gemm(y1p, wk, y2, Rp, C, C, ntaps=9, a_off1=taps, b_off0=[t * C for t in range(9)], relu=True, remap=REMAP_S2C, img_hw=(H, W))
+    torch.cuda.synchronize()
+    g = y1p.view(frames, H + 1, W + 1, C)
+    assert not bool(g[:, 0].any()) and not bool(g[:, :, 0].any())
+    y1 = g[:, 1:, 1:].float()
+    ref = torch.relu(torch.nn.functional.conv2d(y1.permute(0, 3, 1, 2), w2.float(), padding=1)).permute(0, 2, 3, 1).reshape(-1, C)
+    _close(y2, ref)
+    # dgrad form over the same grid: dX = sum_t dY[r - shift_t] W_t, masked by the ReLU of the grid's own values
+    dy = torch.zeros(Rp, C, dtype=torch.bfloat16, device="cuda")
+    dy.view(frames, H + 1, W + 1, C)[:, 1:, 1:] = _rand((frames, H, W, C), 114)
+    dx = torch.full((frames * H * W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    wt = w2.permute(0, 2, 3, 1).reshape(C, 9 * C).contiguous()          # [Cout(K), tap * Cin(N)] read MN-major
+    gemm(dy, wt, dx, Rp, C, C, b_major=1, ntaps=9, a_off1=[-t for t in taps], b_off0=[t * C for t in range(9)], mask=y1p,
+         remap=REMAP_S2C, img_hw=(H, W))
+    torch.cuda.synchronize()
+    dyc = dy.view(frames, H + 1, W + 1, C)[:, 1:, 1:].float().permute(0, 3, 1, 2)
+    refdx = torch.nn.functional.conv_transpose2d(dyc, w2.float(), padding=1).permute(0, 2, 3, 1) * (y1 > 0)
+    _close(dx, refdx.reshape(-1, C))

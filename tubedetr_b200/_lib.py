@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libtdb.so")
 MAX_TAPS = 9
 OUT_BF16, OUT_F32 = 0, 1
-REMAP_NONE, REMAP_C2P, REMAP_P2C, REMAP_C2S, REMAP_S2C = 0, 1, 2, 3, 4
+REMAP_NONE, REMAP_C2P, REMAP_P2C, REMAP_C2S, REMAP_S2C, REMAP_C2P1 = 0, 1, 2, 3, 4, 5
 
 
 class GemmDesc(C.Structure):

@@ -443,6 +443,11 @@ tdb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int h = rem / p.img_w, x = rem - h * p.img_w;
         out_row = ((long long)n * ohp + (h >> 1) + 1) * owp + (x >> 1) + 1;
         s2d_col = ((h & 1) * 2 + (x & 1)) * p.N;
+      } else if (p.remap == TDB_REMAP_COMPACT_TO_PADDED1) {
+        const int hw = p.img_h * p.img_w;
+        const int n = row_t / hw, rem = row_t - n * hw;
+        const int h = rem / p.img_w, x = rem - h * p.img_w;
+        out_row = ((long long)n * (p.img_h + 1) + h + 1) * (p.img_w + 1) + x + 1;
       } else if (p.remap == TDB_REMAP_S2D_TO_COMPACT) {
         const int ohp = p.img_h + 1, owp = p.img_w + 1;
         const int n = row_t / (ohp * owp), rem = row_t - n * (ohp * owp);

@@ -4,7 +4,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, OUT_BF16, OUT_F32, REMAP_C2P, REMAP_C2S, REMAP_NONE, REMAP_P2C, REMAP_S2C  # noqa: F401
+from ._lib import GemmDesc, OUT_BF16, OUT_F32, REMAP_C2P, REMAP_C2P1, REMAP_C2S, REMAP_NONE, REMAP_P2C, REMAP_S2C  # noqa: F401
 
 
 DYNAMIC_TILES = 1 << 11     # TDB_GEMM_FLAG_DYNAMIC_TILES (include/tubedetr_b200.h)

@@ -15,7 +15,7 @@ import os
 import torch
 
 from . import kernels as K
-from .gemm import DYNAMIC_TILES, REMAP_C2P, REMAP_C2S, REMAP_P2C, REMAP_S2C, effective_splits, gemm, splitk_reduce
+from .gemm import DYNAMIC_TILES, REMAP_C2P, REMAP_C2P1, REMAP_C2S, REMAP_P2C, REMAP_S2C, effective_splits, gemm, splitk_reduce
 
 STAGES = ((64, 3, 1), (128, 4, 2), (256, 23, 2), (512, 3, 2))  # width, blocks, stride of first block
 BN_EPS = 1e-5
@@ -32,6 +32,11 @@ S2_IMPLICIT = os.environ.get("TDB_S2_IMPLICIT", "1") != "0"  # stride-2 3x3 conv
 # `ws` copies the backward already uses), the shifts are summed.  Removes the downsample GEMM and the write + re-read of its
 # [rows, 4 * width] output as a residual (layer1.0 at 125 frames: 0.99 GB of HBM traffic)
 DS_JOINT = os.environ.get("TDB_DS_JOINT", "1") != "0"
+# zero-haloed grids of the stride-1 3x3 convs with ONE shared halo row / column per image ((H + 1) x (W + 1) positions instead of
+# (H + 2) x (W + 2): the cell right of a row's last pixel is the next row's halo cell): 8 % (22 x 22) .. 15 % (11 x 11) fewer GEMM rows
+HALO1 = os.environ.get("TDB_HALO1", "1") != "0"
+PADH = 1 if HALO1 else 2
+C2P, P2C = (REMAP_C2P1, REMAP_S2C) if HALO1 else (REMAP_C2P, REMAP_P2C)
 
 
 def _dyn(env, auto):
@@ -265,14 +270,14 @@ class ResNet101Engine:
                         J = self._l1j                                            # layer1.0: the stem wrote x into J[:, width:]
                 y2buf = (lambda: J[:, :width]) if J is not None else (lambda: self.buf(btag + "y2", (Ro, width)))
                 if stride == 1:
-                    Rp = N * (h + 2) * (w + 2)
+                    Rp = N * (h + PADH) * (w + PADH)
                     y1 = self.buf(btag + "y1p", (Rp, width), zero=True)
-                    gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, remap=REMAP_C2P, img_hw=(h, w), debug_flags=ff)
+                    gemm(x, w1, y1, R, width, cin, scale=s1, bias=b1, relu=True, remap=C2P, img_hw=(h, w), debug_flags=ff)
                     y2 = y2buf()
-                    wp = w + 2
+                    wp = w + PADH
                     taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
                     gemm(y1, w2, y2, Rp, width, width, ntaps=9, a_off1=taps, b_off0=[t * width for t in range(9)],
-                         scale=s2, bias=b2, relu=True, remap=REMAP_P2C, img_hw=(h, w), debug_flags=ff)
+                         scale=s2, bias=b2, relu=True, remap=P2C, img_hw=(h, w), debug_flags=ff)
                 elif S2_IMPLICIT and not (keep and nk == N):
                     # stride-2 3x3 conv WITHOUT an im2col matrix: conv1 writes its rows space-to-depth (4 parity planes side by side,
                     # one-pixel zero halo on the top / left of every plane); tap (kh, kw) of the convolution then is the plane
@@ -341,7 +346,7 @@ class ResNet101Engine:
                 rec.update(y1=y1, y2=y2, out=out)
                 if keep:
                     if nk != N:      # differentiate the first nk frames only: row-prefix views of every saved activation
-                        pre = {"x": nk * h * w, "y1": nk * (h + 2) * (w + 2) if stride == 1 else nk * h * w, "y2": nk * ho * wo,
+                        pre = {"x": nk * h * w, "y1": nk * (h + PADH) * (w + PADH) if stride == 1 else nk * h * w, "y2": nk * ho * wo,
                                "out": nk * ho * wo, "col": nk * ho * wo, "xs": nk * ho * wo}
                         for key, rows in pre.items():
                             if key in rec:
@@ -396,17 +401,17 @@ class ResNet101Engine:
             with sc:
                 self._wgrad(g_out, y2, cout, width, Ro, s3, grads[prefix + name + "conv3.weight"])
             if r["stride"] == 1:
-                Rp = N * (h + 2) * (w + 2)
-                wp = w + 2
+                Rp = N * (h + PADH) * (w + PADH)
+                wp = w + PADH
                 taps = [(kh - 1) * wp + (kw - 1) for kh in range(3) for kw in range(3)]
                 g2 = self.buf(f"{tag}:g2p{par}", (Rp, width), zero=True)
-                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=REMAP_C2P, img_hw=(h, w), max_ctas=BWD_MAX_CTAS, debug_flags=bf)
+                gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, remap=C2P, img_hw=(h, w), max_ctas=BWD_MAX_CTAS, debug_flags=bf)
                 # ---- conv2 (implicit 3x3 over the haloed grid)
                 with sc:
                     self._wgrad(g2, y1, width, width, Rp, s2, grads[prefix + name + "conv2.weight"], z_b_off1=taps)
                 g1 = self.buf(f"{tag}:g1{par}", (R, width))
                 gemm(g2, w2s, g1, Rp, width, width, b_major=1, ntaps=9, a_off1=[-t for t in taps],
-                     b_off0=[t * width for t in range(9)], mask=y1, remap=REMAP_P2C, img_hw=(h, w), max_ctas=BWD_MAX_CTAS, debug_flags=bf)
+                     b_off0=[t * width for t in range(9)], mask=y1, remap=P2C, img_hw=(h, w), max_ctas=BWD_MAX_CTAS, debug_flags=bf)
             else:
                 g2 = self.buf(f"{tag}:g2c{par}", (Ro, width))
                 gemm(g_out, w3s, g2, Ro, width, cout, b_major=1, mask=y2, max_ctas=BWD_MAX_CTAS, debug_flags=bf)
