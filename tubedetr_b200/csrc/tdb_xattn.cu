@@ -513,6 +513,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
+constexpr int XR = 10;      // rows in flight per warp in the streaming passes (S = 141: 18 rows per warp = 2 iterations)
+
 __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) {
   pdl_wait();
   pdl_trigger();
@@ -545,15 +547,15 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
   const float* dpb = a.dpbar ? a.dpbar + (long long)f * S : nullptr;
   // ---- pass 1
   float rs = 0.f;
-  for (int j0 = warp; j0 < S; j0 += 32) {            // 4 rows of this warp per iteration: 4 independent 16-byte loads in flight
-    uint4 raw[4];
+  for (int j0 = warp; j0 < S; j0 += 8 * XR) {        // XR rows of this warp per iteration: XR independent 16-byte loads in flight
+    uint4 raw[XR];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < XR; ++u) {
       const int j = j0 + 8 * u;
       raw[u] = j < S ? __ldg(vrow + (long long)j * sv8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < XR; ++u) {
       const int j = j0 + 8 * u;
       if (j < S) {                                   // warp-uniform
         float vv[8];
@@ -579,6 +581,13 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
     }
   }
   if ((lane & 3) == 0) srs[warp * 8 + h] = rs;
+  // the key rows of pass 2's first iteration are requested BEFORE the barrier: their latency overlaps the row-sum exchange
+  uint4 kpre[XR];
+#pragma unroll
+  for (int u = 0; u < XR; ++u) {
+    const int j = warp + 8 * u;
+    kpre[u] = j < S ? __ldg(krow + (long long)j * sk8) : make_uint4(0, 0, 0, 0);
+  }
   __syncthreads();
   float rsum = 0.f;
 #pragma unroll
@@ -587,15 +596,15 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const XattnBwdParams a) 
   float dqa[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) dqa[t] = 0.f;
-  for (int j0 = warp; j0 < S; j0 += 32) {
-    uint4 raw[4];
+  for (int j0 = warp; j0 < S; j0 += 8 * XR) {
+    uint4 raw[XR];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < XR; ++u) {
       const int j = j0 + 8 * u;
-      raw[u] = j < S ? __ldg(krow + (long long)j * sk8) : make_uint4(0, 0, 0, 0);
+      raw[u] = j0 == warp ? kpre[u] : (j < S ? __ldg(krow + (long long)j * sk8) : make_uint4(0, 0, 0, 0));
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < XR; ++u) {
       const int j = j0 + 8 * u;
       if (j < S) {
         float kk[8];
@@ -662,16 +671,16 @@ __global__ void __launch_bounds__(256) xattn_core_fwd_kernel(const XattnCorePara
   const uint4* vrow = reinterpret_cast<const uint4*>(a.v + (long long)f * S * a.ldv) + lane;
   const long long sk8 = a.ldk / 8, sv8 = a.ldv / 8;
   const uint8_t* mk = a.kpm ? a.kpm + (long long)f * S : nullptr;
-  // ---- scores
-  for (int j0 = warp; j0 < S; j0 += 32) {
-    uint4 raw[4];
+  // ---- scores (XR rows of this warp per iteration = XR independent 16-byte loads in flight: the kernel is a latency chain)
+  for (int j0 = warp; j0 < S; j0 += 8 * XR) {
+    uint4 raw[XR];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < XR; ++u) {
       const int j = j0 + 8 * u;
       raw[u] = j < S ? __ldg(krow + (long long)j * sk8) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < XR; ++u) {
       const int j = j0 + 8 * u;
       if (j < S) {
         float kk[8];
@@ -684,6 +693,13 @@ __global__ void __launch_bounds__(256) xattn_core_fwd_kernel(const XattnCorePara
         if ((lane & 3) == 0) sp[h * S + j] = (mk && mk[j]) ? -INFINITY : d;
       }
     }
+  }
+  // the value rows of the context pass's first iteration are requested now: their latency overlaps the softmax
+  uint4 vpre[XR];
+#pragma unroll
+  for (int u = 0; u < XR; ++u) {
+    const int j = warp + 8 * u;
+    vpre[u] = j < S ? __ldg(vrow + (long long)j * sv8) : make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   // ---- softmax: warp = head
@@ -717,15 +733,15 @@ __global__ void __launch_bounds__(256) xattn_core_fwd_kernel(const XattnCorePara
   float oa[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) oa[t] = 0.f;
-  for (int j0 = warp; j0 < S; j0 += 32) {
-    uint4 raw[4];
+  for (int j0 = warp; j0 < S; j0 += 8 * XR) {
+    uint4 raw[XR];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < XR; ++u) {
       const int j = j0 + 8 * u;
-      raw[u] = j < S ? __ldg(vrow + (long long)j * sv8) : make_uint4(0, 0, 0, 0);
+      raw[u] = j0 == warp ? vpre[u] : (j < S ? __ldg(vrow + (long long)j * sv8) : make_uint4(0, 0, 0, 0));
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < XR; ++u) {
       const int j = j0 + 8 * u;
       if (j < S) {
         float vv[8];
